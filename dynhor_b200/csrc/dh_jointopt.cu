@@ -1,0 +1,838 @@
+// dh_jointopt.cu -- sm_100a kernels of the joint pose-optimisation hot path and their C-ABI entry points.
+//
+// One optimisation iteration (jointopt.py:144-160) is six stream-ordered kernels:
+//   k_pose_prep    6D rotation -> R (geometry.py:19-25); closed-form smoothness loss + gradient from mesh moments
+//   k_project      (|s| v) R + T  (camera.py:204-206) and the renderer's projection (camera.py:39-62) -> NDC
+//   k_setup_bin    fill_back + back-face cull + conservative bbox; faces binned to 16-row strips
+//   k_raster       one CTA per (frame, strip): 64-bit (depth, face) z-buffer in shared memory, then the fused
+//                  epilogue: face-index map, coverage bitmap, 2x2 pooling + flip, masked-L2 / IoU integer sums,
+//                  dL/drend map and its sign bitmaps (losses.py:66-78)
+//   k_backward     one CTA per (frame, face chunk): coverage / sign bitmaps staged in shared memory, per-face
+//                  edge-scan pseudo-gradient, projection + rigid-transform backward, CTA reduction to 13 numbers
+//   k_pose_update  per frame: + smoothness gradient, Gram-Schmidt backward, two-group Adam (jointopt.py:135-141)
+//   k_finalize     per-iteration loss / IoU sums -> history row, step counter, optional scale update
+// Compiled with --fmad=false: see dh_core.h for the fp32 contract.
+#include <string.h>
+
+#include <vector>
+
+#include "dh_common.h"
+#include "dh_core.h"
+
+namespace {
+
+using namespace dh;
+
+constexpr int kSH = 16;            // strip height in raster rows
+constexpr int kThreads = 256;      // CTA size of the raster / backward / elementwise kernels
+constexpr int kMaxIS = 512;        // largest raster resolution (bitmaps + z-buffer strip must fit shared memory)
+
+__host__ __device__ inline int raster_size(const dh_sil& s) { return s.aa ? 2 * s.S : s.S; }
+
+// ------------------------------------------------------------------------------------------------ small ops
+__global__ void k_rot6d_to_matrix(const float* __restrict__ rot6d, float* __restrict__ R, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float r6[6], Rm[9];
+    for (int i = 0; i < 6; i++) r6[i] = rot6d[6 * b + i];
+    rot6d_to_R(r6, Rm);
+    for (int i = 0; i < 9; i++) R[9 * b + i] = Rm[i];
+}
+
+__global__ void k_transform_verts(const float* __restrict__ verts, const float* __restrict__ R,
+                                  const float* __restrict__ T, const float* __restrict__ scale,
+                                  float* __restrict__ out, int V) {
+    const int b = blockIdx.y;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float Rm[9], Tm[3], vv[3], o[3];
+    for (int i = 0; i < 9; i++) Rm[i] = R[9 * b + i];
+    for (int i = 0; i < 3; i++) Tm[i] = T[3 * b + i];
+    for (int i = 0; i < 3; i++) vv[i] = verts[3 * v + i];
+    transform_vertex(vv, fabsf(scale[0]), Rm, Tm, o);
+    float* dst = out + ((size_t)b * V + v) * 3;
+    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+}
+
+__global__ void k_masks_prepare(const float* __restrict__ m, int8_t* __restrict__ tri,
+                                unsigned long long* __restrict__ keep_count, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int keep = 0;
+    for (; i < n; i += stride) {
+        const float v = m[i];
+        const int8_t t = (v > 0.0f) ? 1 : ((v >= 0.0f) ? 0 : -1);
+        tri[i] = t;
+        keep += (t >= 0);
+    }
+    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((threadIdx.x & 31) == 0 && keep) atomicAdd(keep_count, (unsigned long long)keep);
+}
+
+__global__ void k_mesh_moments(const float* __restrict__ verts, int V, double* __restrict__ out12) {
+    __shared__ double sm[kThreads / 32][12];
+    double a[12];
+    for (int i = 0; i < 12; i++) a[i] = 0.0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const double x[3] = {verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]};
+        for (int i = 0; i < 3; i++) {
+            a[i] += x[i];
+            for (int j = 0; j < 3; j++) a[3 + 3 * i + j] += x[i] * x[j];
+        }
+    }
+    for (int i = 0; i < 12; i++)
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 12; i++) sm[threadIdx.x >> 5][i] = a[i];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += sm[w][threadIdx.x];
+        out12[threadIdx.x] = s;
+    }
+}
+
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, float step_size, float bc2s) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    adam_update(&p[i], &m[i], &v[i], g[i], step_size, bc2s);
+}
+
+// ------------------------------------------------------------------------------------------------ projection
+// FROM_POSE: verts = canonical mesh [V,3], transformed by R[b], T[b], |s|.  else: verts = camera space [B,V,3].
+// Block (0, b) also clears the frame's bin counters and loss counters for this iteration.
+template <bool FROM_POSE>
+__global__ void __launch_bounds__(kThreads)
+k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const float* __restrict__ trans,
+          const float* __restrict__ scale, const float* __restrict__ K, float orig, float4* __restrict__ proj,
+          int V, int32_t* __restrict__ bin_count, int nstrips, int32_t* __restrict__ loss_counts) {
+    const int b = blockIdx.y;
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < nstrips) bin_count[b * nstrips + threadIdx.x] = 0;
+        if (loss_counts != nullptr && threadIdx.x < 4) loss_counts[b * 4 + threadIdx.x] = 0;
+    }
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float c[3];
+    if (FROM_POSE) {
+        float Rm[9], Tm[3], vv[3];
+        for (int i = 0; i < 9; i++) Rm[i] = Rmat[9 * b + i];
+        for (int i = 0; i < 3; i++) Tm[i] = trans[3 * b + i];
+        for (int i = 0; i < 3; i++) vv[i] = verts[3 * v + i];
+        transform_vertex(vv, fabsf(scale[0]), Rm, Tm, c);
+    } else {
+        const float* src = verts + ((size_t)b * V + v) * 3;
+        c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
+    }
+    float Km[6];
+    for (int i = 0; i < 6; i++) Km[i] = K[9 * b + i];
+    float u, w;
+    project_vertex(c, Km, orig, &u, &w);
+    proj[(size_t)b * V + v] = make_float4(u, w, c[2], 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ binning
+__global__ void __launch_bounds__(kThreads)
+k_setup_bin(const float4* __restrict__ proj, const int32_t* __restrict__ faces, int V, int F, int is,
+            int nstrips, int32_t* __restrict__ bin_count, int32_t* __restrict__ bins) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float4* P = proj + (size_t)b * V;
+    const float4 a0 = P[faces[3 * f + 0]], a1 = P[faces[3 * f + 1]], a2 = P[faces[3 * f + 2]];
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+        float x[3], y[3];
+        x[0] = w ? a2.x : a0.x; y[0] = w ? a2.y : a0.y;
+        x[1] = a1.x;            y[1] = a1.y;
+        x[2] = w ? a0.x : a2.x; y[2] = w ? a0.y : a2.y;
+        int xl, xh, yl, yh;
+        if (!face_bbox(x, y, is, &xl, &xh, &yl, &yh)) continue;
+        const int fn = f + w * F;
+        for (int s = yl / kSH; s <= yh / kSH; s++) {
+            const int slot = atomicAdd(&bin_count[b * nstrips + s], 1);
+            bins[((size_t)b * nstrips + s) * (size_t)(2 * F) + slot] = fn;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ rasteriser
+__device__ __forceinline__ void load_face(const float4* __restrict__ P, const int32_t* __restrict__ faces,
+                                          int fn, int F, FaceSetup& fs, int* ids) {
+    const int w = fn >= F;
+    const int f = w ? fn - F : fn;
+    const int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    ids[0] = w ? i2 : i0; ids[1] = i1; ids[2] = w ? i0 : i2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float4 p = P[ids[k]];
+        fs.x[k] = p.x; fs.y[k] = p.y; fs.z[k] = p.z;
+    }
+}
+
+// FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
+// else : epilogue writes the pooled, flipped silhouette `rend` (the renderer's return value).
+template <bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float* __restrict__ rend,
+         int32_t* __restrict__ loss_counts) {
+    extern __shared__ unsigned long long zbuf[];  // [kSH][is]
+    __shared__ uint32_t abits[kSH][kMaxIS / 32];
+    __shared__ int red[3][kThreads / 32];
+    const int is = raster_size(s);
+    const int nstrips = is / kSH;
+    const int strip = blockIdx.x, b = blockIdx.y;
+    const int row0 = strip * kSH;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    __syncthreads();
+
+    const int count = s.bin_count[b * nstrips + strip];
+    const int32_t* bin = s.bins + ((size_t)b * nstrips + strip) * (size_t)(2 * s.F);
+    const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
+    for (int e = tid; e < count; e += kThreads) {
+        const int fn = bin[e];
+        FaceSetup fs;
+        int ids[3];
+        load_face(P, s.faces, fn, s.F, fs, ids);
+        if (!face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) continue;
+        face_inverse(fs, is);
+        const int r_lo = max(fs.y_lo, row0), r_hi = min(fs.y_hi, row0 + kSH - 1);
+        for (int yi = r_lo; yi <= r_hi; yi++) {
+            const float yp = pix_to_ndc(yi, is);
+            unsigned long long* zrow = zbuf + (yi - row0) * is;
+            for (int xi = fs.x_lo; xi <= fs.x_hi; xi++) {
+                const float xp = pix_to_ndc(xi, is);
+                if (!pixel_inside(fs, xp, yp)) continue;
+                float zp;
+                if (!pixel_depth(fs, xi, yi, s.near_, s.far_, &zp)) continue;
+                const unsigned long long key = zkey(zp, fn);
+                if (key < zrow[xi]) atomicMin(&zrow[xi], key);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue 1: face index map + coverage bitmap (one warp = 32 consecutive pixels of a row)
+    const int wpr = is >> 5;
+    int32_t* fidx = s.fidx + (size_t)b * is * is + (size_t)row0 * is;
+    uint32_t* abits_g = s.alpha_bits + ((size_t)b * is + row0) * wpr;
+    for (int i = tid; i < kSH * is; i += kThreads) {
+        const unsigned long long key = zbuf[i];
+        const bool cov = key != DH_ZKEY_EMPTY;
+        fidx[i] = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
+        const uint32_t word = __ballot_sync(0xffffffffu, cov);
+        if ((tid & 31) == 0) {
+            const int r = i / is, w = (i % is) >> 5;
+            abits[r][w] = word;
+            abits_g[r * wpr + w] = word;
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue 2: output-resolution cells of this strip (2x2 average pool + vertical flip)
+    const int S = s.S;
+    const int cell_rows = s.aa ? kSH / 2 : kSH;
+    const int wprp = (S + 31) >> 5;
+    int sse = 0, inter = 0, uni = 0;
+    for (int ci = tid; ci < cell_rows * S; ci += kThreads) {
+        const int ly = ci / S, x = ci - ly * S;
+        int pop, yo;
+        if (s.aa) {
+            const int r = 2 * ly;
+            const uint32_t w0 = abits[r][x >> 4], w1 = abits[r + 1][x >> 4];
+            const int sh = (2 * x) & 31;
+            pop = __popc((w0 >> sh) & 3u) + __popc((w1 >> sh) & 3u);
+            yo = (is - 1 - (row0 + r)) >> 1;
+        } else {
+            pop = 4 * (int)((abits[ly][x >> 5] >> (x & 31)) & 1u);
+            yo = is - 1 - (row0 + ly);
+        }
+        const size_t o = ((size_t)b * S + yo) * S + x;
+        if (FUSED) {
+            const int m = mask_tri[o];
+            const int keep = m >= 0, ref = m > 0;
+            const int k = keep ? pop - 4 * ref : 0;  // 4 * (image - ref)
+            sse += k * k;
+            inter += ref ? pop : 0;
+            uni += 4 * ref + (keep ? pop : 0) - (ref ? pop : 0);
+            s.gpool[o] = gcoef * ((float)k * 0.5f);
+            const uint32_t pw = __ballot_sync(0xffffffffu, k > 0);
+            const uint32_t nw = __ballot_sync(0xffffffffu, k < 0);
+            if ((tid & 31) == 0) {
+                s.pos_pool[((size_t)b * S + yo) * wprp + (x >> 5)] = pw;
+                s.neg_pool[((size_t)b * S + yo) * wprp + (x >> 5)] = nw;
+            }
+        } else {
+            rend[o] = (float)pop * 0.25f;
+        }
+    }
+    if (FUSED) {
+        for (int o = 16; o > 0; o >>= 1) {
+            sse += __shfl_xor_sync(0xffffffffu, sse, o);
+            inter += __shfl_xor_sync(0xffffffffu, inter, o);
+            uni += __shfl_xor_sync(0xffffffffu, uni, o);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = sse; red[1][tid >> 5] = inter; red[2][tid >> 5] = uni; }
+        __syncthreads();
+        if (tid < 3) {
+            int t = 0;
+            for (int w = 0; w < kThreads / 32; w++) t += red[tid][w];
+            if (t) atomicAdd(&loss_counts[b * 4 + tid], t);
+        }
+    }
+}
+
+// sign bitmaps of a caller-provided dL/drend (API backward)
+__global__ void __launch_bounds__(kThreads)
+k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint32_t* __restrict__ neg_pool,
+             long long ncell) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float v = (i < ncell) ? g[i] : 0.0f;
+    const uint32_t pw = __ballot_sync(0xffffffffu, v > 0.0f);
+    const uint32_t nw = __ballot_sync(0xffffffffu, v < 0.0f);
+    if ((threadIdx.x & 31) == 0 && i < ncell) {
+        pos_pool[i >> 5] = pw;
+        neg_pool[i >> 5] = nw;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i -> bits 2i and 2i+1
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
+// FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
+// else : scatter dL/d(camera-space vertices) into grad_verts [B,V,3] (float atomics).
+template <bool FUSED>
+__global__ void __launch_bounds__(kThreads)
+k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
+           const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
+           float* __restrict__ grad_verts, int nchunks) {
+    extern __shared__ uint32_t smw[];
+    __shared__ float red[kThreads / 32][13];
+    const int is = raster_size(s), S = s.S;
+    const int wpr = is >> 5, wprp = (S + 31) >> 5;
+    uint32_t* s_alpha = smw;
+    uint32_t* s_neg = s_alpha + is * wpr;
+    uint32_t* s_negT = s_neg + is * wpr;
+    uint32_t* s_pos = s_negT + is * wpr;
+    const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+
+    const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
+    const uint32_t* gp = s.pos_pool + (size_t)b * S * wprp;
+    const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
+    for (int i = tid; i < is * wpr; i += kThreads) {
+        const uint32_t a = ga[i];
+        const int r = i / wpr, w = i - r * wpr;
+        const int rf = is - 1 - r;
+        uint32_t nb;
+        if (s.aa) {
+            const uint32_t pw = gn[(rf >> 1) * wprp + (w >> 1)];
+            nb = spread16((w & 1) ? (pw >> 16) : pw);
+        } else {
+            nb = gn[rf * wprp + w];
+        }
+        s_alpha[i] = a;
+        s_neg[i] = ~a & nb;
+    }
+    for (int i = tid; i < S * wprp; i += kThreads) s_pos[i] = gp[i];
+    __syncthreads();
+    {   // column-major copy of s_neg: 32x32 bit-block transposes through ballots
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int blk = warp; blk < wpr * wpr; blk += kThreads / 32) {
+            const int rb = blk / wpr, cb = blk - rb * wpr;
+            const uint32_t word = s_neg[(32 * rb + lane) * wpr + cb];
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
+                if (lane == j) mine = colw;
+            }
+            s_negT[(32 * cb + lane) * wpr + rb] = mine;
+        }
+    }
+    __syncthreads();
+
+    BwdMaps m;
+    m.alpha = s_alpha; m.neg = s_neg; m.negT = s_negT; m.pos_pool = s_pos;
+    m.gpool = s.gpool + (size_t)b * S * S;
+    m.fidx = s.fidx + (size_t)b * is * is;
+    m.is = is; m.S = S; m.aa = s.aa; m.wpr = wpr; m.wpr_pool = wprp;
+    m.gscale = s.aa ? 0.25f : 1.0f;
+
+    float Rm[9], Tm[3], Km[6], s_abs = 1.0f;
+    if (FUSED) {
+        for (int i = 0; i < 9; i++) Rm[i] = Rmat[9 * b + i];
+        for (int i = 0; i < 3; i++) Tm[i] = trans[3 * b + i];
+        s_abs = fabsf(scale[0]);
+    }
+    for (int i = 0; i < 6; i++) Km[i] = s.K[9 * b + i];
+    float acc[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++) acc[i] = 0.0f;
+
+    const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
+    const int per = (s.F + nchunks - 1) / nchunks;
+    const int f0 = chunk * per, f1 = min(s.F, f0 + per);
+    for (int f = f0 + tid; f < f1; f += kThreads) {
+        for (int w = 0; w < 2; w++) {
+            const int fn = f + w * s.F;
+            FaceSetup fs;
+            int ids[3];
+            load_face(P, s.faces, fn, s.F, fs, ids);
+            float g[6];
+            backward_face(fs.x, fs.y, fn, s.eps, m, g);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float gu = g[2 * k], gv = g[2 * k + 1];
+                if (gu == 0.0f && gv == 0.0f) continue;
+                float c[3], vo[3], gc[3];
+                if (FUSED) {
+                    for (int i = 0; i < 3; i++) vo[i] = verts_src[3 * ids[k] + i];
+                    transform_vertex(vo, s_abs, Rm, Tm, c);
+                } else {
+                    const float* src = verts_src + ((size_t)b * s.V + ids[k]) * 3;
+                    c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
+                }
+                project_vertex_backward(c, Km, s.orig_size, gu, gv, gc);
+                if (FUSED) {
+                    for (int j = 0; j < 3; j++) acc[j] += gc[j];
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++) acc[3 + 3 * i + j] += (s_abs * vo[i]) * gc[j];
+                    float dot = 0.0f;
+                    for (int j = 0; j < 3; j++)
+                        dot += (vo[0] * Rm[j] + vo[1] * Rm[3 + j] + vo[2] * Rm[6 + j]) * gc[j];
+                    acc[12] += dot;
+                } else {
+                    float* dst = grad_verts + ((size_t)b * s.V + ids[k]) * 3;
+                    atomicAdd(dst + 0, gc[0]);
+                    atomicAdd(dst + 1, gc[1]);
+                    atomicAdd(dst + 2, gc[2]);
+                }
+            }
+        }
+    }
+    if (FUSED) {
+#pragma unroll
+        for (int i = 0; i < 13; i++)
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if ((tid & 31) == 0)
+            for (int i = 0; i < 13; i++) red[tid >> 5][i] = acc[i];
+        __syncthreads();
+        if (tid < 16) {
+            float t = 0.0f;
+            if (tid < 13)
+                for (int w = 0; w < kThreads / 32; w++) t += red[w][tid];
+            partials[((size_t)b * nchunks + chunk) * 16 + tid] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pose kernels
+__global__ void k_pose_prep(const dh_jointopt p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = p.sil.B;
+    if (b >= B) return;
+    float r6[6], Rm[9];
+    for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
+    rot6d_to_R(r6, Rm);
+    for (int i = 0; i < 9; i++) p.Rmat[9 * b + i] = Rm[i];
+    smooth_terms_frame(b, B, p.rot6d, p.trans, p.halo_prev, p.halo_next, p.scale[0], p.moments, p.sil.V, p.B_total,
+                       p.lw_smooth, p.smooth_terms + (size_t)b * 16);
+}
+
+// mode 0: Adam update in place.  mode 1: write gradients to (grad_rot6d, grad_trans), leave parameters alone.
+// mode 2: per-frame loss terms only (forward-only evaluation; no backward ran, partials are not read).
+__global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__ grad_rot6d,
+                              float* __restrict__ grad_trans, int with_sil) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.sil.B) return;
+    double G[9], gT[3], gs = 0.0;
+    for (int i = 0; i < 9; i++) G[i] = 0.0;
+    for (int i = 0; i < 3; i++) gT[i] = 0.0;
+    if (with_sil && mode != 2) {
+        for (int c = 0; c < p.nchunks; c++) {
+            const float* q = p.partials + ((size_t)b * p.nchunks + c) * 16;
+            for (int i = 0; i < 3; i++) gT[i] += (double)q[i];
+            for (int i = 0; i < 9; i++) G[i] += (double)q[3 + i];
+            gs += (double)q[12];
+        }
+        gs *= (p.scale[0] < 0.0f) ? -1.0 : 1.0;
+    }
+    const double* st = p.smooth_terms + (size_t)b * 16;
+    for (int i = 0; i < 3; i++) gT[i] += st[i];
+    for (int i = 0; i < 9; i++) G[i] += st[3 + i];
+    gs += st[12];
+    float r6[6];
+    for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
+    double g6[6];
+    rot6d_backward(r6, G, g6);
+
+    double* ft = p.frame_terms + (size_t)b * 4;
+    const int32_t* lc = p.loss_counts + b * 4;
+    ft[0] = with_sil ? (double)lc[0] : 0.0;
+    ft[1] = with_sil ? (double)(((float)lc[1] * 0.25f) / ((float)lc[2] * 0.25f + 0.000001f)) : 0.0;
+    ft[2] = st[13];
+    ft[3] = gs;
+
+    if (mode == 2) return;
+    if (mode == 1) {
+        for (int i = 0; i < 6; i++) grad_rot6d[6 * b + i] = (float)g6[i];
+        for (int i = 0; i < 3; i++) grad_trans[3 * b + i] = (float)gT[i];
+        return;
+    }
+    const int t = *p.step + 1;
+    float step_rot, step_tr, bc2s;
+    adam_bias(t, p.lr * 10.0, &step_rot, &bc2s);
+    adam_bias(t, p.lr, &step_tr, &bc2s);
+    for (int i = 0; i < 6; i++)
+        adam_update(&p.rot6d[6 * b + i], &p.adam_m_rot[6 * b + i], &p.adam_v_rot[6 * b + i], (float)g6[i],
+                    step_rot, bc2s);
+    for (int i = 0; i < 3; i++)
+        adam_update(&p.trans[3 * b + i], &p.adam_m_trans[3 * b + i], &p.adam_v_trans[3 * b + i], (float)gT[i],
+                    step_tr, bc2s);
+}
+
+// One CTA.  mode 0: history row + scale update + step++.  mode 1: history row only (grad_scale written).
+// mode 2: history row only.
+__global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int mode, float* __restrict__ grad_scale) {
+    __shared__ double red[kThreads / 32][4];
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < p.sil.B; b += kThreads)
+        for (int i = 0; i < 4; i++) a[i] += p.frame_terms[(size_t)b * 4 + i];
+    for (int i = 0; i < 4; i++)
+        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 4; i++) red[threadIdx.x >> 5][i] = a[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < kThreads / 32; w++)
+            for (int i = 0; i < 4; i++) t[i] += red[w][i];
+        const int step = *p.step;
+        if (step < p.max_iters) {
+            double* h = p.hist + (size_t)step * 4;
+            const double N = (double)(p.B_total - 1) * (double)p.sil.V * 3.0;
+            h[0] = (p.B_total > 1) ? t[2] / N : 0.0;
+            h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
+            h[2] = t[1] / (double)p.B_total;
+            h[3] = t[3];
+        }
+        if (mode == 1 && grad_scale != nullptr) grad_scale[0] = (float)t[3];
+        if (mode == 0) {
+            if (p.optimize_scale) {
+                float step_sz, bc2s;
+                adam_bias(step + 1, p.lr, &step_sz, &bc2s);
+                adam_update(p.scale, &p.adam_mv_scale[0], &p.adam_mv_scale[1], (float)t[3], step_sz, bc2s);
+            }
+            *p.step = step + 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int check_sil(const dh_sil* s) {
+    DH_REQUIRE(s != nullptr, "dh_sil is NULL");
+    DH_REQUIRE(s->B > 0 && s->V > 0 && s->F > 0 && s->S > 0, "B, V, F, S must be positive");
+    const int is = raster_size(*s);
+    if (s->S % 32 != 0 || is > kMaxIS)
+        return fail(DH_ERR_UNSUPPORTED, "S=%d aa=%d: S must be a multiple of 32 and S*(aa?2:1) <= %d", s->S, s->aa,
+                    kMaxIS);
+    DH_REQUIRE(s->faces && s->K && s->proj && s->bin_count && s->bins && s->fidx && s->alpha_bits && s->pos_pool &&
+                   s->neg_pool, "dh_sil has a NULL buffer");
+    DH_REQUIRE(s->B <= 65535, "B > 65535 frames per call (grid.y limit); shard the sequence");
+    return DH_OK;
+}
+
+size_t bwd_smem_bytes(const dh_sil& s) {
+    const int is = raster_size(s);
+    return (size_t)(3 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
+}
+
+template <typename KernelT>
+int set_smem(KernelT kernel, size_t bytes) {
+    if (bytes > 48 * 1024) DH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return DH_OK;
+}
+
+int launch_forward_common(const dh_sil& s, cudaStream_t st) {
+    const int is = raster_size(s);
+    dim3 gb((s.F + kThreads - 1) / kThreads, s.B);
+    k_setup_bin<<<gb, kThreads, 0, st>>>(reinterpret_cast<const float4*>(s.proj), s.faces, s.V, s.F, is, is / kSH,
+                                         s.bin_count, s.bins);
+    DH_LAUNCH_OK("k_setup_bin");
+    return DH_OK;
+}
+
+int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
+                     cudaStream_t st) {
+    const dh_sil& s = p.sil;
+    const int is = raster_size(s), nstrips = is / kSH, B = s.B;
+    const bool with_sil = p.lw_sil > 0.0;
+    k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
+    DH_LAUNCH_OK("k_pose_prep");
+    if (with_sil) {
+        dim3 gv((s.V + kThreads - 1) / kThreads, B);
+        k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
+                                                  reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
+                                                  p.loss_counts);
+        DH_LAUNCH_OK("k_project");
+        int rc = launch_forward_common(s, st);
+        if (rc) return rc;
+        const size_t zb = (size_t)kSH * is * sizeof(unsigned long long);
+        rc = set_smem(k_raster<true>, zb);
+        if (rc) return rc;
+        // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
+        const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
+        k_raster<true><<<dim3(nstrips, B), kThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
+        DH_LAUNCH_OK("k_raster");
+        if (mode != 2) {
+            const size_t sb = bwd_smem_bytes(s);
+            rc = set_smem(k_backward<true>, sb);
+            if (rc) return rc;
+            k_backward<true><<<dim3(p.nchunks, B), kThreads, sb, st>>>(s, p.verts_og, p.Rmat, p.trans, p.scale,
+                                                                        p.partials, nullptr, p.nchunks);
+            DH_LAUNCH_OK("k_backward");
+        }
+    }
+    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0);
+    DH_LAUNCH_OK("k_pose_update");
+    k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
+    DH_LAUNCH_OK("k_finalize");
+    return DH_OK;
+}
+
+int check_plan(const dh_jointopt* p) {
+    DH_REQUIRE(p != nullptr, "dh_jointopt is NULL");
+    int rc = check_sil(&p->sil);
+    if (rc) return rc;
+    DH_REQUIRE(p->sil.gpool != nullptr, "sil.gpool is NULL");
+    DH_REQUIRE(p->verts_og && p->mask_tri && p->rot6d && p->trans && p->scale && p->step && p->hist && p->moments,
+               "dh_jointopt has a NULL parameter/state pointer");
+    DH_REQUIRE(p->adam_m_rot && p->adam_v_rot && p->adam_m_trans && p->adam_v_trans && p->adam_mv_scale,
+               "dh_jointopt has a NULL Adam state pointer");
+    DH_REQUIRE(p->Rmat && p->smooth_terms && p->loss_counts && p->partials && p->frame_terms,
+               "dh_jointopt has a NULL scratch pointer");
+    DH_REQUIRE(p->nchunks >= 1 && p->nchunks <= 64, "nchunks must be in [1,64]");
+    DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
+    DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
+    return DH_OK;
+}
+
+struct GraphEntry {
+    dh_jointopt plan;
+    cudaGraphExec_t exec;
+};
+std::vector<GraphEntry>& graph_cache() {
+    static std::vector<GraphEntry> c;
+    return c;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out8) {
+    DH_REQUIRE(out8 != nullptr && B > 0 && V > 0 && F > 0 && S > 0, "bad arguments");
+    const int64_t is = aa ? 2 * S : S;
+    const int64_t nstrips = (is + kSH - 1) / kSH, wprp = (S + 31) / 32;
+    out8[0] = (int64_t)B * V * 4 * 4;
+    out8[1] = (int64_t)B * nstrips * 4;
+    out8[2] = (int64_t)B * nstrips * 2 * F * 4;
+    out8[3] = (int64_t)B * is * is * 4;
+    out8[4] = (int64_t)B * is * (is / 32) * 4;
+    out8[5] = (int64_t)B * S * wprp * 4;
+    out8[6] = out8[5];
+    out8[7] = (int64_t)B * S * S * 4;
+    return DH_OK;
+}
+
+int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* stream) {
+    int rc = check_sil(s);
+    if (rc) return rc;
+    DH_REQUIRE(verts_cam && rend, "NULL verts_cam / rend");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int is = raster_size(*s), nstrips = is / kSH;
+    dim3 gv((s->V + kThreads - 1) / kThreads, s->B);
+    k_project<false><<<gv, kThreads, 0, st>>>(verts_cam, nullptr, nullptr, nullptr, s->K, s->orig_size,
+                                               reinterpret_cast<float4*>(s->proj), s->V, s->bin_count, nstrips,
+                                               nullptr);
+    DH_LAUNCH_OK("k_project");
+    rc = launch_forward_common(*s, st);
+    if (rc) return rc;
+    const size_t zb = (size_t)kSH * is * sizeof(unsigned long long);
+    rc = set_smem(k_raster<false>, zb);
+    if (rc) return rc;
+    k_raster<false><<<dim3(nstrips, s->B), kThreads, zb, st>>>(*s, nullptr, 0.0f, rend, nullptr);
+    DH_LAUNCH_OK("k_raster");
+    return DH_OK;
+}
+
+int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_rend, float* grad_verts,
+                    void* stream) {
+    int rc = check_sil(s);
+    if (rc) return rc;
+    DH_REQUIRE(verts_cam && grad_rend && grad_verts, "NULL verts_cam / grad_rend / grad_verts");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long ncell = (long long)s->B * s->S * s->S;
+    DH_CUDA(cudaMemsetAsync(grad_verts, 0, (size_t)s->B * s->V * 3 * sizeof(float), st));
+    k_grad_signs<<<(unsigned)((ncell + kThreads - 1) / kThreads), kThreads, 0, st>>>(grad_rend, s->pos_pool,
+                                                                                     s->neg_pool, ncell);
+    DH_LAUNCH_OK("k_grad_signs");
+    dh_sil t = *s;
+    t.gpool = const_cast<float*>(grad_rend);
+    const size_t sb = bwd_smem_bytes(t);
+    rc = set_smem(k_backward<false>, sb);
+    if (rc) return rc;
+    const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
+    k_backward<false><<<dim3(nchunks, s->B), kThreads, sb, st>>>(t, verts_cam, nullptr, nullptr, nullptr, nullptr,
+                                                                  grad_verts, nchunks);
+    DH_LAUNCH_OK("k_backward");
+    return DH_OK;
+}
+
+int dh_rot6d_to_matrix(const float* rot6d, float* R, int32_t B, void* stream) {
+    DH_REQUIRE(rot6d && R && B > 0, "bad arguments");
+    k_rot6d_to_matrix<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rot6d, R, B);
+    DH_LAUNCH_OK("k_rot6d_to_matrix");
+    return DH_OK;
+}
+
+int dh_transform_verts(const float* verts, const float* R, const float* T, const float* scale, float* out,
+                       int32_t B, int32_t V, void* stream) {
+    DH_REQUIRE(verts && R && T && scale && out && B > 0 && V > 0 && B <= 65535, "bad arguments");
+    k_transform_verts<<<dim3((V + kThreads - 1) / kThreads, B), kThreads, 0, (cudaStream_t)stream>>>(verts, R, T,
+                                                                                                     scale, out, V);
+    DH_LAUNCH_OK("k_transform_verts");
+    return DH_OK;
+}
+
+int dh_masks_prepare(const float* target_masks, int8_t* tri, unsigned long long* keep_count, int64_t n,
+                     void* stream) {
+    DH_REQUIRE(target_masks && tri && keep_count && n > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DH_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(unsigned long long), st));
+    long long blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_masks_prepare<<<(unsigned)blocks, kThreads, 0, st>>>(target_masks, tri, keep_count, (long long)n);
+    DH_LAUNCH_OK("k_masks_prepare");
+    return DH_OK;
+}
+
+int dh_mesh_moments(const float* verts, int32_t V, double* out12, void* stream) {
+    DH_REQUIRE(verts && out12 && V > 0, "bad arguments");
+    k_mesh_moments<<<1, kThreads, 0, (cudaStream_t)stream>>>(verts, V, out12);
+    DH_LAUNCH_OK("k_mesh_moments");
+    return DH_OK;
+}
+
+int dh_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, double lr, int32_t t,
+                 void* stream) {
+    DH_REQUIRE(param && grad && m && v && n > 0 && t >= 1, "bad arguments");
+    float step_size, bc2s;
+    adam_bias(t, lr, &step_size, &bc2s);
+    k_adam<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(param, grad, m, v,
+                                                                                           (long long)n, step_size,
+                                                                                           bc2s);
+    DH_LAUNCH_OK("k_adam");
+    return DH_OK;
+}
+
+int dh_jointopt_scratch_bytes(int32_t B, int32_t nchunks, int64_t* out5) {
+    DH_REQUIRE(out5 != nullptr && B > 0 && nchunks > 0, "bad arguments");
+    out5[0] = (int64_t)B * 9 * 4;
+    out5[1] = (int64_t)B * 16 * 8;
+    out5[2] = (int64_t)B * 4 * 4;
+    out5[3] = (int64_t)B * nchunks * 16 * 4;
+    out5[4] = (int64_t)B * 4 * 8;
+    return DH_OK;
+}
+
+int dh_jointopt_default_chunks(int32_t B, int32_t F) {
+    (void)B;
+    int c = (F + 4 * kThreads - 1) / (4 * kThreads);  // ~4 faces per thread
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    return c;
+}
+
+int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(n_iters >= 0, "n_iters < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!use_graph) {
+        for (int it = 0; it < n_iters; it++) {
+            rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, st);
+            if (rc) return rc;
+        }
+        return DH_OK;
+    }
+    cudaGraphExec_t exec = nullptr;
+    for (auto& e : graph_cache())
+        if (memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0) exec = e.exec;
+    if (exec == nullptr) {
+        // warm the function attributes outside capture
+        rc = set_smem(k_raster<true>, (size_t)kSH * raster_size(p->sil) * sizeof(unsigned long long));
+        if (rc) return rc;
+        rc = set_smem(k_backward<true>, bwd_smem_bytes(p->sil));
+        if (rc) return rc;
+        cudaStream_t cs;
+        DH_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        DH_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            return rc ? rc : fail(DH_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        if (ce != cudaSuccess) return fail(DH_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        GraphEntry e;
+        memcpy(&e.plan, p, sizeof(dh_jointopt));
+        e.exec = exec;
+        graph_cache().push_back(e);
+    }
+    for (int it = 0; it < n_iters; it++) DH_CUDA(cudaGraphLaunch(exec, st));
+    return DH_OK;
+}
+
+int dh_jointopt_eval(const dh_jointopt* p, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    return launch_iteration(*p, 2, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans, float* grad_scale, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(grad_rot6d && grad_trans, "NULL gradient outputs");
+    return launch_iteration(*p, 1, grad_rot6d, grad_trans, grad_scale, (cudaStream_t)stream);
+}
+
+int dh_jointopt_release(const dh_jointopt* p) {
+    auto& c = graph_cache();
+    for (size_t i = 0; i < c.size();) {
+        if (p == nullptr || memcmp(&c[i].plan, p, sizeof(dh_jointopt)) == 0) {
+            cudaGraphExecDestroy(c[i].exec);
+            c.erase(c.begin() + i);
+        } else {
+            i++;
+        }
+    }
+    return DH_OK;
+}
+
+}  // extern "C"

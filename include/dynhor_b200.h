@@ -1,0 +1,161 @@
+/*
+ * dynhor_b200.h -- C ABI of libdynhor_b200.so (hand-written sm_100a kernels for Dynhor/ObjTracker's joint
+ * pose-optimisation hot path and DINO template matching).
+ *
+ * Conventions:
+ *   - every entry point returns 0 on success, a negative dh_status on failure; dh_last_error() gives the
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host; the caller (PyTorch) owns every
+ *     buffer, including scratch; sizes are given by the dh_*_bytes helpers / documented shapes.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host synchronisation unless
+ *     stated.  One host thread per GPU.
+ *   - "fn" numbers faces after the renderer's fill_back doubling: fn in [0,F) = faces as given,
+ *     fn in [F,2F) = the same faces with reversed winding.
+ *
+ * The reference has no FFI of its own (pure Python, SURVEY.md section 8b "Reference's own plugin API: none");
+ * each entry point cites the Python interface it replaces, relative to /root/reference/ObjTracker.
+ * The ctypes binding a maintainer would add is dynhor_b200/_lib.py.
+ */
+#ifndef DYNHOR_B200_H
+#define DYNHOR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dh_status {
+    DH_OK = 0,
+    DH_ERR_INVALID = -1,   /* bad argument (shape / flag / null pointer)        */
+    DH_ERR_CUDA = -2,      /* a CUDA runtime call or kernel launch failed        */
+    DH_ERR_UNSUPPORTED = -3, /* valid request outside what the kernels implement */
+    DH_ERR_NO_DEVICE = -4  /* no sm_100 device                                   */
+} dh_status;
+
+int dh_version(void);
+const char* dh_last_error(void);
+/* sm count, compute capability of the current device */
+int dh_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Silhouette renderer state.  Replaces nr.renderer.Renderer(image_size=S, K, R=I, t=0, orig_size,
+ * anti_aliasing)(verts, faces, mode="silhouettes")   utils/losses.py:36-40,68;
+ * pose_initializtion.py:98-105,146-147,160.
+ * Raster resolution is = S*2 if aa else S; `is` must be a multiple of 32 and <= 512.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dh_sil {
+    int32_t B, V, F, S, aa;           /* frames, vertices, faces (before fill_back), output size, anti-aliasing */
+    float near_, far_, eps, orig_size; /* renderer near/far planes, backward eps (1e-4), projection orig_size   */
+    const int32_t* faces;              /* [F,3]   shared by all frames (run.py:158 stacks identical copies)      */
+    const float* K;                    /* [B,3,3] ROI intrinsics in unit-image coordinates                       */
+    /* scratch, caller-allocated (sizes from dh_sil_scratch_bytes, in this order) */
+    float* proj;                       /* [B,V,4]  NDC u, v, depth z, pad                                        */
+    int32_t* bin_count;                /* [B,nstrips]                                                            */
+    int32_t* bins;                     /* [B,nstrips,2F]                                                         */
+    int32_t* fidx;                     /* [B,is,is] face index map (-1 none), rasteriser row order               */
+    uint32_t* alpha_bits;              /* [B,is,is/32] coverage bitmap, rasteriser row order                     */
+    uint32_t* pos_pool;                /* [B,S,ceil(S/32)] bitmap: dL/drend > 0                                  */
+    uint32_t* neg_pool;                /* [B,S,ceil(S/32)] bitmap: dL/drend < 0                                  */
+    float* gpool;                      /* [B,S,S] dL/drend (fused path writes it; API path copies grad_rend in)  */
+} dh_sil;
+
+/* bytes of each scratch array, out[8] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,
+ * neg_pool, gpool) */
+int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out8);
+
+/* rend[B,S,S] = silhouettes of camera-space vertices verts_cam[B,V,3]  (forward of the renderer call). */
+int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* stream);
+/* grad_verts[B,V,3] (overwritten) = pseudo-gradient of sum(grad_rend * rend) w.r.t. verts_cam; must follow a
+ * dh_sil_forward on the same state (uses its fidx / alpha_bits).   autograd of utils/losses.py:68. */
+int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_rend, float* grad_verts,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small geometry ops (drop-in pieces of utils/geometry.py and utils/camera.py).
+ * ------------------------------------------------------------------------------------------------ */
+/* utils/geometry.py:7-25  rot6d [B,3,2] -> R [B,3,3] (columns b1,b2,b3) */
+int dh_rot6d_to_matrix(const float* rot6d, float* R, int32_t B, void* stream);
+/* utils/camera.py:179-207  out[B,V,3] = (|scale| * verts[V,3]) @ R[B] + T[B] */
+int dh_transform_verts(const float* verts, const float* R, const float* T, const float* scale, float* out,
+                       int32_t B, int32_t V, void* stream);
+/* target masks f32 [B,S,S] in {-1,0,1} -> tri-state int8 + number of keep (>=0) pixels (device uint64) */
+int dh_masks_prepare(const float* target_masks, int8_t* tri, unsigned long long* keep_count, int64_t n,
+                     void* stream);
+/* mesh moments in double: out[0..2] = sum v, out[3..11] = sum v v^T (row-major) */
+int dh_mesh_moments(const float* verts, int32_t V, double* out12, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused joint optimisation:  jointopt.py:144-160 (zero_grad, forward, weighting, backward, Adam step)
+ * for the local frame range of one GPU.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dh_jointopt {
+    dh_sil sil;                    /* renderer state; sil.K, sil.faces as above                                 */
+    const float* verts_og;         /* [V,3] canonical mesh                     jointopt.py:39                   */
+    const int8_t* mask_tri;        /* [B,S,S] {-1 occluder, 0 background, 1 object}   jointopt.py:50-53         */
+    float* rot6d;                  /* [B,3,2] parameters, updated in place     jointopt.py:37-38                */
+    float* trans;                  /* [B,1,3] parameters, updated in place     jointopt.py:30-31                */
+    float* scale;                  /* [1]     int_scales_object                jointopt.py:40-48                */
+    float* adam_m_rot; float* adam_v_rot;      /* [B,6] each */
+    float* adam_m_trans; float* adam_v_trans;  /* [B,3] each */
+    float* adam_mv_scale;          /* [2] */
+    int32_t* step;                 /* [1] device iteration counter (0 before the first step)                   */
+    double* hist;                  /* [max_iters,4] per-iteration partial sums of this rank:                     */
+                                   /*   loss_smooth_obj, loss_sil_obj, iou_object, (unused)                      */
+    int32_t max_iters;
+    /* neighbours' boundary poses for the smoothness term (frame-range sharding) */
+    const float* halo_prev;        /* [9] rot6d(6)+trans(3) of global frame first-1, or NULL at the start        */
+    const float* halo_next;        /* [9] of global frame last+1, or NULL at the end                            */
+    int32_t B_total;               /* frames in the whole sequence (all ranks)                                  */
+    double keep_sum;               /* sum over ALL ranks of keep-mask pixels      utils/losses.py:71             */
+    double lw_sil, lw_smooth;      /* loss weights, 0 disables a term             jointopt.py:81,86,147-150      */
+    double lr;                     /* translations/scale lr; rotations use 10*lr  jointopt.py:135-141            */
+    int32_t optimize_scale;        /* jointopt.py:42-46                                                         */
+    const double* moments;         /* [12] from dh_mesh_moments                                                  */
+    /* scratch */
+    float* Rmat;                   /* [B,9]                                                                      */
+    double* smooth_terms;          /* [B,16]: gT(3) gR(9) gs(1) pair_sse(1) pad(2)                               */
+    int32_t* loss_counts;          /* [B,4]: 16*SSE, 4*inter, 4*union, pad                                       */
+    float* partials;               /* [B,nchunks,16] per-CTA pose-gradient partial sums                          */
+    double* frame_terms;           /* [B,4]: 16*SSE, iou, pair_sse, scale-grad                                   */
+    int32_t nchunks;
+} dh_jointopt;
+
+/* bytes of the dh_jointopt scratch arrays: out[5] = Rmat, smooth_terms, loss_counts, partials, frame_terms */
+int dh_jointopt_scratch_bytes(int32_t B, int32_t nchunks, int64_t* out5);
+/* recommended number of face chunks per frame for the backward kernel */
+int dh_jointopt_default_chunks(int32_t B, int32_t F);
+/* run n_iters fused iterations on `stream` (no host sync).  use_graph != 0: capture one iteration into a CUDA
+ * graph (cached per plan address) and replay it. */
+int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, void* stream);
+/* forward only: losses of the current parameters into hist[*step] without touching parameters or step. */
+int dh_jointopt_eval(const dh_jointopt* p, void* stream);
+/* gradients of the weighted loss w.r.t. rot6d [B,6] and trans [B,3] (and scale [1]) for the current
+ * parameters, without an optimiser step (parity tests; also the backward of Joint_Optimizer.forward). */
+int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans, float* grad_scale, void* stream);
+/* drop cached graphs */
+int dh_jointopt_release(const dh_jointopt* p);
+
+/* torch.optim.Adam single step on a flat fp32 tensor (jointopt.py:135-141,160), t = 1-based step number */
+int dh_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, double lr, int32_t t,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DINO template matching:  pose_initializtion.py:295-296 (aligned-patch masked cosine) + :299,309
+ * (argmax / topk).  Inputs are pre-scaled bf16 banks so that score[n,f] = <templ[n,:], frames[f,:]>:
+ *   templ [N,Kdim]  = r[n,p,:] / |r[n,p,:]|
+ *   frames[Fm,Kdim] = m_f[p] * g[f,p,:] / |g[f,p,:]| / sum_p m_f[p]          (Kdim = P*D)
+ * Output: scores fp32 [Fm,N] (optional, may be NULL), top-k values [Fm,k] and indices [Fm,k] (largest first,
+ * lowest index first on exact ties).
+ * ------------------------------------------------------------------------------------------------ */
+int dh_dino_workspace_bytes(int32_t N, int32_t Fm, int64_t Kdim, int64_t* bytes);
+int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int32_t Fm, int64_t Kdim, int32_t k,
+                 float* scores, float* topk_vals, int32_t* topk_idx, void* workspace, int64_t workspace_bytes,
+                 void* stream);
+/* builds the pre-scaled bf16 banks from fp32 features [n,P,D] (+ optional mask [n,P], NULL = all ones) */
+int dh_dino_prescale(const float* feats, const float* mask, int32_t n, int32_t P, int32_t D, void* out_bf16,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNHOR_B200_H */

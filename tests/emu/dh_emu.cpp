@@ -1,0 +1,252 @@
+// tests/emu/dh_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host build of dynhor_b200/csrc/dh_core.h (the per-face / per-pixel arithmetic the CUDA kernels call), driven by
+// serial loops that mirror the kernels' glue (strip binning, shared-memory z-buffer, bitmap staging).  The CPU
+// test-suite (-m "not gpu") compares it with the oracle so that logic errors are caught without a GPU.
+// The product never loads this library; the GPU tests exercise the real kernels through the C ABI.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../dynhor_b200/csrc/dh_core.h"
+
+using namespace dh;
+
+static const int kSH = 16;
+
+static uint32_t spread16(uint32_t x) {
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+
+static void load_face(const float* P, const int32_t* faces, int fn, int F, FaceSetup& fs, int* ids) {
+    const int w = fn >= F;
+    const int f = w ? fn - F : fn;
+    const int i0 = faces[3 * f + 0], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+    ids[0] = w ? i2 : i0; ids[1] = i1; ids[2] = w ? i0 : i2;
+    for (int k = 0; k < 3; k++) {
+        fs.x[k] = P[4 * ids[k] + 0];
+        fs.y[k] = P[4 * ids[k] + 1];
+        fs.z[k] = P[4 * ids[k] + 2];
+    }
+}
+
+extern "C" {
+
+void emu_rot6d_to_R(const float* r6, float* R, int B) {
+    for (int b = 0; b < B; b++) rot6d_to_R(r6 + 6 * b, R + 9 * b);
+}
+
+void emu_rot6d_backward(const float* r6, const double* G, double* g6, int B) {
+    for (int b = 0; b < B; b++) rot6d_backward(r6 + 6 * b, G + 9 * b, g6 + 6 * b);
+}
+
+// proj [B,V,4] from the canonical mesh and poses (k_project<true>)
+void emu_project_pose(const float* verts_og, int V, const float* Rmat, const float* trans, float s_abs,
+                      const float* K, float orig, int B, float* proj, float* verts_cam) {
+    for (int b = 0; b < B; b++)
+        for (int v = 0; v < V; v++) {
+            float c[3], u, w;
+            transform_vertex(verts_og + 3 * v, s_abs, Rmat + 9 * b, trans + 3 * b, c);
+            project_vertex(c, K + 9 * b, orig, &u, &w);
+            float* o = proj + ((size_t)b * V + v) * 4;
+            o[0] = u; o[1] = w; o[2] = c[2]; o[3] = 0.f;
+            if (verts_cam) memcpy(verts_cam + ((size_t)b * V + v) * 3, c, 12);
+        }
+}
+
+// proj [B,V,4] from camera-space vertices (k_project<false>)
+void emu_project_cam(const float* verts_cam, int V, const float* K, float orig, int B, float* proj) {
+    for (int b = 0; b < B; b++)
+        for (int v = 0; v < V; v++) {
+            const float* c = verts_cam + ((size_t)b * V + v) * 3;
+            float u, w;
+            project_vertex(c, K + 9 * b, orig, &u, &w);
+            float* o = proj + ((size_t)b * V + v) * 4;
+            o[0] = u; o[1] = w; o[2] = c[2]; o[3] = 0.f;
+        }
+}
+
+// k_setup_bin + k_raster (epilogue 1): fidx [B,is,is], alpha_bits [B,is,is/32]
+void emu_raster(const float* proj, const int32_t* faces, int B, int V, int F, int is, float near, float far,
+                int32_t* fidx, uint32_t* alpha_bits) {
+    const int nstrips = is / kSH, wpr = is / 32;
+    for (int b = 0; b < B; b++) {
+        const float* P = proj + (size_t)b * V * 4;
+        std::vector<std::vector<int>> bins(nstrips);
+        for (int f = 0; f < F; f++)
+            for (int w = 0; w < 2; w++) {
+                FaceSetup fs;
+                int ids[3];
+                load_face(P, faces, f + w * F, F, fs, ids);
+                int xl, xh, yl, yh;
+                if (!face_bbox(fs.x, fs.y, is, &xl, &xh, &yl, &yh)) continue;
+                for (int s = yl / kSH; s <= yh / kSH; s++) bins[s].push_back(f + w * F);
+            }
+        for (int strip = 0; strip < nstrips; strip++) {
+            const int row0 = strip * kSH;
+            std::vector<unsigned long long> zbuf((size_t)kSH * is, DH_ZKEY_EMPTY);
+            // reversed order on purpose: the result must not depend on the order of bin entries
+            for (int e = (int)bins[strip].size() - 1; e >= 0; e--) {
+                const int fn = bins[strip][e];
+                FaceSetup fs;
+                int ids[3];
+                load_face(P, faces, fn, F, fs, ids);
+                if (!face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) continue;
+                face_inverse(fs, is);
+                const int r_lo = fs.y_lo > row0 ? fs.y_lo : row0;
+                const int r_hi = fs.y_hi < row0 + kSH - 1 ? fs.y_hi : row0 + kSH - 1;
+                for (int yi = r_lo; yi <= r_hi; yi++) {
+                    const float yp = pix_to_ndc(yi, is);
+                    for (int xi = fs.x_lo; xi <= fs.x_hi; xi++) {
+                        const float xp = pix_to_ndc(xi, is);
+                        if (!pixel_inside(fs, xp, yp)) continue;
+                        float zp;
+                        if (!pixel_depth(fs, xi, yi, near, far, &zp)) continue;
+                        const unsigned long long key = zkey(zp, fn);
+                        unsigned long long& cell = zbuf[(size_t)(yi - row0) * is + xi];
+                        if (key < cell) cell = key;
+                    }
+                }
+            }
+            for (int i = 0; i < kSH * is; i++) {
+                const unsigned long long key = zbuf[i];
+                const bool cov = key != DH_ZKEY_EMPTY;
+                const int r = row0 + i / is, c = i % is;
+                fidx[((size_t)b * is + r) * is + c] = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
+                uint32_t& word = alpha_bits[((size_t)b * is + r) * wpr + (c >> 5)];
+                if ((c & 31) == 0) word = 0;
+                if (cov) word |= 1u << (c & 31);
+            }
+        }
+    }
+}
+
+// k_raster<true> epilogue 2 for whole frames: integer loss sums, dL/drend and its sign bitmaps
+void emu_loss_epilogue(const uint32_t* alpha_bits, const int8_t* mask_tri, int B, int S, int aa, float gcoef,
+                       int32_t* loss_counts, float* gpool, uint32_t* pos_pool, uint32_t* neg_pool, float* rend) {
+    const int is = aa ? 2 * S : S, wpr = is / 32, wprp = (S + 31) / 32;
+    for (int b = 0; b < B; b++) {
+        int sse = 0, inter = 0, uni = 0;
+        for (int yo = 0; yo < S; yo++)
+            for (int x = 0; x < S; x++) {
+                int pop;
+                if (aa) {
+                    const int r1 = is - 1 - 2 * yo, r0 = r1 - 1;
+                    const uint32_t w0 = alpha_bits[((size_t)b * is + r0) * wpr + (x >> 4)];
+                    const uint32_t w1 = alpha_bits[((size_t)b * is + r1) * wpr + (x >> 4)];
+                    const int sh = (2 * x) & 31;
+                    pop = __builtin_popcount((w0 >> sh) & 3u) + __builtin_popcount((w1 >> sh) & 3u);
+                } else {
+                    const int r = is - 1 - yo;
+                    pop = 4 * (int)((alpha_bits[((size_t)b * is + r) * wpr + (x >> 5)] >> (x & 31)) & 1u);
+                }
+                const size_t o = ((size_t)b * S + yo) * S + x;
+                if (rend) rend[o] = (float)pop * 0.25f;
+                if (!mask_tri) continue;
+                const int m = mask_tri[o];
+                const int keep = m >= 0, ref = m > 0;
+                const int k = keep ? pop - 4 * ref : 0;
+                sse += k * k;
+                inter += ref ? pop : 0;
+                uni += 4 * ref + (keep ? pop : 0) - (ref ? pop : 0);
+                gpool[o] = gcoef * ((float)k * 0.5f);
+                uint32_t& pw = pos_pool[((size_t)b * S + yo) * wprp + (x >> 5)];
+                uint32_t& nw = neg_pool[((size_t)b * S + yo) * wprp + (x >> 5)];
+                if ((x & 31) == 0) { pw = 0; nw = 0; }
+                if (k > 0) pw |= 1u << (x & 31);
+                if (k < 0) nw |= 1u << (x & 31);
+            }
+        if (loss_counts) {
+            loss_counts[4 * b + 0] = sse;
+            loss_counts[4 * b + 1] = inter;
+            loss_counts[4 * b + 2] = uni;
+            loss_counts[4 * b + 3] = 0;
+        }
+    }
+}
+
+// k_grad_signs
+void emu_grad_signs(const float* g, long long ncell, uint32_t* pos_pool, uint32_t* neg_pool) {
+    for (long long i = 0; i < ncell; i++) {
+        if ((i & 31) == 0) { pos_pool[i >> 5] = 0; neg_pool[i >> 5] = 0; }
+        if (g[i] > 0.f) pos_pool[i >> 5] |= 1u << (i & 31);
+        if (g[i] < 0.f) neg_pool[i >> 5] |= 1u << (i & 31);
+    }
+}
+
+// k_backward: grad_faces [B,2F,3,2] (NDC x,y gradient of every face vertex) and, when verts_cam != NULL,
+// the scattered camera-space vertex gradient grad_verts [B,V,3].
+void emu_backward(const float* proj, const int32_t* faces, const int32_t* fidx, const uint32_t* alpha_bits,
+                  const float* gpool, const uint32_t* pos_pool, const uint32_t* neg_pool, int B, int V, int F, int S,
+                  int aa, float eps, float* grad_faces, const float* verts_cam, const float* K, float orig,
+                  float* grad_verts) {
+    const int is = aa ? 2 * S : S, wpr = is / 32, wprp = (S + 31) / 32;
+    if (grad_verts) memset(grad_verts, 0, sizeof(float) * (size_t)B * V * 3);
+    for (int b = 0; b < B; b++) {
+        std::vector<uint32_t> s_alpha((size_t)is * wpr), s_neg((size_t)is * wpr), s_negT((size_t)is * wpr, 0u);
+        const uint32_t* ga = alpha_bits + (size_t)b * is * wpr;
+        const uint32_t* gn = neg_pool + (size_t)b * S * wprp;
+        for (int i = 0; i < is * wpr; i++) {
+            const uint32_t a = ga[i];
+            const int r = i / wpr, w = i - r * wpr;
+            const int rf = is - 1 - r;
+            uint32_t nb;
+            if (aa) {
+                const uint32_t pw = gn[(rf >> 1) * wprp + (w >> 1)];
+                nb = spread16((w & 1) ? (pw >> 16) : pw);
+            } else {
+                nb = gn[rf * wprp + w];
+            }
+            s_alpha[i] = a;
+            s_neg[i] = ~a & nb;
+        }
+        for (int r = 0; r < is; r++)
+            for (int c = 0; c < is; c++)
+                if ((s_neg[(size_t)r * wpr + (c >> 5)] >> (c & 31)) & 1u) s_negT[(size_t)c * wpr + (r >> 5)] |= 1u << (r & 31);
+        BwdMaps m;
+        m.alpha = s_alpha.data(); m.neg = s_neg.data(); m.negT = s_negT.data();
+        m.pos_pool = pos_pool + (size_t)b * S * wprp;
+        m.gpool = gpool + (size_t)b * S * S;
+        m.fidx = fidx + (size_t)b * is * is;
+        m.is = is; m.S = S; m.aa = aa; m.wpr = wpr; m.wpr_pool = wprp;
+        m.gscale = aa ? 0.25f : 1.0f;
+        const float* P = proj + (size_t)b * V * 4;
+        for (int fn = 0; fn < 2 * F; fn++) {
+            FaceSetup fs;
+            int ids[3];
+            load_face(P, faces, fn, F, fs, ids);
+            float g[6];
+            backward_face(fs.x, fs.y, fn, eps, m, g);
+            memcpy(grad_faces + ((size_t)b * 2 * F + fn) * 6, g, sizeof(g));
+            if (!grad_verts) continue;
+            for (int k = 0; k < 3; k++) {
+                if (g[2 * k] == 0.f && g[2 * k + 1] == 0.f) continue;
+                float gc[3];
+                project_vertex_backward(verts_cam + ((size_t)b * V + ids[k]) * 3, K + 9 * b, orig, g[2 * k],
+                                        g[2 * k + 1], gc);
+                for (int j = 0; j < 3; j++) grad_verts[((size_t)b * V + ids[k]) * 3 + j] += gc[j];
+            }
+        }
+    }
+}
+
+// k_pose_prep: st [B,16]
+void emu_smooth_terms(const float* rot6d, const float* trans, const float* halo_prev, const float* halo_next,
+                      float scale, const double* moments, int V, int B, int B_total, double lw_smooth, double* st) {
+    for (int b = 0; b < B; b++)
+        smooth_terms_frame(b, B, rot6d, trans, halo_prev, halo_next, scale, moments, V, B_total, lw_smooth,
+                           st + (size_t)16 * b);
+}
+
+void emu_adam(float* p, const float* g, float* m, float* v, long long n, double lr, int t) {
+    float step_size, bc2s;
+    adam_bias(t, lr, &step_size, &bc2s);
+    for (long long i = 0; i < n; i++) adam_update(&p[i], &m[i], &v[i], g[i], step_size, bc2s);
+}
+
+}  // extern "C"
