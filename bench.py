@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- joint pose-optimisation throughput (frame-iterations / second) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-gpu F]
+
+A "step" is one fused optimisation iteration (forward + backward + Adam, jointopt.py:144-160) over every frame
+of the sequence.  Workload at N=1 = BASELINE.json configs[1]: custom_shoes-shaped joint optimisation, 300 frames
+of a 480x640 sequence, 5k-vertex mesh (V=5002, F=10000), 256x256 ROIs rendered at 512x512 with anti-aliasing,
+loss weights of configs/custom_shoes.yaml.  N>1: weak scaling, 300 frames per GPU, frame-range sharding with a
+one-frame pose halo exchange per iteration (no other data-path collective).
+
+One JSON line on stdout (rank 0).  `--impl reference` times the CPU oracle (the restatement of the reference's
+CPU-incapable path) on the host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+LW = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}   # configs/custom_shoes.yaml:17-18
+LR = 1e-4                                         # configs/custom_shoes.yaml:15
+MESH = "uv50x100"                                 # V=5002, F=10000 ("5k-vertex mesh")
+H, W, S = 480, 640, 256
+METRIC = "jointopt frame-iters/sec (fwd+bwd+Adam)"
+UNIT = "frame-iters/s"
+
+
+def algorithmic_bytes_per_frame(V, S=256):
+    """SURVEY.md 8(d) kernel-boundary model, per frame-iteration, split by kernel (fp32, u8 coverage, i32 index)."""
+    SS = 2 * S
+    return {
+        "project": 12 * V,                          # writes projected vertices
+        "raster": 12 * V + 5 * SS * SS + SS * SS + 8 * S * S,  # raster fwd + the loss kernel fused into it
+        "backward": 5 * SS * SS + 8 * S * S + 12 * V + 12 * V,
+        "pose_update": 12 * V + 288,
+        "total": 60 * V + 11 * SS * SS + 16 * S * S + 288,
+    }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- data
+def gpu_render_fn(vc, faces, K, size):
+    from dynhor_b200.renderer import Renderer
+    B = len(vc)
+    r = Renderer(image_size=size, K=torch.from_numpy(K).cuda(), R=torch.eye(3)[None].cuda(),
+                 t=torch.zeros(1, 3).cuda(), orig_size=1, anti_aliasing=False)
+    with torch.no_grad():
+        return r(torch.from_numpy(vc).cuda(), torch.from_numpy(faces).cuda()[None].repeat(B, 1, 1),
+                 mode="silhouettes").cpu().numpy()
+
+
+def oracle_render_fn(vc, faces, K, size):
+    from oracle import nr_oracle
+    B = len(vc)
+    r = nr_oracle.Renderer(image_size=size, K=torch.from_numpy(K), R=torch.eye(3)[None], t=torch.zeros(1, 3),
+                           orig_size=1, anti_aliasing=False)
+    return r(torch.from_numpy(vc), torch.from_numpy(faces)[None].repeat(B, 1, 1), mode="silhouettes").numpy()
+
+
+def build_model(seq):
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import Joint_Optimizer
+    params = synth.to_object_parameters(seq)
+    B = len(params)
+    return Joint_Optimizer(
+        translations_object=torch.cat([p["translations"] for p in params]),
+        rotations_object=torch.cat([p["rotations"] for p in params]),
+        verts_object_og=torch.from_numpy(seq["verts"]),
+        faces_object=torch.from_numpy(seq["faces"]),
+        camintr_rois_object=torch.cat([p["K_roi"][:, 0] for p in params]),
+        target_masks_object=torch.cat([p["target_masks"] for p in params]),
+        int_scale_init=1, optimize_object_scale=False)
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_baseline(frames=None, iters=1):
+    """The CPU oracle (kind "port": the reference cannot run on CPU) on a bounded sample of
+    the same workload: `frames` custom_shoes-shaped frames x `iters` full iterations, all host threads."""
+    from dynhor_b200 import synth
+    from oracle import jointopt_oracle as jo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    frames = frames or max(2, min(cores, 64))
+    seq = synth.make_sequence(frames, H, W, mesh=MESH, seed=0, render_fn=oracle_render_fn, period=300)
+    orc = jo.JointOptOracle(seq["rot6d_init"], seq["T_init"], seq["verts"], seq["faces"], seq["K_roi"],
+                            seq["target_masks"], lr=LR)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        orc.step(LW)
+    dt = time.perf_counter() - t0
+    return {"value": frames * iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{frames} frames x {iters} iteration(s) of the N=1 workload (5k-vertex mesh, 512x512 AA "
+                      f"raster), {dt:.1f} s of CPU work, OpenMP + torch threads = {cores}"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    cores = os.cpu_count() or 1
+    frames = max(2, min(cores // 2, 32))
+    cb_rows = []
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(frames=2, iters=1)
+    t_total = 0.0
+    for _ in range(steps):
+        cb, dt = cpu_baseline(frames=frames, iters=1)
+        cb_rows.append(cb)
+        t_total += dt
+    value = frames * steps / t_total
+    cb = dict(cb_rows[-1])
+    cb["value"] = value
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * t_total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "custom_shoes-shaped joint optimisation (BASELINE configs[1] frame shape): "
+                               f"{frames}-frame bounded sample per step, 480x640, 5k-vertex mesh, 256x256 ROI at "
+                               "512x512 AA; CPU oracle port of the reference path (reference itself is CUDA-only)",
+                   "frames_per_step": frames},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import FusedJointOpt, joint_optimize
+    from dynhor_b200.sharding import FrameShard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    Bl = args.frames_per_gpu
+    B_total = Bl * world
+    shard = FrameShard(rank, world, B_total)
+    seq = synth.make_sequence(Bl, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=B_total,
+                              frame_offset=shard.start)
+    V, F = len(seq["verts"]), len(seq["faces"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K fused iterations, inputs already in HBM
+    model = build_model(seq)
+    fused = FusedJointOpt(model, LW, LR, args.steps + args.warmup + 64, shard=shard)
+    fused.run(args.warmup, use_graph=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fused.run(args.steps, use_graph=True)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = B_total * args.steps / (ms / 1000.0)
+    hist = fused.history()
+
+    # ---- per-kernel times (CUDA events on the launch stream) -> roofline of the dominant kernel
+    prof = fused.profile(5)
+    fused.release()
+    ab = algorithmic_bytes_per_frame(V, S)
+    top = max(("project", "raster", "backward", "pose_update"), key=lambda k: prof[k])
+    peak, peak_kind = measured_peaks()
+    achieved = ab[top] * Bl / (prof[top] / 1000.0) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath)).get(top)
+            traffic = t["dram_bytes_per_frame"] * Bl if t else None
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_kind} hbm_gbs",
+                "algorithmic_bytes_per_launch": ab[top] * Bl, "kernel_ms": prof[top],
+                "kernel_ms_all": prof,
+                "whole_step": {"algorithmic_bytes": ab["total"] * Bl,
+                               "achieved": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9,
+                               "frac": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9 / peak}}
+
+    # ---- end to end through the public call with HOST buffers (H2D of inputs, D2H of results inside the timing)
+    full = seq if world == 1 else None
+    if world > 1:
+        # every rank holds the full-sequence host inputs, like run.py would; masks of other ranks are rebuilt
+        # from the all-gathered local masks
+        m_local = torch.from_numpy(seq["target_masks"]).cuda()
+        ms_all = [torch.empty_like(m_local) for _ in range(world)]
+        dist.all_gather(ms_all, m_local)
+        full = synth.make_sequence(B_total, H, W, mesh=MESH, seed=0, render_fn=None, period=B_total)
+        full["target_masks"] = torch.cat(ms_all).cpu().numpy()
+    params = synth.to_object_parameters(full)
+    for p in params:
+        for k in ("rotations", "translations", "K_roi", "target_masks"):
+            p[k] = p[k].pin_memory()
+    faces_b = np.stack([full["faces"]] * B_total)
+    e2e_iters = args.steps
+    h2d = sum(p[k].numel() * p[k].element_size() for p in params[shard.start:shard.stop]
+              for k in ("rotations", "translations", "K_roi", "target_masks"))
+    h2d += full["verts"].nbytes + faces_b.nbytes
+    joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=LW, num_iterations=2, lr=LR)
+    barrier()
+    t0 = time.perf_counter()
+    model2, evo = joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=LW,
+                                 num_iterations=e2e_iters, lr=LR, board=None)
+    rot_h = model2.rotations_object.detach().cpu()
+    tr_h = model2.translations_object.detach().cpu()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    d2h = rot_h.numel() * 4 + tr_h.numel() * 4 + 4 * 8 * e2e_iters
+    dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt = float(dt_t.item())
+    e2e = {"value": B_total * e2e_iters / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
+           "d2h_bytes_per_step": d2h / e2e_iters, "iterations": e2e_iters, "seconds": dt,
+           "final_loss": evo["loss"][-1]}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"custom_shoes-shaped joint pose optimisation, {Bl} frames per GPU "
+                                   f"({B_total} total) 480x640, 5k-vertex mesh (V={V}, F={F}), 256x256 ROI rendered "
+                                   "512x512 + 2x2 pool, lw_sil 1 / lw_smooth 10, lr 1e-4 (BASELINE configs[1])",
+                       "frames_per_gpu": Bl, "frames_total": B_total, "parallelism": f"frame-shard x{world}",
+                       "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
+                             "no explicit flush", "cuda_graph": True},
+            "roofline": roofline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": 7 * args.steps,
+            "loss_first_last": [hist["loss"][0], hist["loss"][-1]],
+            "iou_first_last": [hist["iou_object"][0], hist["iou_object"][-1]],
+        }
+        if cb is not None:
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)     # configs/custom_shoes.yaml:14 joint_num_iterations
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=300)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,11 +57,13 @@ DH_HD void rot6d_to_R(const float* r6, float* R) {
     const float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
     const float d = (b1[0] * a2[0] + b1[1] * a2[1]) + b1[2] * a2[2];
     const float u2[3] = {a2[0] - d * b1[0], a2[1] - d * b1[1], a2[2] - d * b1[2]};
-    float n2 = sqrtf((u2[0] * u2[0] + u2[1] * u2[1]) + u2[2] * u2[2]);
+    // torch's CPU kernels (the oracle): the norm of the contiguous u2 is an FMA chain, the norm of the strided
+    // a1 above is not; cross is fma(a, b, -(c * d)).  Mirrored so that R is bit-identical to the oracle's.
+    float n2 = sqrtf(fmaf(u2[2], u2[2], fmaf(u2[1], u2[1], u2[0] * u2[0])));
     n2 = fmaxf(n2, 1e-12f);
     const float b2[3] = {u2[0] / n2, u2[1] / n2, u2[2] / n2};
-    const float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2],
-                         b1[0] * b2[1] - b1[1] * b2[0]};
+    const float b3[3] = {fmaf(b1[1], b2[2], -(b1[2] * b2[1])), fmaf(b1[2], b2[0], -(b1[0] * b2[2])),
+                         fmaf(b1[0], b2[1], -(b1[1] * b2[0]))};
     for (int i = 0; i < 3; i++) {
         R[3 * i + 0] = b1[i];
         R[3 * i + 1] = b2[i];
@@ -121,7 +123,8 @@ DH_HD void rot6d_backward(const float* r6, const double* G, double* g6) {
     }
 }
 
-// (|s| v) @ R + T, the k-ordered FMA chain of a K=3 matmul (matches torch CPU matmul bit for bit).
+// (|s| v) @ R + T, the k-ordered FMA chain of a K=3 matmul.  Matches torch's CPU bmm (the oracle) bit for bit
+// for meshes of more than 44 vertices (below that torch takes a non-FMA small-matrix path).
 DH_HD void transform_vertex(const float* v, float s_abs, const float* R, const float* T, float* out) {
     const float s0 = s_abs * v[0], s1 = s_abs * v[1], s2 = s_abs * v[2];
     for (int j = 0; j < 3; j++) {

@@ -571,21 +571,29 @@ int launch_forward_common(const dh_sil& s, cudaStream_t st) {
     return DH_OK;
 }
 
+// Optional per-kernel timing: 8 events bracket the 7 kernels of one iteration (dh_jointopt_profile).
+struct IterEvents { cudaEvent_t ev[8]; };
+#define DH_REC(i) do { if (evs) cudaEventRecord(evs->ev[i], st); } while (0)
+
 int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
-                     cudaStream_t st) {
+                     cudaStream_t st, IterEvents* evs = nullptr) {
     const dh_sil& s = p.sil;
     const int is = raster_size(s), nstrips = is / kSH, B = s.B;
     const bool with_sil = p.lw_sil > 0.0;
+    DH_REC(0);
     k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
     DH_LAUNCH_OK("k_pose_prep");
+    DH_REC(1);
     if (with_sil) {
         dim3 gv((s.V + kThreads - 1) / kThreads, B);
         k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
                                                   reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
                                                   p.loss_counts);
         DH_LAUNCH_OK("k_project");
+        DH_REC(2);
         int rc = launch_forward_common(s, st);
         if (rc) return rc;
+        DH_REC(3);
         const size_t zb = (size_t)kSH * is * sizeof(unsigned long long);
         rc = set_smem(k_raster<true>, zb);
         if (rc) return rc;
@@ -593,6 +601,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
         k_raster<true><<<dim3(nstrips, B), kThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
         DH_LAUNCH_OK("k_raster");
+        DH_REC(4);
         if (mode != 2) {
             const size_t sb = bwd_smem_bytes(s);
             rc = set_smem(k_backward<true>, sb);
@@ -601,11 +610,16 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
                                                                         p.partials, nullptr, p.nchunks);
             DH_LAUNCH_OK("k_backward");
         }
+    } else {
+        DH_REC(2); DH_REC(3); DH_REC(4);
     }
+    DH_REC(5);
     k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0);
     DH_LAUNCH_OK("k_pose_update");
+    DH_REC(6);
     k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
     DH_LAUNCH_OK("k_finalize");
+    DH_REC(7);
     return DH_OK;
 }
 
@@ -820,6 +834,29 @@ int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans
     if (rc) return rc;
     DH_REQUIRE(grad_rot6d && grad_trans, "NULL gradient outputs");
     return launch_iteration(*p, 1, grad_rot6d, grad_trans, grad_scale, (cudaStream_t)stream);
+}
+
+int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_host, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(n_iters > 0 && ms_out_host != nullptr, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    IterEvents evs;
+    for (int i = 0; i < 8; i++) DH_CUDA(cudaEventCreate(&evs.ev[i]));
+    for (int i = 0; i < 7; i++) ms_out_host[i] = 0.0f;
+    for (int it = 0; it < n_iters; it++) {
+        rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, st, &evs);
+        if (rc) break;
+        cudaError_t e = cudaEventSynchronize(evs.ev[7]);
+        if (e != cudaSuccess) { rc = fail(DH_ERR_CUDA, "profile sync: %s", cudaGetErrorString(e)); break; }
+        for (int i = 0; i < 7; i++) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, evs.ev[i], evs.ev[i + 1]);
+            ms_out_host[i] += ms / (float)n_iters;
+        }
+    }
+    for (int i = 0; i < 8; i++) cudaEventDestroy(evs.ev[i]);
+    return rc;
 }
 
 int dh_jointopt_release(const dh_jointopt* p) {

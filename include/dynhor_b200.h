@@ -132,6 +132,9 @@ int dh_jointopt_eval(const dh_jointopt* p, void* stream);
 /* gradients of the weighted loss w.r.t. rot6d [B,6] and trans [B,3] (and scale [1]) for the current
  * parameters, without an optimiser step (parity tests; also the backward of Joint_Optimizer.forward). */
 int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans, float* grad_scale, void* stream);
+/* run n_iters iterations eagerly with CUDA events around each of the 7 kernels; ms_out_host[7] (HOST memory) =
+ * average milliseconds of pose_prep, project, setup_bin, raster, backward, pose_update, finalize.  Synchronises. */
+int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_host, void* stream);
 /* drop cached graphs */
 int dh_jointopt_release(const dh_jointopt* p);
 

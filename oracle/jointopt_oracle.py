@@ -109,9 +109,9 @@ class JointOptOracle:
         loss_dict, metric_dict = self.forward(loss_weights)
         loss = sum(loss_dict[k] * loss_weights[k.replace("loss", "lw")] for k in loss_dict)
         loss.backward()
-        out = {k: float(v) for k, v in loss_dict.items()}
+        out = {k: float(v.detach()) for k, v in loss_dict.items()}
         out.update(metric_dict)
-        out["loss"] = float(loss)
+        out["loss"] = float(loss.detach())
         g = {"rot6d": self.rotations_object.grad.detach().clone().numpy(),
              "trans": self.translations_object.grad.detach().clone().numpy()}
         if self.optimize_object_scale:

@@ -142,7 +142,7 @@ def geometry_case(ref):
     rot6d = torch.randn(7, 3, 2, generator=g)
     R = ref_geometry.rot6d_to_matrix(rot6d)
     assert torch.equal(R, jointopt_oracle.rot6d_to_matrix(rot6d))
-    verts = torch.randn(7, 33, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 1.7])
+    verts = torch.randn(7, 64, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 1.7])
     K = torch.eye(3)[None].repeat(7, 1, 1)
     K[:, 0, 0] = 1.9 + torch.rand(7, generator=g)
     K[:, 1, 1] = 2.1 + torch.rand(7, generator=g)

@@ -1,0 +1,352 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against
+  (a) the golden vectors produced by the reference's own Python + the CPU oracle (tests/golden),
+  (b) the CPU oracle on seeded inputs at reference-sized meshes,
+  (c) size-independent properties (determinism, graph == eager, frame sharding == single shard).
+Bars (BASELINE.json north_star): coverage masks / face ownership bit-exact, losses 1e-4 relative, pose gradients
+1e-3 relative per iteration.  /root/reference is never read here."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (GOLDEN, JOINT_CASES, golden_alpha, load_golden, object_parameters_from_golden, rel_err,
+                     unpack_alpha)
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4   # north_star: loss values within 1e-4 relative error
+GRAD_RTOL = 1e-3   # north_star: pose gradients within 1e-3 relative error
+
+
+def _model_from_golden(g):
+    from dynhor_b200.jointopt import Joint_Optimizer
+    params = object_parameters_from_golden(g)
+    B = len(params)
+    faces = torch.from_numpy(np.stack([g["faces"].astype(np.int64)] * B))
+    model = Joint_Optimizer(
+        translations_object=torch.cat([p["translations"] for p in params]),
+        rotations_object=torch.cat([p["rotations"] for p in params]),
+        verts_object_og=torch.from_numpy(g["verts"]), faces_object=faces,
+        camintr_rois_object=torch.cat([p["K_roi"][:, 0] for p in params]),
+        target_masks_object=torch.cat([p["target_masks"] for p in params]),
+        int_scale_init=1, optimize_object_scale=bool(g["scale_opt"]))
+    return model
+
+
+def _lw(g):
+    return {"lw_sil_obj": float(g["lw_sil_obj"]), "lw_smooth_obj": float(g["lw_smooth_obj"])}
+
+
+def test_native_library_is_loaded():
+    from dynhor_b200 import _lib
+    lib = _lib.load()
+    sm, maj, mi = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.dh_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mi)) == 0
+    assert maj.value >= 10 and sm.value > 0
+    assert any("libdynhor_b200.so" in line for line in open("/proc/self/maps"))
+
+
+def test_geometry_ops_bit_exact():
+    from dynhor_b200.camera import compute_transformation_persp
+    from dynhor_b200.geometry import rot6d_to_matrix
+    g = np.load(os.path.join(GOLDEN, "geometry.npz"))
+    R = rot6d_to_matrix(torch.from_numpy(g["rot6d"]).cuda())
+    assert np.array_equal(R.cpu().numpy(), g["R"])
+    vt = compute_transformation_persp(torch.from_numpy(g["verts"][0]).cuda(), torch.from_numpy(g["T"]).cuda(),
+                                      torch.from_numpy(g["R"]).cuda(), (torch.ones(1) * 1.3).cuda())
+    assert np.array_equal(vt.cpu().numpy(), g["verts_t"])
+
+
+@pytest.mark.parametrize("name", JOINT_CASES)
+def test_renderer_forward_bit_exact_vs_golden(name):
+    """Renderer call (losses.py:68): silhouettes, coverage and face ownership identical to the reference run."""
+    g = load_golden(name)
+    model = _model_from_golden(g)
+    with torch.no_grad():
+        verts = model.get_verts_object()
+        rend = model.losses.sil_renderer(verts, model.faces_object, mode="silhouettes")
+    assert np.array_equal(rend.cpu().numpy(), g["ref_rend0"])
+    st = model.losses.sil_renderer._state
+    assert np.array_equal(st.face_index_map().cpu().numpy(), g["orc_face_index0"])
+    assert np.array_equal(unpack_alpha(st.coverage_bits().cpu().numpy()), golden_alpha(g))
+
+
+@pytest.mark.parametrize("name", JOINT_CASES)
+def test_fused_losses_and_gradients_vs_golden(name):
+    from dynhor_b200.jointopt import FusedJointOpt
+    g = load_golden(name)
+    model = _model_from_golden(g)
+    fused = FusedJointOpt(model, _lw(g), float(g["lr"]), 4)
+    ev = fused.evaluate()
+    assert abs(ev["loss_sil_obj"][0] - g["ref_loss_sil"][0]) <= LOSS_RTOL * g["ref_loss_sil"][0]
+    assert abs(ev["loss_smooth_obj"][0] - g["ref_loss_smooth"][0]) <= LOSS_RTOL * g["ref_loss_smooth"][0]
+    assert abs(ev["loss"][0] - g["ref_loss"][0]) <= LOSS_RTOL * g["ref_loss"][0]
+    assert abs(ev["iou_object"][0] - g["ref_iou"][0]) <= 1e-6
+    g_rot, g_tr, g_s = fused.grads()
+    assert rel_err(g_rot.cpu().numpy(), g["ref_grad_rot6d"]) < GRAD_RTOL
+    assert rel_err(g_tr.cpu().numpy(), g["ref_grad_trans"]) < GRAD_RTOL
+    # per-frame bars as well (each frame's 6+3 numbers)
+    for b in range(len(g["ref_grad_rot6d"])):
+        assert rel_err(g_rot[b].cpu().numpy(), g["ref_grad_rot6d"][b]) < GRAD_RTOL
+        assert rel_err(g_tr[b].cpu().numpy(), g["ref_grad_trans"][b]) < GRAD_RTOL
+    if int(g["scale_opt"]):
+        assert abs(float(g_s) - float(g["ref_grad_scale"][0])) < GRAD_RTOL * abs(float(g["ref_grad_scale"][0]))
+    # the fused forward wrote the same maps as the reference run
+    assert np.array_equal(fused.sil.face_index_map().cpu().numpy(), g["orc_face_index0"])
+
+
+@pytest.mark.parametrize("name", JOINT_CASES)
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_joint_optimize_matches_reference_run(name, use_graph):
+    """The drop-in call (jointopt.py:93-161): loss curves, IoU and final poses of the whole loop."""
+    from dynhor_b200.jointopt import joint_optimize
+    g = load_golden(name)
+    params = object_parameters_from_golden(g)
+    B = len(params)
+
+    class Board:
+        def __init__(self):
+            self.rows = []
+
+        def add_scalar(self, k, v, step):
+            self.rows.append((k, v, step))
+
+    board = Board()
+    model, evo = joint_optimize(params, objvertices=g["verts"], objfaces=np.stack([g["faces"].astype(np.int64)] * B),
+                                loss_weights=_lw(g), num_iterations=int(g["iters"]), lr=float(g["lr"]), board=board,
+                                optimize_object_scale=bool(g["scale_opt"]), use_graph=use_graph)
+    assert list(evo.keys()) == ["loss_smooth_obj", "loss_sil_obj", "iou_object", "loss"]
+    assert all(isinstance(v, float) for v in evo["loss"]) and len(evo["loss"]) == int(g["iters"])
+    assert np.allclose(evo["loss"], g["ref_loss"], rtol=LOSS_RTOL, atol=0)
+    assert np.allclose(evo["loss_sil_obj"], g["ref_loss_sil"], rtol=LOSS_RTOL, atol=0)
+    assert np.allclose(evo["loss_smooth_obj"], g["ref_loss_smooth"], rtol=LOSS_RTOL, atol=0)
+    assert np.allclose(evo["iou_object"], g["ref_iou"], rtol=0, atol=1e-5)
+    lr = float(g["lr"])
+    assert np.abs(model.rotations_object.detach().cpu().numpy() - g["ref_final_rot6d"]).max() < 0.05 * 10 * lr
+    assert np.abs(model.translations_object.detach().cpu().numpy() - g["ref_final_trans"]).max() < 0.05 * lr
+    if int(g["scale_opt"]):
+        assert abs(float(model.int_scales_object) - float(g["ref_final_scale"][0])) < 0.05 * lr
+    assert len(board.rows) == 2 * int(g["iters"])
+    assert model.rotations_object.shape == (B, 3, 2) and model.translations_object.shape == (B, 1, 3)
+
+
+@pytest.mark.parametrize("name", ["s64_b5", "s128_b6_lr"])
+def test_autograd_path_with_torch_adam_matches_reference_run(name):
+    """Joint_Optimizer.forward + loss.backward() + torch.optim.Adam, exactly the reference loop
+    (jointopt.py:125-160), on the CUDA renderer's autograd.Function."""
+    g = load_golden(name)
+    model = _model_from_golden(g)
+    lw, lr = _lw(g), float(g["lr"])
+    rigid = [v for k, v in model.named_parameters() if "rotation" not in k]
+    rot = [v for k, v in model.named_parameters() if "rotation" in k]
+    opt = torch.optim.Adam([{"params": rigid, "lr": lr}, {"params": rot, "lr": lr * 10}])
+    losses, ious = [], []
+    for step in range(int(g["iters"])):
+        opt.zero_grad()
+        loss_dict, metric_dict = model(loss_weights=lw)
+        loss = sum(loss_dict[k] * lw[k.replace("loss", "lw")] for k in loss_dict)
+        if step == 0:
+            loss.backward(retain_graph=False)
+            assert rel_err(model.rotations_object.grad.cpu().numpy(), g["ref_grad_rot6d"]) < GRAD_RTOL
+            assert rel_err(model.translations_object.grad.cpu().numpy(), g["ref_grad_trans"]) < GRAD_RTOL
+        else:
+            loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        ious.append(metric_dict["iou_object"])
+    assert np.allclose(losses, g["ref_loss"], rtol=LOSS_RTOL)
+    assert np.allclose(ious, g["ref_iou"], atol=1e-5)
+    assert np.abs(model.rotations_object.detach().cpu().numpy() - g["ref_final_rot6d"]).max() < 0.05 * 10 * lr
+
+
+def _oracle_render_fn(vc, faces, K, size):
+    from oracle import nr_oracle
+    B = len(vc)
+    r = nr_oracle.Renderer(image_size=size, K=torch.from_numpy(K), R=torch.eye(3)[None], t=torch.zeros(1, 3),
+                           orig_size=1, anti_aliasing=False)
+    return r(torch.from_numpy(vc), torch.from_numpy(faces)[None].repeat(B, 1, 1), mode="silhouettes").numpy()
+
+
+def _model_from_seq(seq, scale_opt=False):
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import Joint_Optimizer
+    params = synth.to_object_parameters(seq)
+    B = len(params)
+    return Joint_Optimizer(
+        translations_object=torch.cat([p["translations"] for p in params]),
+        rotations_object=torch.cat([p["rotations"] for p in params]),
+        verts_object_og=torch.from_numpy(seq["verts"]),
+        faces_object=torch.from_numpy(np.stack([seq["faces"]] * B)),
+        camintr_rois_object=torch.cat([p["K_roi"][:, 0] for p in params]),
+        target_masks_object=torch.cat([p["target_masks"] for p in params]),
+        int_scale_init=1, optimize_object_scale=scale_opt)
+
+
+@pytest.fixture(scope="module")
+def big_seq():
+    """custom_shoes-shaped frames: 5k-vertex mesh (V=5002, F=10000), 256x256 ROI, 480x640 camera."""
+    from dynhor_b200 import synth
+    return synth.make_sequence(4, mesh="uv50x100", seed=7, render_fn=_oracle_render_fn, period=300)
+
+
+def test_reference_size_frames_vs_oracle(big_seq):
+    """BASELINE configs[0]/[1] frame shape against the CPU oracle computed here: rasteriser maps bit-exact on the
+    kernel's own projected vertices, end-to-end silhouettes bit-exact, losses 1e-4, gradients 1e-3."""
+    from dynhor_b200.jointopt import FusedJointOpt
+    from oracle import jointopt_oracle as jo
+    from oracle import nr_oracle
+    seq = big_seq
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    model = _model_from_seq(seq)
+    fused = FusedJointOpt(model, lw, 1e-4, 4)
+    ev = fused.evaluate()
+    g_rot, g_tr, _ = fused.grads()
+    B, V = len(seq["R_init"]), len(seq["verts"])
+    # (1) rasteriser proper: oracle C rasteriser on the vertices the kernel projected
+    proj = fused.sil.buffers[0].view(torch.float32).view(B, V, 4)[:, :, :3].cpu().numpy()
+    faces2 = np.concatenate([seq["faces"], seq["faces"][:, ::-1]], 0)
+    maps = nr_oracle.rasterize_forward_np(proj[np.arange(B)[:, None, None], faces2[None]], 512)
+    assert np.array_equal(fused.sil.face_index_map().cpu().numpy(), maps["face_index"])
+    assert np.array_equal(unpack_alpha(fused.sil.coverage_bits().cpu().numpy()), maps["alpha"] > 0.5)
+    # (2) end to end against the oracle pipeline (torch CPU projection)
+    orc = jo.JointOptOracle(seq["rot6d_init"], seq["T_init"], seq["verts"], seq["faces"], seq["K_roi"],
+                            seq["target_masks"], lr=1e-4)
+    with torch.no_grad():
+        rend_o = orc.render().numpy()
+    with torch.no_grad():
+        rend_g = model.losses.sil_renderer(model.get_verts_object(), model.faces_object, mode="silhouettes")
+    assert np.array_equal(rend_g.cpu().numpy(), rend_o)
+    out, grads = orc.loss_and_grads(lw)
+    assert abs(ev["loss_sil_obj"][0] - out["loss_sil_obj"]) <= LOSS_RTOL * out["loss_sil_obj"]
+    assert abs(ev["loss_smooth_obj"][0] - out["loss_smooth_obj"]) <= LOSS_RTOL * out["loss_smooth_obj"]
+    assert abs(ev["iou_object"][0] - out["iou_object"]) <= 1e-6
+    for b in range(B):
+        assert rel_err(g_rot[b].cpu().numpy(), grads["rot6d"][b]) < GRAD_RTOL, b
+        assert rel_err(g_tr[b].cpu().numpy(), grads["trans"][b]) < GRAD_RTOL, b
+
+
+def test_renderer_backward_arbitrary_gradient_vs_oracle(big_seq):
+    """dh_sil_backward with a random upstream gradient vs the oracle's autograd on the same vertices."""
+    from dynhor_b200.renderer import Renderer
+    from oracle import nr_oracle
+    seq = big_seq
+    B = 2
+    cam = (seq["verts"][None].astype(np.float64) @ seq["R_init"][:B].astype(np.float64)
+           + seq["T_init"][:B]).astype(np.float32)
+    K = seq["K_roi"][:B]
+    g_rend = np.random.default_rng(0).normal(size=(B, 256, 256)).astype(np.float32)
+    faces = torch.from_numpy(seq["faces"])[None].repeat(B, 1, 1)
+    vo = torch.from_numpy(cam).requires_grad_(True)
+    ro = nr_oracle.Renderer(image_size=256, K=torch.from_numpy(K), R=torch.eye(3)[None], t=torch.zeros(1, 3),
+                            orig_size=1)
+    rend_o = ro(vo, faces, mode="silhouettes")
+    rend_o.backward(torch.from_numpy(g_rend))
+    vg = torch.from_numpy(cam).cuda().requires_grad_(True)
+    rg = Renderer(image_size=256, K=torch.from_numpy(K).cuda(), R=torch.eye(3)[None].cuda(),
+                  t=torch.zeros(1, 3).cuda(), orig_size=1)
+    rend_g = rg(vg, faces.cuda(), mode="silhouettes")
+    rend_g.backward(torch.from_numpy(g_rend).cuda())
+    assert np.array_equal(rend_g.detach().cpu().numpy(), rend_o.detach().numpy())
+    assert rel_err(vg.grad.cpu().numpy(), vo.grad.numpy()) < GRAD_RTOL
+
+
+def test_no_antialiasing_renderer_vs_oracle(big_seq):
+    """anti_aliasing=False at 256 (the stage-1 renderer, pose_initializtion.py:98-105)."""
+    from dynhor_b200.renderer import Renderer
+    seq = big_seq
+    B = 2
+    cam = (seq["verts"][None].astype(np.float64) @ seq["R_gt"][:B].astype(np.float64)
+           + seq["T_gt"][:B]).astype(np.float32)
+    sil_o = _oracle_render_fn(cam, seq["faces"], seq["K_roi"][:B], 256)
+    rg = Renderer(image_size=256, K=torch.from_numpy(seq["K_roi"][:B]).cuda(), R=torch.eye(3)[None].cuda(),
+                  t=torch.zeros(1, 3).cuda(), orig_size=1, anti_aliasing=False)
+    sil_g = rg(torch.from_numpy(cam).cuda(), torch.from_numpy(seq["faces"]).cuda()[None].repeat(B, 1, 1),
+               mode="silhouettes")
+    assert np.array_equal(sil_g.cpu().numpy(), sil_o)
+
+
+def _gpu_render_fn(vc, faces, K, size):
+    from dynhor_b200.renderer import Renderer
+    B = len(vc)
+    r = Renderer(image_size=size, K=torch.from_numpy(K).cuda(), R=torch.eye(3)[None].cuda(),
+                 t=torch.zeros(1, 3).cuda(), orig_size=1, anti_aliasing=False)
+    with torch.no_grad():
+        return r(torch.from_numpy(vc).cuda(), torch.from_numpy(faces).cuda()[None].repeat(B, 1, 1),
+                 mode="silhouettes").cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def full_seq():
+    """BASELINE configs[1] shape at a bounded frame count: 5k-vertex mesh, 256x256 ROIs, 48 frames."""
+    from dynhor_b200 import synth
+    return synth.make_sequence(48, mesh="uv50x100", seed=11, render_fn=_gpu_render_fn, period=300)
+
+
+def test_full_size_properties(full_seq):
+    """Size-independent properties at reference frame size: run-to-run determinism, CUDA graph == eager launches,
+    2-way frame sharding == single shard (bit-identical parameters), loss decreases, IoU increases."""
+    from dynhor_b200.jointopt import FusedJointOpt
+    from dynhor_b200.sharding import FrameShard
+    seq = full_seq
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    iters = 12
+
+    def run(use_graph):
+        model = _model_from_seq(seq)
+        fused = FusedJointOpt(model, lw, 1e-4, iters)
+        fused.run(iters, use_graph=use_graph)
+        return model, fused.history(), fused
+
+    m1, h1, f1 = run(True)
+    m2, h2, _ = run(True)
+    m3, h3, _ = run(False)
+    for a, b in ((m1, m2), (m1, m3)):
+        assert torch.equal(a.rotations_object, b.rotations_object)
+        assert torch.equal(a.translations_object, b.translations_object)
+    assert h1["loss"] == h2["loss"] == h3["loss"]
+    assert h1["loss"][-1] < h1["loss"][0] and h1["iou_object"][-1] > h1["iou_object"][0]
+
+    # two shards emulated on one GPU: halos swapped by hand after every iteration
+    B = len(seq["R_init"])
+    keep_sum = f1.keep_sum
+    import copy
+    shards, fused_s = [], []
+    for r in range(2):
+        sh = FrameShard(r, 2, B)
+        sub = {k: (v[sh.start:sh.stop] if isinstance(v, np.ndarray) and len(v) == B and k not in ("verts", "faces")
+                   else v) for k, v in seq.items()}
+        model = _model_from_seq(sub)
+        shards.append(model)
+        fused_s.append(FusedJointOpt(model, lw, 1e-4, iters, shard=sh, keep_sum=keep_sum, exchange=False))
+
+    def pose(model, i):
+        return torch.cat([model.rotations_object.detach()[i].reshape(6), model.translations_object.detach()[i].reshape(3)])
+
+    for it in range(iters):
+        fused_s[0].halo[1].copy_(pose(shards[1], 0))
+        fused_s[1].halo[0].copy_(pose(shards[0], -1))
+        for f in fused_s:
+            f.run(1, use_graph=True)
+    rot = torch.cat([m.rotations_object.detach() for m in shards])
+    tr = torch.cat([m.translations_object.detach() for m in shards])
+    assert torch.equal(rot, m1.rotations_object.detach())
+    assert torch.equal(tr, m1.translations_object.detach())
+    hs = [f.history() for f in fused_s]
+    tot = np.asarray(hs[0]["loss"]) + np.asarray(hs[1]["loss"])
+    assert np.allclose(tot, h1["loss"], rtol=1e-12)
+
+
+def test_error_behaviour():
+    """Reference error conventions: ValueError for masks outside [0,1], AssertionError on shapes."""
+    from dynhor_b200.losses import batch_mask_iou
+    from dynhor_b200.renderer import shared_faces
+    with pytest.raises(ValueError):
+        batch_mask_iou(torch.full((1, 4, 4), 2.0).cuda(), torch.zeros(1, 4, 4).cuda())
+    with pytest.raises(AssertionError):
+        shared_faces(torch.zeros(3, 4, dtype=torch.int64).cuda())
+    with pytest.raises(NotImplementedError):
+        f = torch.zeros(2, 5, 3, dtype=torch.int64).cuda()
+        f[1, 0, 0] = 1
+        shared_faces(f)
