@@ -270,9 +270,15 @@ DH_HD unsigned long long zkey(float zp, int fn) {
 // Maps a face needs for the edge-scan pseudo-gradient.  Bitmaps are 32 pixels per word, bit i = pixel 32*w+i.
 struct BwdMaps {
     const uint32_t* alpha;     // [is][is/32]  row-major coverage (rasteriser row order, i.e. before the flip)
-    const uint32_t* neg;       // [is][is/32]  row-major: alpha == 0 && grad < 0
+    const uint32_t* neg;       // [is][is/32]  row-major: alpha == 0 && grad < 0   (optional: NULL -> derived from
+                               //              alpha and neg_pool on the fly)
     const uint32_t* negT;      // [is][is/32]  column-major copy of `neg`: negT[c][r/32]
     const uint32_t* pos_pool;  // [S][ceil(S/32)] output-resolution bitmap: grad > 0
+    const uint32_t* neg_pool;  // [S][ceil(S/32)] output-resolution bitmap: grad < 0
+    const int16_t* row_lo;     // [is] first / last set bit of every row / column of `neg` (lo > hi: none);
+    const int16_t* row_hi;     //      optional (NULL -> no range filter)
+    const int16_t* col_lo;
+    const int16_t* col_hi;
     const float* gpool;        // [S][S]  dL/d(rendered silhouette) at output resolution
     const int32_t* fidx;       // [is][is] face index map (-1 none)
     int is, S, aa, wpr, wpr_pool;
@@ -286,76 +292,147 @@ DH_HD bool pos_at(const BwdMaps& m, int r, int c) {
     const int x = cell_x(m, c);
     return (m.pos_pool[cell_y(m, r) * m.wpr_pool + (x >> 5)] >> (x & 31)) & 1u;
 }
+DH_HD uint32_t spread16(uint32_t x) {  // bit i -> bits 2i and 2i+1
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x | (x << 1);
+}
+// word w of row r of the "uncovered and gradient < 0" bitmap, from the coverage and the pooled sign bitmap
+DH_HD uint32_t neg_row_word(const uint32_t* alpha, const uint32_t* neg_pool, int is, int aa, int wpr, int wprp, int r,
+                            int w) {
+    const int rf = is - 1 - r;
+    uint32_t nb;
+    if (aa) {
+        const uint32_t pw = neg_pool[(rf >> 1) * wprp + (w >> 1)];
+        nb = spread16((w & 1) ? (pw >> 16) : pw);
+    } else {
+        nb = neg_pool[rf * wprp + w];
+    }
+    return ~alpha[r * wpr + w] & nb;
+}
+// word w of the scan line of (axis, d0): column d0 (axis 0) or row d0 (axis 1)
+DH_HD uint32_t neg_line_word(const BwdMaps& m, int axis, int d0, int w) {
+    if (axis == 0) return m.negT[d0 * m.wpr + w];
+    if (m.neg != nullptr) return m.neg[d0 * m.wpr + w];
+    return neg_row_word(m.alpha, m.neg_pool, m.is, m.aa, m.wpr, m.wpr_pool, d0, w);
+}
 
-// One (diff, d1) contribution to the two vertices of the current edge.
-DH_HD void edge_accumulate(float diff, int d0, int d1, float d1_cross, float p00, float p10, float eps, int is,
-                           float* g_a, float* g_b) {
+// One edge of a face seen along one axis: p0 -> p1 is the edge, p2 the opposite vertex; component 0 is the
+// coordinate the scan steps along (d0), component 1 the one it scans (d1).
+struct Span {
+    float p00, p01, p10, p11, p20, p21, slope;
+    int direction, d0_from, d0_to;
+};
+// px, py: pixel coordinates of the three vertices (ndc_to_pix), in the winding's order.
+DH_HD void span_setup(const float* px, const float* py, int edge, int axis, int is, Span& sp) {
+    const int i0 = edge, i1 = (edge + 1) % 3, i2 = (edge + 2) % 3;
+    sp.p00 = axis ? py[i0] : px[i0]; sp.p01 = axis ? px[i0] : py[i0];
+    sp.p10 = axis ? py[i1] : px[i1]; sp.p11 = axis ? px[i1] : py[i1];
+    sp.p20 = axis ? py[i2] : px[i2]; sp.p21 = axis ? px[i2] : py[i2];
+    if (axis == 0) sp.direction = (sp.p00 < sp.p10) ? -1 : 1;
+    else           sp.direction = (sp.p00 < sp.p10) ? 1 : -1;
+    sp.d0_from = f2i_sat(fmaxf(ceilf(fminf(sp.p00, sp.p10)), 0.0f));
+    sp.d0_to = f2i_sat(fminf(fmaxf(sp.p00, sp.p10), (float)(is - 1)));
+    sp.slope = (sp.p11 - sp.p01) / (sp.p10 - sp.p00);
+}
+// Crossing of the edge with scan line d0: the pixel just inside (d1_in) and just outside (d1_out) the face.
+DH_HD bool span_crossing(const Span& sp, int d0, int is, float* d1_cross, int* d1_in, int* d1_out) {
+    float c = sp.slope * ((float)d0 - sp.p00);
+    c = c + sp.p01;
+    int in;
+    if (0 < sp.direction) in = f2i_sat(floorf(c));
+    else                  in = f2i_sat(ceilf(c));
+    const int out = in + sp.direction;
+    *d1_cross = c; *d1_in = in; *d1_out = out;
+    if (in < 0 || is <= in) return false;
+    if (out < 0 || is <= out) return false;
+    return true;
+}
+DH_HD void out_scan_range(int direction, int d1_out, int is, int* from, int* to) {
+    const int d1_limit = (0 < direction) ? is - 1 : 0;
+    int f = d1_out < d1_limit ? d1_out : d1_limit;
+    if (f < 0) f = 0;
+    int t = d1_out > d1_limit ? d1_out : d1_limit;
+    if (t > is - 1) t = is - 1;
+    *from = f; *to = t;
+}
+DH_HD void in_scan_range(const Span& sp, int d0, int d1_in, int is, int* from, int* to) {
+    float c2;
+    if (((float)d0 - sp.p00) * ((float)d0 - sp.p20) < 0.0f) {
+        c2 = (sp.p21 - sp.p01) / (sp.p20 - sp.p00);
+        c2 = c2 * ((float)d0 - sp.p00);
+        c2 = c2 + sp.p01;
+    } else {
+        c2 = (sp.p11 - sp.p21) / (sp.p10 - sp.p20);
+        c2 = c2 * ((float)d0 - sp.p20);
+        c2 = c2 + sp.p21;
+    }
+    int d1_limit;
+    if (0 < sp.direction) d1_limit = f2i_sat(ceilf(c2));
+    else                  d1_limit = f2i_sat(floorf(c2));
+    int f = d1_in < d1_limit ? d1_in : d1_limit;
+    if (f < 0) f = 0;
+    int t = d1_in > d1_limit ? d1_in : d1_limit;
+    if (t > is - 1) t = is - 1;
+    *from = f; *to = t;
+}
+// The two terms (diff / dist) one pixel d1 of the scan contributes to the edge's vertices p0 (ta) and p1 (tb);
+// the gradient accumulates MINUS these.
+DH_HD void edge_terms(float diff, int d0, int d1, float d1_cross, float p00, float p10, float eps, int is, float* ta,
+                      float* tb) {
+    *ta = 0.0f; *tb = 0.0f;
     if (p10 != (float)d0) {
         float t = (p10 - p00) / (p10 - (float)d0);
         t = t * ((float)d1 - d1_cross);
         float dist = (t * 2.0f) / (float)is;
         dist = (0.0f < dist) ? dist + eps : dist - eps;
-        *g_a = *g_a - diff / dist;
+        *ta = diff / dist;
     }
     if (p00 != (float)d0) {
         float t = (p10 - p00) / ((float)d0 - p00);
         t = t * ((float)d1 - d1_cross);
         float dist = (t * 2.0f) / (float)is;
         dist = (0.0f < dist) ? dist + eps : dist - eps;
-        *g_b = *g_b - diff / dist;
+        *tb = diff / dist;
     }
 }
 
-// Pseudo-gradient of the loss w.r.t. the NDC (x,y) of the three vertices of face `fn`.
+// Pseudo-gradient of the loss w.r.t. the NDC (x,y) of the three vertices of face `fn`, one face per call (the
+// serial form: used by the host emulation and as the definition the warp-cooperative kernel must reproduce).
 // grad: [3][2] (vertex, xy), overwritten.  fx,fy: NDC coordinates in this winding's vertex order.
 DH_HD void backward_face(const float* fx, const float* fy, int fn, float eps, const BwdMaps& m, float* grad) {
     for (int k = 0; k < 6; k++) grad[k] = 0.0f;
     if (!finite3(fx[0], fx[1], fx[2]) || !finite3(fy[0], fy[1], fy[2])) return;
     if (face_backside(fx[0], fy[0], fx[1], fy[1], fx[2], fy[2])) return;
     const int is = m.is;
-    for (int edge_num = 0; edge_num < 3; edge_num++) {
-        int pi[3];
-        float pp[3][2];
-        for (int num = 0; num < 3; num++) {
-            pi[num] = (edge_num + num) % 3;
-            pp[num][0] = ndc_to_pix(fx[pi[num]], is);
-            pp[num][1] = ndc_to_pix(fy[pi[num]], is);
-        }
+    float px[3], py[3];
+    for (int k = 0; k < 3; k++) {
+        px[k] = ndc_to_pix(fx[k], is);
+        py[k] = ndc_to_pix(fy[k], is);
+    }
+    for (int edge = 0; edge < 3; edge++) {
         for (int axis = 0; axis < 2; axis++) {
-            const float p00 = pp[0][axis], p01 = pp[0][1 - axis];
-            const float p10 = pp[1][axis], p11 = pp[1][1 - axis];
-            const float p20 = pp[2][axis], p21 = pp[2][1 - axis];
-            int direction;
-            if (axis == 0) direction = (p00 < p10) ? -1 : 1;
-            else           direction = (p00 < p10) ? 1 : -1;
-            const int d0_from = f2i_sat(fmaxf(ceilf(fminf(p00, p10)), 0.0f));
-            const int d0_to = f2i_sat(fminf(fmaxf(p00, p10), (float)(is - 1)));
-            const float slope = (p11 - p01) / (p10 - p00);
-            float* g_a = &grad[pi[0] * 2 + (1 - axis)];
-            float* g_b = &grad[pi[1] * 2 + (1 - axis)];
-            for (int d0 = d0_from; d0 <= d0_to; d0++) {
-                float d1_cross = slope * ((float)d0 - p00);
-                d1_cross = d1_cross + p01;
-                int d1_in;
-                if (0 < direction) d1_in = f2i_sat(floorf(d1_cross));
-                else               d1_in = f2i_sat(ceilf(d1_cross));
-                const int d1_out = d1_in + direction;
-                if (d1_in < 0 || is <= d1_in) continue;
-                if (d1_out < 0 || is <= d1_out) continue;
+            Span sp;
+            span_setup(px, py, edge, axis, is, sp);
+            float* g_a = &grad[edge * 2 + (1 - axis)];
+            float* g_b = &grad[((edge + 1) % 3) * 2 + (1 - axis)];
+            for (int d0 = sp.d0_from; d0 <= sp.d0_to; d0++) {
+                float d1_cross;
+                int d1_in, d1_out;
+                if (!span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) continue;
                 const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
                 const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
                 // ---- out scan: uncovered pixels beyond the edge whose gradient asks for coverage
                 {
-                    const int d1_limit = (0 < direction) ? is - 1 : 0;
-                    int d1_from = d1_out < d1_limit ? d1_out : d1_limit;
-                    if (d1_from < 0) d1_from = 0;
-                    int d1_to = d1_out > d1_limit ? d1_out : d1_limit;
-                    if (d1_to > is - 1) d1_to = is - 1;
-                    const uint32_t* line = (axis == 0) ? (m.negT + d0 * m.wpr) : (m.neg + d0 * m.wpr);
+                    int d1_from, d1_to;
+                    out_scan_range(sp.direction, d1_out, is, &d1_from, &d1_to);
                     const int w_from = d1_from >> 5, w_to = d1_to >> 5;
                     bool owner_known = false, owner = false;
                     for (int w = w_from; w <= w_to; w++) {
-                        uint32_t bits = line[w];
+                        uint32_t bits = neg_line_word(m, axis, d0, w);
                         if (w == w_from) bits &= 0xFFFFFFFFu << (d1_from & 31);
                         if (w == w_to) bits &= 0xFFFFFFFFu >> (31 - (d1_to & 31));
                         if (!bits) continue;
@@ -370,29 +447,17 @@ DH_HD void backward_face(const float* fx, const float* fy, int fn, float eps, co
                             const float g = (axis == 0) ? grad_at(m, d1, d0) : grad_at(m, d0, d1);
                             const float diff = (0.0f - 1.0f) * g;
                             if (diff <= 0.0f) continue;
-                            edge_accumulate(diff, d0, d1, d1_cross, p00, p10, eps, is, g_a, g_b);
+                            float ta, tb;
+                            edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
+                            *g_a = *g_a - ta;
+                            *g_b = *g_b - tb;
                         }
                     }
                 }
                 // ---- in scan: this face's own pixels, only when the pixel just outside the edge is uncovered
                 if (!alpha_at(m, r_out, c_out)) {
-                    float d0_cross2;
-                    if (((float)d0 - p00) * ((float)d0 - p20) < 0.0f) {
-                        d0_cross2 = (p21 - p01) / (p20 - p00);
-                        d0_cross2 = d0_cross2 * ((float)d0 - p00);
-                        d0_cross2 = d0_cross2 + p01;
-                    } else {
-                        d0_cross2 = (p11 - p21) / (p10 - p20);
-                        d0_cross2 = d0_cross2 * ((float)d0 - p20);
-                        d0_cross2 = d0_cross2 + p21;
-                    }
-                    int d1_limit;
-                    if (0 < direction) d1_limit = f2i_sat(ceilf(d0_cross2));
-                    else               d1_limit = f2i_sat(floorf(d0_cross2));
-                    int d1_from = d1_in < d1_limit ? d1_in : d1_limit;
-                    if (d1_from < 0) d1_from = 0;
-                    int d1_to = d1_in > d1_limit ? d1_in : d1_limit;
-                    if (d1_to > is - 1) d1_to = is - 1;
+                    int d1_from, d1_to;
+                    in_scan_range(sp, d0, d1_in, is, &d1_from, &d1_to);
                     for (int d1 = d1_from; d1 <= d1_to; d1++) {
                         const int r = (axis == 0) ? d1 : d0, c = (axis == 0) ? d0 : d1;
                         if (!alpha_at(m, r, c)) continue;
@@ -400,7 +465,10 @@ DH_HD void backward_face(const float* fx, const float* fy, int fn, float eps, co
                         if (m.fidx[r * is + c] != fn) continue;
                         const float diff = (1.0f - 0.0f) * grad_at(m, r, c);
                         if (diff <= 0.0f) continue;
-                        edge_accumulate(diff, d0, d1, d1_cross, p00, p10, eps, is, g_a, g_b);
+                        float ta, tb;
+                        edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
+                        *g_a = *g_a - ta;
+                        *g_b = *g_b - tb;
                     }
                 }
             }

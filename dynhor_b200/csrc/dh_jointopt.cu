@@ -171,6 +171,22 @@ __device__ __forceinline__ void load_face(const float4* __restrict__ P, const in
     }
 }
 
+// Depth of one queued hit and the z-buffer update.  ent = slot | x << 5 | local_row << 15.
+__device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32], const int* fns,
+                                           unsigned long long* zbuf, int is, int row0, float near, float far) {
+    const int slot = ent & 31, xi = (ent >> 5) & 1023, yl = ent >> 15;
+    FaceSetup f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) f.inv[k] = setup[k][slot];
+#pragma unroll
+    for (int k = 0; k < 3; k++) f.z[k] = setup[9 + k][slot];
+    float zp;
+    if (!pixel_depth(f, xi, row0 + yl, near, far, &zp)) return;
+    const unsigned long long key = zkey(zp, fns[slot]);
+    unsigned long long* cell = zbuf + yl * is + xi;
+    if (key < *cell) atomicMin(cell, key);
+}
+
 // FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
 // else : epilogue writes the pooled, flipped silhouette `rend` (the renderer's return value).
 template <bool FUSED>
@@ -180,37 +196,71 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
     __shared__ uint32_t abits[kSH][kMaxIS / 32];
     __shared__ int red[3][kThreads / 32];
+    __shared__ float s_setup[kThreads / 32][12][32];  // per warp: inv[9], z[3] of the 32 faces of the batch
+    __shared__ int s_fn[kThreads / 32][32];
+    __shared__ uint32_t s_queue[kThreads / 32][64];   // pending (lane slot, x, local row) hits
     const int is = raster_size(s);
     const int nstrips = is / kSH;
     const int strip = blockIdx.x, b = blockIdx.y;
     const int row0 = strip * kSH;
     const int tid = threadIdx.x;
     for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
     __syncthreads();
 
     const int count = s.bin_count[b * nstrips + strip];
     const int32_t* bin = s.bins + ((size_t)b * nstrips + strip) * (size_t)(2 * s.F);
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
-    for (int e = tid; e < count; e += kThreads) {
-        const int fn = bin[e];
+    // Warp-synchronous batches of 32 bin entries.  Each lane sets up one face and walks its clipped bounding box
+    // doing only the (cheap) edge tests; pixels that pass are compacted into a per-warp queue, and whenever 32
+    // are pending the whole warp evaluates their depths (the expensive IEEE divisions) at full lane occupancy.
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int base = warp * 32; base < count; base += (kThreads / 32) * 32) {
+        const int e = base + lane;
         FaceSetup fs;
-        int ids[3];
-        load_face(P, s.faces, fn, s.F, fs, ids);
-        if (!face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) continue;
-        face_inverse(fs, is);
-        const int r_lo = max(fs.y_lo, row0), r_hi = min(fs.y_hi, row0 + kSH - 1);
-        for (int yi = r_lo; yi <= r_hi; yi++) {
-            const float yp = pix_to_ndc(yi, is);
-            unsigned long long* zrow = zbuf + (yi - row0) * is;
-            for (int xi = fs.x_lo; xi <= fs.x_hi; xi++) {
-                const float xp = pix_to_ndc(xi, is);
-                if (!pixel_inside(fs, xp, yp)) continue;
-                float zp;
-                if (!pixel_depth(fs, xi, yi, s.near_, s.far_, &zp)) continue;
-                const unsigned long long key = zkey(zp, fn);
-                if (key < zrow[xi]) atomicMin(&zrow[xi], key);
+        int npix = 0, bw = 1, x_lo = 0, r_lo = 0;
+        if (e < count) {
+            const int fn = bin[e];
+            int ids[3];
+            load_face(P, s.faces, fn, s.F, fs, ids);
+            if (face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) {
+                face_inverse(fs, is);
+                r_lo = max(fs.y_lo, row0);
+                const int r_hi = min(fs.y_hi, row0 + kSH - 1);
+                x_lo = fs.x_lo;
+                bw = fs.x_hi - fs.x_lo + 1;
+                npix = (r_hi >= r_lo) ? bw * (r_hi - r_lo + 1) : 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) s_setup[warp][k][lane] = fs.inv[k];
+#pragma unroll
+                for (int k = 0; k < 3; k++) s_setup[warp][9 + k][lane] = fs.z[k];
+                s_fn[warp][lane] = fn;
             }
         }
+        __syncwarp();
+        int qn = 0, i = 0, xi = x_lo, yi = r_lo;
+        while (__any_sync(0xffffffffu, i < npix)) {
+            bool hit = false;
+            uint32_t ent = 0;
+            if (i < npix) {
+                hit = pixel_inside(fs, pix_to_ndc(xi, is), pix_to_ndc(yi, is));
+                ent = (uint32_t)lane | ((uint32_t)xi << 5) | ((uint32_t)(yi - row0) << 15);
+                i++;
+                if (++xi >= x_lo + bw) { xi = x_lo; yi++; }
+            }
+            const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+            if (hit) s_queue[warp][qn + __popc(hits & lt_mask)] = ent;
+            qn += __popc(hits);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                raster_hit(s_queue[warp][qn + lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
+                __syncwarp();
+            }
+        }
+        if (lane < qn) raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
+        __syncwarp();
     }
     __syncthreads();
 
@@ -284,28 +334,107 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     }
 }
 
-// sign bitmaps of a caller-provided dL/drend (API backward)
+// sign bitmaps and per-frame max magnitude of a caller-provided dL/drend (API backward)
 __global__ void __launch_bounds__(kThreads)
 k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint32_t* __restrict__ neg_pool,
-             long long ncell) {
+             float* __restrict__ gmax, long long ncell, int cells_per_frame, float gscale) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const float v = (i < ncell) ? g[i] : 0.0f;
     const uint32_t pw = __ballot_sync(0xffffffffu, v > 0.0f);
     const uint32_t nw = __ballot_sync(0xffffffffu, v < 0.0f);
+    float mx = fabsf(v) * gscale;
+    if (!(mx <= 3.0e38f)) mx = 0.0f;  // NaN / inf gradients do not size the fixed point
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0 && i < ncell) {
         pos_pool[i >> 5] = pw;
         neg_pool[i >> 5] = nw;
+        if (mx > 0.0f) atomicMax(reinterpret_cast<int*>(gmax) + (int)(i / cells_per_frame), __float_as_int(mx));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i -> bits 2i and 2i+1
-    x &= 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x | (x << 1);
+// Warp-cooperative edge-scan backward.  The per-face algorithm of dh_core.h::backward_face is cut into three
+// stages with per-warp queues in shared memory between them, so that each stage runs at (nearly) full lanes:
+//   items  front-facing (face, winding) pairs, compacted from the chunk's faces;
+//   phase 1 (lane = item): walks the 6 (edge, axis) spans of the face and emits one task per scan-line crossing
+//           that can contribute: OUT if the line has "wanted but uncovered" pixels beyond the edge (O(1) test
+//           against per-line first/last ranges), IN if the pixel just outside the edge is uncovered;
+//   phase 2 (lane = task): ownership test on the face-index map, then the pixel loop; the two edge-vertex terms
+//           are accumulated in 64-bit fixed point (shared-memory atomics), which makes the sum exact and hence
+//           independent of task order: bit-identical results run to run.
+//   tail    (lane = item): fixed point -> float, projection / rigid-transform backward, pose accumulators.
+constexpr int kBwdWarps = kThreads / 32;
+constexpr int kTaskCap = 96, kItemCap = 96;
+
+struct BwdWarp {
+    float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot
+    int fn[32];
+    unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
+    uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9
+    uint32_t items[kItemCap];            // face | winding << 31
+};
+
+__device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long long v) {
+    if (v != 0) atomicAdd(a, (unsigned long long)v);
+}
+
+// phase 2: one task per lane
+__device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale) {
+    const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1, d0 = (int)(t >> 9);
+    const int is = m.is;
+    float px[3], py[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { px[k] = W.px[k][slot]; py[k] = W.py[k][slot]; }
+    Span sp;
+    span_setup(px, py, edge, axis, is, sp);
+    float d1_cross;
+    int d1_in, d1_out;
+    span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out);
+    const int fn = W.fn[slot];
+    long long sa = 0, sb = 0;
+    if (kind == 0) {
+        const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
+        if (m.fidx[r_in * is + c_in] == fn) {
+            int from, to;
+            out_scan_range(sp.direction, d1_out, is, &from, &to);
+            from = max(from, (int)((axis == 0) ? m.col_lo[d0] : m.row_lo[d0]));
+            to = min(to, (int)((axis == 0) ? m.col_hi[d0] : m.row_hi[d0]));
+            const int w_from = from >> 5, w_to = to >> 5;
+            for (int w = w_from; w <= w_to; w++) {
+                uint32_t bits = neg_line_word(m, axis, d0, w);
+                if (w == w_from) bits &= 0xFFFFFFFFu << (from & 31);
+                if (w == w_to) bits &= 0xFFFFFFFFu >> (31 - (to & 31));
+                while (bits) {
+                    const int d1 = (w << 5) + ctz32(bits);
+                    bits &= bits - 1;
+                    const float g = (axis == 0) ? grad_at(m, d1, d0) : grad_at(m, d0, d1);
+                    const float diff = (0.0f - 1.0f) * g;
+                    if (diff <= 0.0f) continue;
+                    float ta, tb;
+                    edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
+                    sa += __float2ll_rn(ta * fpscale);
+                    sb += __float2ll_rn(tb * fpscale);
+                }
+            }
+        }
+    } else {
+        int from, to;
+        in_scan_range(sp, d0, d1_in, is, &from, &to);
+        for (int d1 = from; d1 <= to; d1++) {
+            const int r = (axis == 0) ? d1 : d0, c = (axis == 0) ? d0 : d1;
+            if (!alpha_at(m, r, c)) continue;
+            if (!pos_at(m, r, c)) continue;
+            if (m.fidx[r * is + c] != fn) continue;
+            const float diff = (1.0f - 0.0f) * grad_at(m, r, c);
+            if (diff <= 0.0f) continue;
+            float ta, tb;
+            edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
+            sa += __float2ll_rn(ta * fpscale);
+            sb += __float2ll_rn(tb * fpscale);
+        }
+    }
+    atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], sa);
+    atomic_add_fixed(&W.acc[((edge + 1) % 3) * 2 + (1 - axis)][slot], sb);
 }
 
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
@@ -316,56 +445,85 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks) {
     extern __shared__ uint32_t smw[];
-    __shared__ float red[kThreads / 32][13];
+    __shared__ float red[kBwdWarps][13];
+    __shared__ int16_t s_rng[4][kMaxIS];  // row_lo, row_hi, col_lo, col_hi
+    __shared__ BwdWarp s_warp[kBwdWarps];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
-    uint32_t* s_neg = s_alpha + is * wpr;
-    uint32_t* s_negT = s_neg + is * wpr;
+    uint32_t* s_negT = s_alpha + is * wpr;
     uint32_t* s_pos = s_negT + is * wpr;
+    uint32_t* s_negp = s_pos + S * wprp;
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
-    const uint32_t* gp = s.pos_pool + (size_t)b * S * wprp;
-    const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
-    for (int i = tid; i < is * wpr; i += kThreads) {
-        const uint32_t a = ga[i];
-        const int r = i / wpr, w = i - r * wpr;
-        const int rf = is - 1 - r;
-        uint32_t nb;
-        if (s.aa) {
-            const uint32_t pw = gn[(rf >> 1) * wprp + (w >> 1)];
-            nb = spread16((w & 1) ? (pw >> 16) : pw);
-        } else {
-            nb = gn[rf * wprp + w];
-        }
-        s_alpha[i] = a;
-        s_neg[i] = ~a & nb;
+    // ---- stage the frame's bitmaps
+    {
+        const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
+        const uint32_t* gp = s.pos_pool + (size_t)b * S * wprp;
+        const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
+        for (int i = tid; i < is * wpr; i += kThreads) s_alpha[i] = ga[i];
+        for (int i = tid; i < S * wprp; i += kThreads) { s_pos[i] = gp[i]; s_negp[i] = gn[i]; }
     }
-    for (int i = tid; i < S * wprp; i += kThreads) s_pos[i] = gp[i];
     __syncthreads();
-    {   // column-major copy of s_neg: 32x32 bit-block transposes through ballots
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int blk = warp; blk < wpr * wpr; blk += kThreads / 32) {
-            const int rb = blk / wpr, cb = blk - rb * wpr;
-            const uint32_t word = s_neg[(32 * rb + lane) * wpr + cb];
-            uint32_t mine = 0;
+    // column-major copy of the "uncovered && grad < 0" bitmap: 32x32 bit-block transposes through ballots
+    for (int blk = warp; blk < wpr * wpr; blk += kBwdWarps) {
+        const int rb = blk / wpr, cb = blk - rb * wpr;
+        const uint32_t word = neg_row_word(s_alpha, s_negp, is, s.aa, wpr, wprp, 32 * rb + lane, cb);
+        uint32_t mine = 0;
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
-                if (lane == j) mine = colw;
-            }
-            s_negT[(32 * cb + lane) * wpr + rb] = mine;
+        for (int j = 0; j < 32; j++) {
+            const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
+            if (lane == j) mine = colw;
         }
+        s_negT[(32 * cb + lane) * wpr + rb] = mine;
+    }
+    // first / last set pixel of every row
+    for (int r = tid; r < is; r += kThreads) {
+        int lo = is, hi = -1;
+        for (int w = 0; w < wpr; w++) {
+            const uint32_t bits = neg_row_word(s_alpha, s_negp, is, s.aa, wpr, wprp, r, w);
+            if (bits) {
+                if (lo == is) lo = (w << 5) + ctz32(bits);
+                hi = (w << 5) + 31 - __clz((int)bits);
+            }
+        }
+        s_rng[0][r] = (int16_t)lo;
+        s_rng[1][r] = (int16_t)hi;
+    }
+    __syncthreads();
+    for (int c = tid; c < is; c += kThreads) {
+        int lo = is, hi = -1;
+        for (int w = 0; w < wpr; w++) {
+            const uint32_t bits = s_negT[c * wpr + w];
+            if (bits) {
+                if (lo == is) lo = (w << 5) + ctz32(bits);
+                hi = (w << 5) + 31 - __clz((int)bits);
+            }
+        }
+        s_rng[2][c] = (int16_t)lo;
+        s_rng[3][c] = (int16_t)hi;
     }
     __syncthreads();
 
     BwdMaps m;
-    m.alpha = s_alpha; m.neg = s_neg; m.negT = s_negT; m.pos_pool = s_pos;
+    m.alpha = s_alpha; m.neg = nullptr; m.negT = s_negT; m.pos_pool = s_pos; m.neg_pool = s_negp;
+    m.row_lo = s_rng[0]; m.row_hi = s_rng[1]; m.col_lo = s_rng[2]; m.col_hi = s_rng[3];
     m.gpool = s.gpool + (size_t)b * S * S;
     m.fidx = s.fidx + (size_t)b * is * is;
     m.is = is; m.S = S; m.aa = s.aa; m.wpr = wpr; m.wpr_pool = wprp;
     m.gscale = s.aa ? 0.25f : 1.0f;
+
+    // fixed-point scale: |term| <= gmax / eps; 2^38 / that bound leaves 2^24 terms of headroom in 63 bits
+    const float gmax = s.gmax[b];
+    float fpscale = 0.0f, fpinv = 0.0f;
+    if (gmax > 0.0f) {
+        int e;
+        frexpf(gmax / fmaxf(s.eps, 1e-7f), &e);
+        fpscale = ldexpf(1.0f, 38 - e);
+        fpinv = ldexpf(1.0f, e - 38);
+    }
 
     float Rm[9], Tm[3], Km[6], s_abs = 1.0f;
     if (FUSED) {
@@ -378,58 +536,150 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
 #pragma unroll
     for (int i = 0; i < 13; i++) acc[i] = 0.0f;
 
+    BwdWarp& W = s_warp[warp];
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
     const int per = (s.F + nchunks - 1) / nchunks;
     const int f0 = chunk * per, f1 = min(s.F, f0 + per);
-    for (int f = f0 + tid; f < f1; f += kThreads) {
-        for (int w = 0; w < 2; w++) {
-            const int fn = f + w * s.F;
-            FaceSetup fs;
-            int ids[3];
-            load_face(P, s.faces, fn, s.F, fs, ids);
-            float g[6];
-            backward_face(fs.x, fs.y, fn, s.eps, m, g);
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float gu = g[2 * k], gv = g[2 * k + 1];
-                if (gu == 0.0f && gv == 0.0f) continue;
-                float c[3], vo[3], gc[3];
-                if (FUSED) {
-                    for (int i = 0; i < 3; i++) vo[i] = verts_src[3 * ids[k] + i];
-                    transform_vertex(vo, s_abs, Rm, Tm, c);
-                } else {
-                    const float* src = verts_src + ((size_t)b * s.V + ids[k]) * 3;
-                    c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
-                }
-                project_vertex_backward(c, Km, s.orig_size, gu, gv, gc);
-                if (FUSED) {
-                    for (int j = 0; j < 3; j++) acc[j] += gc[j];
-                    for (int i = 0; i < 3; i++)
-                        for (int j = 0; j < 3; j++) acc[3 + 3 * i + j] += (s_abs * vo[i]) * gc[j];
-                    float dot = 0.0f;
-                    for (int j = 0; j < 3; j++)
-                        dot += (vo[0] * Rm[j] + vo[1] * Rm[3 + j] + vo[2] * Rm[6 + j]) * gc[j];
-                    acc[12] += dot;
-                } else {
-                    float* dst = grad_verts + ((size_t)b * s.V + ids[k]) * 3;
-                    atomicAdd(dst + 0, gc[0]);
-                    atomicAdd(dst + 1, gc[1]);
-                    atomicAdd(dst + 2, gc[2]);
+    int n_items = 0;
+    // the warp owns faces f0 + warp*32 + [0,32) + k * (warps*32)
+    for (int fbase = f0 + warp * 32; (fbase < f1 || n_items > 0) && gmax > 0.0f; fbase += kBwdWarps * 32) {
+        // ---- gather front-facing (face, winding) items of the next 32 faces
+        if (fbase < f1) {
+            const int f = fbase + lane;
+            bool v0 = false, v1 = false;
+            if (f < f1) {
+                const float4 a0 = P[s.faces[3 * f + 0]], a1 = P[s.faces[3 * f + 1]], a2 = P[s.faces[3 * f + 2]];
+                if (finite3(a0.x, a1.x, a2.x) && finite3(a0.y, a1.y, a2.y)) {
+                    v0 = !face_backside(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y);
+                    v1 = !face_backside(a2.x, a2.y, a1.x, a1.y, a0.x, a0.y);
                 }
             }
+            const uint32_t m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
+            if (v0) W.items[n_items + __popc(m0 & lt_mask)] = (uint32_t)f;
+            if (v1) W.items[n_items + __popc(m0) + __popc(m1 & lt_mask)] = (uint32_t)f | 0x80000000u;
+            n_items += __popc(m0) + __popc(m1);
+            __syncwarp();
+        }
+        const bool last = fbase + kBwdWarps * 32 >= f1;
+        // ---- process full batches of 32 items (and the remainder at the very end)
+        while (n_items >= 32 || (last && n_items > 0)) {
+            const int nb = min(n_items, 32);
+            n_items -= nb;
+            const bool have = lane < nb;
+            float px[3], py[3];
+            int ids[3] = {0, 0, 0};
+            if (have) {
+                const uint32_t it = W.items[n_items + lane];
+                const int fn = (int)(it & 0x7FFFFFFFu) + ((it >> 31) ? s.F : 0);
+                FaceSetup fs;
+                load_face(P, s.faces, fn, s.F, fs, ids);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    px[k] = ndc_to_pix(fs.x[k], is);
+                    py[k] = ndc_to_pix(fs.y[k], is);
+                    W.px[k][lane] = px[k];
+                    W.py[k][lane] = py[k];
+                }
+                W.fn[lane] = fn;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) W.acc[k][lane] = 0ull;
+            __syncwarp();
+            // ---- phase 1: enumerate crossings, emit tasks
+            int n_tasks = 0;
+            int span_id = have ? 0 : 6, d0 = 0;
+            Span sp;
+            if (have) {
+                span_setup(px, py, 0, 0, is, sp);
+                d0 = sp.d0_from;
+            }
+            while (__any_sync(0xffffffffu, span_id < 6)) {
+                bool t_out = false, t_in = false;
+                uint32_t tw = 0;
+                if (span_id < 6) {
+                    if (d0 > sp.d0_to) {
+                        span_id++;
+                        if (span_id < 6) {
+                            span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
+                            d0 = sp.d0_from;
+                        }
+                    } else {
+                        const int axis = span_id & 1;
+                        float d1_cross;
+                        int d1_in, d1_out;
+                        if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) {
+                            int from, to;
+                            out_scan_range(sp.direction, d1_out, is, &from, &to);
+                            const int lo = (axis == 0) ? m.col_lo[d0] : m.row_lo[d0];
+                            const int hi = (axis == 0) ? m.col_hi[d0] : m.row_hi[d0];
+                            t_out = max(from, lo) <= min(to, hi);
+                            const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
+                            t_in = !alpha_at(m, r_out, c_out);
+                            tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
+                                 ((uint32_t)d0 << 9);
+                        }
+                        d0++;
+                    }
+                }
+                const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
+                if (t_out) W.tasks[n_tasks + __popc(mo & lt_mask)] = tw;
+                if (t_in) W.tasks[n_tasks + __popc(mo) + __popc(mi & lt_mask)] = tw | (1u << 8);
+                n_tasks += __popc(mo) + __popc(mi);
+                __syncwarp();
+                while (n_tasks >= 32) {
+                    n_tasks -= 32;
+                    bwd_task(W.tasks[n_tasks + lane], W, m, s.eps, fpscale);
+                    __syncwarp();
+                }
+            }
+            if (lane < n_tasks) bwd_task(W.tasks[lane], W, m, s.eps, fpscale);
+            __syncwarp();
+            // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
+            if (have) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float gu = -(float)((double)(long long)W.acc[2 * k][lane] * (double)fpinv);
+                    const float gv = -(float)((double)(long long)W.acc[2 * k + 1][lane] * (double)fpinv);
+                    if (gu == 0.0f && gv == 0.0f) continue;
+                    float c[3], vo[3], gc[3];
+                    if (FUSED) {
+                        for (int i = 0; i < 3; i++) vo[i] = verts_src[3 * ids[k] + i];
+                        transform_vertex(vo, s_abs, Rm, Tm, c);
+                    } else {
+                        const float* src = verts_src + ((size_t)b * s.V + ids[k]) * 3;
+                        c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
+                    }
+                    project_vertex_backward(c, Km, s.orig_size, gu, gv, gc);
+                    if (FUSED) {
+                        for (int j = 0; j < 3; j++) acc[j] += gc[j];
+                        for (int i = 0; i < 3; i++)
+                            for (int j = 0; j < 3; j++) acc[3 + 3 * i + j] += (s_abs * vo[i]) * gc[j];
+                        float dot = 0.0f;
+                        for (int j = 0; j < 3; j++)
+                            dot += (vo[0] * Rm[j] + vo[1] * Rm[3 + j] + vo[2] * Rm[6 + j]) * gc[j];
+                        acc[12] += dot;
+                    } else {
+                        float* dst = grad_verts + ((size_t)b * s.V + ids[k]) * 3;
+                        atomicAdd(dst + 0, gc[0]);
+                        atomicAdd(dst + 1, gc[1]);
+                        atomicAdd(dst + 2, gc[2]);
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
     if (FUSED) {
 #pragma unroll
         for (int i = 0; i < 13; i++)
             for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        if ((tid & 31) == 0)
-            for (int i = 0; i < 13; i++) red[tid >> 5][i] = acc[i];
+        if (lane == 0)
+            for (int i = 0; i < 13; i++) red[warp][i] = acc[i];
         __syncthreads();
         if (tid < 16) {
             float t = 0.0f;
             if (tid < 13)
-                for (int w = 0; w < kThreads / 32; w++) t += red[w][tid];
+                for (int w = 0; w < kBwdWarps; w++) t += red[w][tid];
             partials[((size_t)b * nchunks + chunk) * 16 + tid] = t;
         }
     }
@@ -546,14 +796,14 @@ int check_sil(const dh_sil* s) {
         return fail(DH_ERR_UNSUPPORTED, "S=%d aa=%d: S must be a multiple of 32 and S*(aa?2:1) <= %d", s->S, s->aa,
                     kMaxIS);
     DH_REQUIRE(s->faces && s->K && s->proj && s->bin_count && s->bins && s->fidx && s->alpha_bits && s->pos_pool &&
-                   s->neg_pool, "dh_sil has a NULL buffer");
+                   s->neg_pool && s->gmax, "dh_sil has a NULL buffer");
     DH_REQUIRE(s->B <= 65535, "B > 65535 frames per call (grid.y limit); shard the sequence");
     return DH_OK;
 }
 
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(3 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
+    return (size_t)(2 * is * (is / 32) + 2 * s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
 }
 
 template <typename KernelT>
@@ -656,6 +906,7 @@ extern "C" {
 
 int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out8) {
     DH_REQUIRE(out8 != nullptr && B > 0 && V > 0 && F > 0 && S > 0, "bad arguments");
+    out8[8] = (int64_t)B * 4;
     const int64_t is = aa ? 2 * S : S;
     const int64_t nstrips = (is + kSH - 1) / kSH, wprp = (S + 31) / 32;
     out8[0] = (int64_t)B * V * 4 * 4;
@@ -698,8 +949,9 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     cudaStream_t st = (cudaStream_t)stream;
     const long long ncell = (long long)s->B * s->S * s->S;
     DH_CUDA(cudaMemsetAsync(grad_verts, 0, (size_t)s->B * s->V * 3 * sizeof(float), st));
-    k_grad_signs<<<(unsigned)((ncell + kThreads - 1) / kThreads), kThreads, 0, st>>>(grad_rend, s->pos_pool,
-                                                                                     s->neg_pool, ncell);
+    DH_CUDA(cudaMemsetAsync(s->gmax, 0, (size_t)s->B * sizeof(float), st));
+    k_grad_signs<<<(unsigned)((ncell + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+        grad_rend, s->pos_pool, s->neg_pool, s->gmax, ncell, s->S * s->S, s->aa ? 0.25f : 1.0f);
     DH_LAUNCH_OK("k_grad_signs");
     dh_sil t = *s;
     t.gpool = const_cast<float*>(grad_rend);

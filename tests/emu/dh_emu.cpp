@@ -14,15 +14,6 @@ using namespace dh;
 
 static const int kSH = 16;
 
-static uint32_t spread16(uint32_t x) {
-    x &= 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x | (x << 1);
-}
-
 static void load_face(const float* P, const int32_t* faces, int fn, int F, FaceSetup& fs, int* ids) {
     const int w = fn >= F;
     const int f = w ? fn - F : fn;
@@ -209,7 +200,9 @@ void emu_backward(const float* proj, const int32_t* faces, const int32_t* fidx, 
             for (int c = 0; c < is; c++)
                 if ((s_neg[(size_t)r * wpr + (c >> 5)] >> (c & 31)) & 1u) s_negT[(size_t)c * wpr + (r >> 5)] |= 1u << (r & 31);
         BwdMaps m;
-        m.alpha = s_alpha.data(); m.neg = s_neg.data(); m.negT = s_negT.data();
+        m.alpha = s_alpha.data(); m.neg = (b & 1) ? s_neg.data() : nullptr; m.negT = s_negT.data();
+        m.neg_pool = gn;  // odd frames use the stored row-major bitmap, even frames the on-the-fly derivation
+        m.row_lo = m.row_hi = m.col_lo = m.col_hi = nullptr;
         m.pos_pool = pos_pool + (size_t)b * S * wprp;
         m.gpool = gpool + (size_t)b * S * S;
         m.fidx = fidx + (size_t)b * is * is;
