@@ -177,6 +177,14 @@ struct FaceSetup {
     int x_lo, x_hi, y_lo, y_hi;  // conservative pixel bounding box, clamped to the image (empty if culled)
 };
 
+#define kBoxSlack 0.015625f
+
+#if defined(__CUDA_ARCH__)
+#define DH_APPROX_DIV(a, b) __fdividef((a), (b))
+#else
+#define DH_APPROX_DIV(a, b) ((a) / (b))
+#endif
+
 // Conservative pixel bbox of a face; false if the face cannot produce a recorded pixel (back side, non-finite
 // coordinates or fully off-screen).
 DH_HD bool face_bbox(const float* x, const float* y, int is, int* x_lo, int* x_hi, int* y_lo, int* y_hi) {
@@ -189,8 +197,10 @@ DH_HD bool face_bbox(const float* x, const float* y, int is, int* x_lo, int* x_h
     const float xmax = fminf(fmaxf(fmaxf(px0, fmaxf(px1, px2)), -3.0f), lim);
     const float ymin = fminf(fmaxf(fminf(py0, fminf(py1, py2)), -3.0f), lim);
     const float ymax = fminf(fmaxf(fmaxf(py0, fmaxf(py1, py2)), -3.0f), lim);
-    int xl = (int)ceilf(xmin) - 1, xh = (int)floorf(xmax) + 1;
-    int yl = (int)ceilf(ymin) - 1, yh = (int)floorf(ymax) + 1;
+    // A pixel centre can pass the three fp32 edge tests only within ~1e-6 px of the exact triangle (rounding of
+    // the edge functions near the face), so 1/64 px of slack around the vertices' bounding box is conservative.
+    int xl = (int)ceilf(xmin - kBoxSlack), xh = (int)floorf(xmax + kBoxSlack);
+    int yl = (int)ceilf(ymin - kBoxSlack), yh = (int)floorf(ymax + kBoxSlack);
     if (xl < 0) xl = 0;
     if (yl < 0) yl = 0;
     if (xh > is - 1) xh = is - 1;
@@ -219,6 +229,29 @@ DH_HD void face_inverse(FaceSetup& f, int is) {
     den = den + p[0][0] * (p[1][1] - p[2][1]);
     den = den + p[1][0] * (p[2][1] - p[0][1]);
     for (int k = 0; k < 9; k++) f.inv[k] = fi[k] / den;
+}
+
+// Conservative pixel interval [xa, xb] of row `yp` (NDC) that can pass the three edge tests, clipped to
+// [x_lo, x_hi]: every edge with dy != 0 bounds x from one side.  Only a pre-filter -- pixel_inside still decides --
+// so approximate division plus 1/64 px of slack is enough.
+DH_HD void row_span(const FaceSetup& f, float yp, int is, int x_lo, int x_hi, int* xa, int* xb) {
+    float lo = -3.0e38f, hi = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i + 1) % 3;
+        const float dx = f.x[j] - f.x[i], dy = f.y[j] - f.y[i];
+        if (dy != 0.0f) {
+            const float xb_ = f.x[i] + DH_APPROX_DIV((yp - f.y[i]) * dx, dy);
+            if (dy > 0.0f) hi = fminf(hi, xb_);
+            else           lo = fmaxf(lo, xb_);
+        }
+    }
+    // NDC -> pixel coordinates, clamped so the int conversion is safe
+    const float plo = fminf(fmaxf(0.5f * (lo * (float)is + (float)is - 1.0f), -2.0f), (float)(is + 2));
+    const float phi = fminf(fmaxf(0.5f * (hi * (float)is + (float)is - 1.0f), -2.0f), (float)(is + 2));
+    const int a = (int)ceilf(plo - kBoxSlack), b = (int)floorf(phi + kBoxSlack);
+    *xa = a > x_lo ? a : x_lo;
+    *xb = b < x_hi ? b : x_hi;
 }
 
 // true if pixel centre (xp,yp) [NDC] is not rejected by any of the three edge tests
@@ -398,6 +431,21 @@ DH_HD void edge_terms(float diff, int d0, int d1, float d1_cross, float p00, flo
         dist = (0.0f < dist) ? dist + eps : dist - eps;
         *tb = diff / dist;
     }
+}
+
+// The same two terms with the per-crossing factors hoisted out of the pixel loop (kernel path).  The final
+// quotient uses the approximate divider on the device: gradients carry a 1e-3 bar, not a bit-exact one.
+struct EdgeCoef { float ka, kb; };  // 0 where the reference skips the term (edge end point exactly on the line)
+DH_HD void edge_coefs(float p00, float p10, int d0, EdgeCoef& c) {
+    c.ka = (p10 != (float)d0) ? (p10 - p00) / (p10 - (float)d0) : 0.0f;
+    c.kb = (p00 != (float)d0) ? (p10 - p00) / ((float)d0 - p00) : 0.0f;
+}
+DH_HD float edge_term_fast(float k, float diff, int d1, float d1_cross, float eps, float two_over_is, bool pow2,
+                           int is) {
+    const float t = k * ((float)d1 - d1_cross);
+    float dist = pow2 ? t * two_over_is : (t * 2.0f) / (float)is;
+    dist = (0.0f < dist) ? dist + eps : dist - eps;
+    return DH_APPROX_DIV(diff, dist);
 }
 
 // Pseudo-gradient of the loss w.r.t. the NDC (x,y) of the three vertices of face `fn`, one face per call (the

@@ -109,7 +109,7 @@ k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const
           int V, int32_t* __restrict__ bin_count, int nstrips, int32_t* __restrict__ loss_counts) {
     const int b = blockIdx.y;
     if (blockIdx.x == 0) {
-        if ((int)threadIdx.x < nstrips) bin_count[b * nstrips + threadIdx.x] = 0;
+        if ((int)threadIdx.x < 2 * nstrips) bin_count[b * nstrips * 2 + threadIdx.x] = 0;
         if (loss_counts != nullptr && threadIdx.x < 4) loss_counts[b * 4 + threadIdx.x] = 0;
     }
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,27 +133,62 @@ k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const
 }
 
 // ------------------------------------------------------------------------------------------------ binning
+// Each (frame, strip) bin holds two groups: faces in their given winding (fn < F) fill the bin from the front,
+// reversed windings (fn >= F) from the back.  For an outward-oriented closed mesh the first group is the near
+// side of the object, so rasterising it first lets the depth pre-test skip most of the second group.
+// bin_count: [B, nstrips, 2].  Counters are first accumulated per CTA in shared memory, so the global atomics
+// are one per (CTA, strip, group) instead of one per face.
+constexpr int kMaxStrips = kMaxIS / kSH;
+
 __global__ void __launch_bounds__(kThreads)
 k_setup_bin(const float4* __restrict__ proj, const int32_t* __restrict__ faces, int V, int F, int is,
             int nstrips, int32_t* __restrict__ bin_count, int32_t* __restrict__ bins) {
+    __shared__ int s_cnt[kMaxStrips][2];
+    __shared__ int s_base[kMaxStrips][2];
     const int b = blockIdx.y;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const float4* P = proj + (size_t)b * V;
-    const float4 a0 = P[faces[3 * f + 0]], a1 = P[faces[3 * f + 1]], a2 = P[faces[3 * f + 2]];
+    const int tid = threadIdx.x;
+    if (tid < 2 * kMaxStrips) (&s_cnt[0][0])[tid] = 0;
+    __syncthreads();
+    // up to 2 windings x 2 strips are kept in registers; anything beyond goes straight to the global counters
+    int e_fn[4], e_strip[4], e_slot[4], ne = 0;
+    if (f < F) {
+        const float4* P = proj + (size_t)b * V;
+        const float4 a0 = P[faces[3 * f + 0]], a1 = P[faces[3 * f + 1]], a2 = P[faces[3 * f + 2]];
 #pragma unroll
-    for (int w = 0; w < 2; w++) {
-        float x[3], y[3];
-        x[0] = w ? a2.x : a0.x; y[0] = w ? a2.y : a0.y;
-        x[1] = a1.x;            y[1] = a1.y;
-        x[2] = w ? a0.x : a2.x; y[2] = w ? a0.y : a2.y;
-        int xl, xh, yl, yh;
-        if (!face_bbox(x, y, is, &xl, &xh, &yl, &yh)) continue;
-        const int fn = f + w * F;
-        for (int s = yl / kSH; s <= yh / kSH; s++) {
-            const int slot = atomicAdd(&bin_count[b * nstrips + s], 1);
-            bins[((size_t)b * nstrips + s) * (size_t)(2 * F) + slot] = fn;
+        for (int w = 0; w < 2; w++) {
+            float x[3], y[3];
+            x[0] = w ? a2.x : a0.x; y[0] = w ? a2.y : a0.y;
+            x[1] = a1.x;            y[1] = a1.y;
+            x[2] = w ? a0.x : a2.x; y[2] = w ? a0.y : a2.y;
+            int xl, xh, yl, yh;
+            if (!face_bbox(x, y, is, &xl, &xh, &yl, &yh)) continue;
+            const int fn = f + w * F;
+            for (int st = yl / kSH; st <= yh / kSH; st++) {
+                if (ne < 4) {
+                    e_fn[ne] = fn; e_strip[ne] = st;
+                    e_slot[ne] = atomicAdd(&s_cnt[st][w], 1);
+                    ne++;
+                } else {
+                    const int slot = atomicAdd(&bin_count[(b * nstrips + st) * 2 + w], 1);
+                    int32_t* bin = bins + ((size_t)b * nstrips + st) * (size_t)(2 * F);
+                    bin[w ? 2 * F - 1 - slot : slot] = fn;
+                }
+            }
         }
+    }
+    __syncthreads();
+    if (tid < 2 * nstrips) {
+        const int st = tid >> 1, w = tid & 1;
+        const int c = s_cnt[st][w];
+        s_base[st][w] = c ? atomicAdd(&bin_count[(b * nstrips + st) * 2 + w], c) : 0;
+    }
+    __syncthreads();
+    for (int k = 0; k < ne; k++) {
+        const int w = e_fn[k] >= F;
+        const int slot = s_base[e_strip[k]][w] + e_slot[k];
+        int32_t* bin = bins + ((size_t)b * nstrips + e_strip[k]) * (size_t)(2 * F);
+        bin[w ? 2 * F - 1 - slot : slot] = e_fn[k];
     }
 }
 
@@ -172,9 +207,15 @@ __device__ __forceinline__ void load_face(const float4* __restrict__ P, const in
 }
 
 // Depth of one queued hit and the z-buffer update.  ent = slot | x << 5 | local_row << 15.
+// setup rows: inv[9], z[3], zcull (nearest vertex depth * (1 - 1e-5), or -inf when the bound does not apply).
 __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32], const int* fns,
                                            unsigned long long* zbuf, int is, int row0, float near, float far) {
     const int slot = ent & 31, xi = (ent >> 5) & 1023, yl = ent >> 15;
+    unsigned long long* cell = zbuf + yl * is + xi;
+    const unsigned long long cur = *cell;
+    // the face cannot be nearer than its nearest vertex (zp is a clamped, normalised harmonic blend of the three
+    // vertex depths, >= zmin * (1 - 1e-6)): skip the divisions if the pixel already holds something nearer
+    if (__uint_as_float((uint32_t)(cur >> 32)) < setup[12][slot]) return;
     FaceSetup f;
 #pragma unroll
     for (int k = 0; k < 9; k++) f.inv[k] = setup[k][slot];
@@ -183,8 +224,7 @@ __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32
     float zp;
     if (!pixel_depth(f, xi, row0 + yl, near, far, &zp)) return;
     const unsigned long long key = zkey(zp, fns[slot]);
-    unsigned long long* cell = zbuf + yl * is + xi;
-    if (key < *cell) atomicMin(cell, key);
+    if (key < cur) atomicMin(cell, key);
 }
 
 // FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
@@ -196,73 +236,126 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
     __shared__ uint32_t abits[kSH][kMaxIS / 32];
     __shared__ int red[3][kThreads / 32];
-    __shared__ float s_setup[kThreads / 32][12][32];  // per warp: inv[9], z[3] of the 32 faces of the batch
+    __shared__ float s_ndc[kMaxIS];                    // NDC coordinate of every pixel centre
+    __shared__ float s_setup[kThreads / 32][13][32];   // per warp: inv[9], z[3], zcull of the batch's faces
+    __shared__ float s_geo[kThreads / 32][6][32];      // per warp: NDC x[3], y[3]
+    __shared__ uint32_t s_box[kThreads / 32][32];      // x_lo | x_hi << 10 | local first row << 20
+    __shared__ int s_start[kThreads / 32][32];         // first row-item of every face of the batch
     __shared__ int s_fn[kThreads / 32][32];
-    __shared__ uint32_t s_queue[kThreads / 32][64];   // pending (lane slot, x, local row) hits
+    __shared__ uint32_t s_queue[kThreads / 32][64];    // pending (lane slot, x, local row) hits
+    __shared__ int s_next;
     const int is = raster_size(s);
     const int nstrips = is / kSH;
     const int strip = blockIdx.x, b = blockIdx.y;
     const int row0 = strip * kSH;
     const int tid = threadIdx.x;
     for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    for (int i = tid; i < is; i += kThreads) s_ndc[i] = pix_to_ndc(i, is);
+    if (tid == 0) s_next = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
     __syncthreads();
 
-    const int count = s.bin_count[b * nstrips + strip];
     const int32_t* bin = s.bins + ((size_t)b * nstrips + strip) * (size_t)(2 * s.F);
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
-    // Warp-synchronous batches of 32 bin entries.  Each lane sets up one face and walks its clipped bounding box
-    // doing only the (cheap) edge tests; pixels that pass are compacted into a per-warp queue, and whenever 32
-    // are pending the whole warp evaluates their depths (the expensive IEEE divisions) at full lane occupancy.
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int base = warp * 32; base < count; base += (kThreads / 32) * 32) {
-        const int e = base + lane;
-        FaceSetup fs;
-        int npix = 0, bw = 1, x_lo = 0, r_lo = 0;
-        if (e < count) {
-            const int fn = bin[e];
-            int ids[3];
-            load_face(P, s.faces, fn, s.F, fs, ids);
-            if (face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) {
-                face_inverse(fs, is);
-                r_lo = max(fs.y_lo, row0);
-                const int r_hi = min(fs.y_hi, row0 + kSH - 1);
-                x_lo = fs.x_lo;
-                bw = fs.x_hi - fs.x_lo + 1;
-                npix = (r_hi >= r_lo) ? bw * (r_hi - r_lo + 1) : 0;
+    // Two passes (given windings, then reversed windings), warp-synchronous batches of 32 bin entries handed out
+    // dynamically.  Per batch: (1) lane = face: set-up; (2) lane = (face, row): analytic x-span of the row, then
+    // the exact edge tests pixel by pixel, survivors compacted into a per-warp queue; (3) whenever 32 hits are
+    // pending, lane = hit: depth (the expensive IEEE divisions) and z-buffer update at full lane occupancy.
+    for (int pass = 0; pass < 2; pass++) {
+        const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_next, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= count) break;
+            const int e = base + lane;
+            int nrows = 0;
+            if (e < count) {
+                const int fn = pass ? bin[2 * s.F - 1 - e] : bin[e];
+                FaceSetup fs;
+                int ids[3];
+                load_face(P, s.faces, fn, s.F, fs, ids);
+                if (face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) {
+                    face_inverse(fs, is);
+                    const int r_lo = max(fs.y_lo, row0), r_hi = min(fs.y_hi, row0 + kSH - 1);
+                    nrows = max(r_hi - r_lo + 1, 0);
 #pragma unroll
-                for (int k = 0; k < 9; k++) s_setup[warp][k][lane] = fs.inv[k];
+                    for (int k = 0; k < 9; k++) s_setup[warp][k][lane] = fs.inv[k];
 #pragma unroll
-                for (int k = 0; k < 3; k++) s_setup[warp][9 + k][lane] = fs.z[k];
-                s_fn[warp][lane] = fn;
+                    for (int k = 0; k < 3; k++) {
+                        s_setup[warp][9 + k][lane] = fs.z[k];
+                        s_geo[warp][k][lane] = fs.x[k];
+                        s_geo[warp][3 + k][lane] = fs.y[k];
+                    }
+                    const float zmin = fminf(fs.z[0], fminf(fs.z[1], fs.z[2]));
+                    s_setup[warp][12][lane] = (zmin > 0.0f) ? zmin * (1.0f - 1e-5f) : -3.0e38f;
+                    s_box[warp][lane] = (uint32_t)fs.x_lo | ((uint32_t)fs.x_hi << 10) | ((uint32_t)(r_lo - row0) << 20);
+                    s_fn[warp][lane] = fn;
+                }
             }
-        }
-        __syncwarp();
-        int qn = 0, i = 0, xi = x_lo, yi = r_lo;
-        while (__any_sync(0xffffffffu, i < npix)) {
-            bool hit = false;
-            uint32_t ent = 0;
-            if (i < npix) {
-                hit = pixel_inside(fs, pix_to_ndc(xi, is), pix_to_ndc(yi, is));
-                ent = (uint32_t)lane | ((uint32_t)xi << 5) | ((uint32_t)(yi - row0) << 15);
-                i++;
-                if (++xi >= x_lo + bw) { xi = x_lo; yi++; }
+            int incl = nrows;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-            if (hit) s_queue[warp][qn + __popc(hits & lt_mask)] = ent;
-            qn += __popc(hits);
+            s_start[warp][lane] = incl - nrows;
+            const int total_rows = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
-            if (qn >= 32) {
-                qn -= 32;
-                raster_hit(s_queue[warp][qn + lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
-                __syncwarp();
+            int qn = 0;
+            for (int it0 = 0; it0 < total_rows; it0 += 32) {
+                const int it = it0 + lane;
+                int xi = 1, xb = 0, slot = 0, rl = 0;
+                FaceSetup fs;
+                float yp = 0.0f;
+                if (it < total_rows) {
+                    // last face whose first row-item is <= it (faces without rows share their successor's start)
+                    int lo = 0, hi = 31;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (s_start[warp][mid] <= it) lo = mid; else hi = mid - 1;
+                    }
+                    slot = lo;
+                    const uint32_t box = s_box[warp][slot];
+                    rl = (int)(box >> 20) + (it - s_start[warp][slot]);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        fs.x[k] = s_geo[warp][k][slot];
+                        fs.y[k] = s_geo[warp][3 + k][slot];
+                    }
+                    yp = s_ndc[row0 + rl];
+                    row_span(fs, yp, is, (int)(box & 1023u), (int)((box >> 10) & 1023u), &xi, &xb);
+                }
+                while (__any_sync(0xffffffffu, xi <= xb)) {
+                    bool hit = false;
+                    uint32_t ent = 0;
+                    if (xi <= xb) {
+                        hit = pixel_inside(fs, s_ndc[xi], yp);
+                        ent = (uint32_t)slot | ((uint32_t)xi << 5) | ((uint32_t)rl << 15);
+                        xi++;
+                    }
+                    const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+                    if (hit) s_queue[warp][qn + __popc(hits & lt_mask)] = ent;
+                    qn += __popc(hits);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        raster_hit(s_queue[warp][qn + lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_,
+                                   s.far_);
+                        __syncwarp();
+                    }
+                }
             }
+            if (lane < qn) raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
+            __syncwarp();
         }
-        if (lane < qn) raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
-        __syncwarp();
+        __syncthreads();
+        if (tid == 0) s_next = 0;
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- epilogue 1: face index map + coverage bitmap (one warp = 32 consecutive pixels of a row)
     const int wpr = is >> 5;
@@ -391,6 +484,10 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
     int d1_in, d1_out;
     span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out);
     const int fn = W.fn[slot];
+    EdgeCoef ec;
+    edge_coefs(sp.p00, sp.p10, d0, ec);
+    const bool pow2 = (is & (is - 1)) == 0;
+    const float two_over_is = 2.0f / (float)is;
     long long sa = 0, sb = 0;
     if (kind == 0) {
         const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
@@ -410,10 +507,10 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
                     const float g = (axis == 0) ? grad_at(m, d1, d0) : grad_at(m, d0, d1);
                     const float diff = (0.0f - 1.0f) * g;
                     if (diff <= 0.0f) continue;
-                    float ta, tb;
-                    edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
-                    sa += __float2ll_rn(ta * fpscale);
-                    sb += __float2ll_rn(tb * fpscale);
+                    if (ec.ka != 0.0f)
+                        sa += __float2ll_rn(edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
+                    if (ec.kb != 0.0f)
+                        sb += __float2ll_rn(edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
                 }
             }
         }
@@ -427,10 +524,10 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
             if (m.fidx[r * is + c] != fn) continue;
             const float diff = (1.0f - 0.0f) * grad_at(m, r, c);
             if (diff <= 0.0f) continue;
-            float ta, tb;
-            edge_terms(diff, d0, d1, d1_cross, sp.p00, sp.p10, eps, is, &ta, &tb);
-            sa += __float2ll_rn(ta * fpscale);
-            sb += __float2ll_rn(tb * fpscale);
+            if (ec.ka != 0.0f)
+                sa += __float2ll_rn(edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
+            if (ec.kb != 0.0f)
+                sb += __float2ll_rn(edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
         }
     }
     atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], sa);
@@ -448,6 +545,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     __shared__ float red[kBwdWarps][13];
     __shared__ int16_t s_rng[4][kMaxIS];  // row_lo, row_hi, col_lo, col_hi
     __shared__ BwdWarp s_warp[kBwdWarps];
+    __shared__ int s_next_group;
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
@@ -465,6 +563,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
         for (int i = tid; i < is * wpr; i += kThreads) s_alpha[i] = ga[i];
         for (int i = tid; i < S * wprp; i += kThreads) { s_pos[i] = gp[i]; s_negp[i] = gn[i]; }
+        if (tid == 0) s_next_group = 0;
     }
     __syncthreads();
     // column-major copy of the "uncovered && grad < 0" bitmap: 32x32 bit-block transposes through ballots
@@ -541,8 +640,11 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     const int per = (s.F + nchunks - 1) / nchunks;
     const int f0 = chunk * per, f1 = min(s.F, f0 + per);
     int n_items = 0;
-    // the warp owns faces f0 + warp*32 + [0,32) + k * (warps*32)
-    for (int fbase = f0 + warp * 32; (fbase < f1 || n_items > 0) && gmax > 0.0f; fbase += kBwdWarps * 32) {
+    // groups of 32 faces are handed to the warps dynamically; a warp that finds no group left flushes its items
+    for (bool more = gmax > 0.0f; more;) {
+        int fbase = 0;
+        if (lane == 0) fbase = f0 + atomicAdd(&s_next_group, 32);
+        fbase = __shfl_sync(0xffffffffu, fbase, 0);
         // ---- gather front-facing (face, winding) items of the next 32 faces
         if (fbase < f1) {
             const int f = fbase + lane;
@@ -560,7 +662,8 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             n_items += __popc(m0) + __popc(m1);
             __syncwarp();
         }
-        const bool last = fbase + kBwdWarps * 32 >= f1;
+        const bool last = fbase >= f1;
+        more = !last;
         // ---- process full batches of 32 items (and the remainder at the very end)
         while (n_items >= 32 || (last && n_items > 0)) {
             const int nb = min(n_items, 32);
@@ -808,7 +911,8 @@ size_t bwd_smem_bytes(const dh_sil& s) {
 
 template <typename KernelT>
 int set_smem(KernelT kernel, size_t bytes) {
-    if (bytes > 48 * 1024) DH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // always: static + dynamic shared memory together may exceed the 48 KB default even when `bytes` does not
+    DH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return DH_OK;
 }
 
@@ -910,7 +1014,7 @@ int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa,
     const int64_t is = aa ? 2 * S : S;
     const int64_t nstrips = (is + kSH - 1) / kSH, wprp = (S + 31) / 32;
     out8[0] = (int64_t)B * V * 4 * 4;
-    out8[1] = (int64_t)B * nstrips * 4;
+    out8[1] = (int64_t)B * nstrips * 2 * 4;
     out8[2] = (int64_t)B * nstrips * 2 * F * 4;
     out8[3] = (int64_t)B * is * is * 4;
     out8[4] = (int64_t)B * is * (is / 32) * 4;

@@ -50,8 +50,8 @@ typedef struct dh_sil {
     const float* K;                    /* [B,3,3] ROI intrinsics in unit-image coordinates                       */
     /* scratch, caller-allocated (sizes from dh_sil_scratch_bytes, in this order) */
     float* proj;                       /* [B,V,4]  NDC u, v, depth z, pad                                        */
-    int32_t* bin_count;                /* [B,nstrips]                                                            */
-    int32_t* bins;                     /* [B,nstrips,2F]                                                         */
+    int32_t* bin_count;                /* [B,nstrips,2] entries per (strip, winding group)                       */
+    int32_t* bins;                     /* [B,nstrips,2F] given windings from the front, reversed from the back   */
     int32_t* fidx;                     /* [B,is,is] face index map (-1 none), rasteriser row order               */
     uint32_t* alpha_bits;              /* [B,is,is/32] coverage bitmap, rasteriser row order                     */
     uint32_t* pos_pool;                /* [B,S,ceil(S/32)] bitmap: dL/drend > 0                                  */

@@ -93,7 +93,9 @@ void emu_raster(const float* proj, const int32_t* faces, int B, int V, int F, in
                 const int r_hi = fs.y_hi < row0 + kSH - 1 ? fs.y_hi : row0 + kSH - 1;
                 for (int yi = r_lo; yi <= r_hi; yi++) {
                     const float yp = pix_to_ndc(yi, is);
-                    for (int xi = fs.x_lo; xi <= fs.x_hi; xi++) {
+                    int xa, xb;
+                    row_span(fs, yp, is, fs.x_lo, fs.x_hi, &xa, &xb);
+                    for (int xi = xa; xi <= xb; xi++) {
                         const float xp = pix_to_ndc(xi, is);
                         if (!pixel_inside(fs, xp, yp)) continue;
                         float zp;

@@ -110,3 +110,34 @@ def test_emu_smoothness_closed_form_sharded_equals_unsharded():
     a = E.smooth_terms(seq["rot6d_init"][:4], seq["T_init"][:4], 1.0, mom, V, 7, 10.0, None, pose[4])
     b = E.smooth_terms(seq["rot6d_init"][4:], seq["T_init"][4:], 1.0, mom, V, 7, 10.0, pose[3], None)
     assert np.array_equal(np.concatenate([a, b]), st)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_emu_raster_triangle_soup_vs_bruteforce_oracle(seed):
+    """Edge cases of the binned / span-filtered rasteriser against the brute-force oracle: slivers, degenerate
+    (collinear, repeated-vertex) faces, faces partly or fully off-screen, behind the near plane, exact depth ties,
+    vertices exactly on pixel centres."""
+    rng = np.random.default_rng(seed)
+    V, F, is_ = 60, 150, 64
+    proj = np.zeros((1, V, 4), np.float32)
+    proj[0, :, 0] = rng.uniform(-1.3, 1.3, V)
+    proj[0, :, 1] = rng.uniform(-1.3, 1.3, V)
+    proj[0, :, 2] = rng.uniform(0.05, 3.0, V)
+    # a few vertices exactly on pixel centres / with identical depth (ties)
+    proj[0, :8, 0] = (2 * rng.integers(0, is_, 8) + 1 - is_) / is_
+    proj[0, :8, 1] = (2 * rng.integers(0, is_, 8) + 1 - is_) / is_
+    proj[0, 8:20, 2] = 1.0
+    faces = rng.integers(0, V, size=(F, 3)).astype(np.int32)
+    faces[:10, 2] = faces[:10, 1]                      # repeated vertex
+    for k in range(10, 25):                            # slivers: third vertex almost on the edge
+        a, b = proj[0, faces[k, 0]], proj[0, faces[k, 1]]
+        t = rng.uniform(-0.2, 1.2)
+        proj[0, V - 1 - (k - 10), :2] = a[:2] + t * (b[:2] - a[:2]) + rng.normal(size=2) * 1e-6
+        faces[k, 2] = V - 1 - (k - 10)
+    fidx, abits = E.raster(proj, faces, is_)
+    faces2 = np.concatenate([faces, faces[:, ::-1]], 0)
+    fv = proj[:, :, :3][np.arange(1)[:, None, None], faces2[None]]
+    maps = nr_oracle.rasterize_forward_np(fv, is_)
+    assert np.array_equal(maps["face_index"], fidx)
+    assert np.array_equal(unpack_alpha(abits), maps["alpha"] > 0.5)
+    assert (fidx >= 0).mean() > 0.2
