@@ -471,8 +471,29 @@ __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long lon
     if (v != 0) atomicAdd(a, (unsigned long long)v);
 }
 
+// dL/d(raster pixel) at (r, c).  Fused path: rebuilt from the staged coverage bitmap exactly as k_raster's
+// epilogue computed it (gpool = gcoef * (k * 0.5), k = keep * (pop - 4 ref)), so the pixel loops never wait on
+// global memory.  `wanted` tells which sign bitmap selected the pixel: true -> k = pop - 4 (< 0, object missing),
+// false -> k = pop (> 0, object where background is wanted).  API path: the caller's gradient map.
+template <bool FUSED>
+__device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool wanted, float gcoef) {
+    if (!FUSED) return grad_at(m, r, c);
+    int pop;
+    if (m.aa) {
+        const int sh = c & 30;
+        const uint32_t w0 = m.alpha[(r & ~1) * m.wpr + (c >> 5)], w1 = m.alpha[(r | 1) * m.wpr + (c >> 5)];
+        pop = __popc((w0 >> sh) & 3u) + __popc((w1 >> sh) & 3u);
+    } else {
+        pop = 4 * (int)((m.alpha[r * m.wpr + (c >> 5)] >> (c & 31)) & 1u);
+    }
+    const int k = wanted ? pop - 4 : pop;
+    return (gcoef * ((float)k * 0.5f)) * m.gscale;
+}
+
 // phase 2: one task per lane
-__device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale) {
+template <bool FUSED>
+__device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale,
+                                         float gcoef) {
     const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1, d0 = (int)(t >> 9);
     const int is = m.is;
     float px[3], py[3];
@@ -504,7 +525,8 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
                 while (bits) {
                     const int d1 = (w << 5) + ctz32(bits);
                     bits &= bits - 1;
-                    const float g = (axis == 0) ? grad_at(m, d1, d0) : grad_at(m, d0, d1);
+                    const float g = (axis == 0) ? grad_value<FUSED>(m, d1, d0, true, gcoef)
+                                                : grad_value<FUSED>(m, d0, d1, true, gcoef);
                     const float diff = (0.0f - 1.0f) * g;
                     if (diff <= 0.0f) continue;
                     if (ec.ka != 0.0f)
@@ -522,7 +544,7 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
             if (!alpha_at(m, r, c)) continue;
             if (!pos_at(m, r, c)) continue;
             if (m.fidx[r * is + c] != fn) continue;
-            const float diff = (1.0f - 0.0f) * grad_at(m, r, c);
+            const float diff = (1.0f - 0.0f) * grad_value<FUSED>(m, r, c, false, gcoef);
             if (diff <= 0.0f) continue;
             if (ec.ka != 0.0f)
                 sa += __float2ll_rn(edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
@@ -540,12 +562,11 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kThreads)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
-           float* __restrict__ grad_verts, int nchunks) {
+           float* __restrict__ grad_verts, int nchunks, float gcoef) {
     extern __shared__ uint32_t smw[];
     __shared__ float red[kBwdWarps][13];
     __shared__ int16_t s_rng[4][kMaxIS];  // row_lo, row_hi, col_lo, col_hi
     __shared__ BwdWarp s_warp[kBwdWarps];
-    __shared__ int s_next_group;
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
@@ -563,7 +584,6 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
         for (int i = tid; i < is * wpr; i += kThreads) s_alpha[i] = ga[i];
         for (int i = tid; i < S * wprp; i += kThreads) { s_pos[i] = gp[i]; s_negp[i] = gn[i]; }
-        if (tid == 0) s_next_group = 0;
     }
     __syncthreads();
     // column-major copy of the "uncovered && grad < 0" bitmap: 32x32 bit-block transposes through ballots
@@ -640,11 +660,11 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     const int per = (s.F + nchunks - 1) / nchunks;
     const int f0 = chunk * per, f1 = min(s.F, f0 + per);
     int n_items = 0;
-    // groups of 32 faces are handed to the warps dynamically; a warp that finds no group left flushes its items
+    // groups of 32 faces go to the warps round-robin (a STATIC assignment: the per-thread float accumulators of the
+    // tail then see the same faces in the same order every run, which keeps the result bit-reproducible)
+    int fbase = f0 + warp * 32 - kBwdWarps * 32;
     for (bool more = gmax > 0.0f; more;) {
-        int fbase = 0;
-        if (lane == 0) fbase = f0 + atomicAdd(&s_next_group, 32);
-        fbase = __shfl_sync(0xffffffffu, fbase, 0);
+        fbase += kBwdWarps * 32;
         // ---- gather front-facing (face, winding) items of the next 32 faces
         if (fbase < f1) {
             const int f = fbase + lane;
@@ -731,11 +751,11 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                 __syncwarp();
                 while (n_tasks >= 32) {
                     n_tasks -= 32;
-                    bwd_task(W.tasks[n_tasks + lane], W, m, s.eps, fpscale);
+                    bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
                     __syncwarp();
                 }
             }
-            if (lane < n_tasks) bwd_task(W.tasks[lane], W, m, s.eps, fpscale);
+            if (lane < n_tasks) bwd_task<FUSED>(W.tasks[lane], W, m, s.eps, fpscale, gcoef);
             __syncwarp();
             // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
             if (have) {
@@ -961,7 +981,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
             rc = set_smem(k_backward<true>, sb);
             if (rc) return rc;
             k_backward<true><<<dim3(p.nchunks, B), kThreads, sb, st>>>(s, p.verts_og, p.Rmat, p.trans, p.scale,
-                                                                        p.partials, nullptr, p.nchunks);
+                                                                        p.partials, nullptr, p.nchunks, gcoef);
             DH_LAUNCH_OK("k_backward");
         }
     } else {
@@ -1064,7 +1084,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     if (rc) return rc;
     const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
     k_backward<false><<<dim3(nchunks, s->B), kThreads, sb, st>>>(t, verts_cam, nullptr, nullptr, nullptr, nullptr,
-                                                                  grad_verts, nchunks);
+                                                                  grad_verts, nchunks, 0.0f);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
 }
