@@ -1,0 +1,89 @@
+"""DINO template matching of ObjTracker's view selection on the B200 tensor cores.
+
+Replaces the two steps of pose_initializtion.py:286-321 that are data-parallel over templates and frames:
+    dino_cos = (cos_mask * sum(gt_feat * render_feats, -1) / (|gt_feat| |render_feats| + 1e-6)).sum(1) / cos_mask.sum(1)
+                                                                              pose_initializtion.py:295-296
+    torch.argmax(dino_cos) / torch.topk(dino_cos, k, largest=True)            pose_initializtion.py:299,309
+The scores depend only on (frame features, template bank), not on the previous frame, so all frames are scored in
+one GEMM; the sequential candidate gating (:300-321) stays on the host in `select_view`.
+Everything here needs CUDA tensors and the native library; there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .geometry import rotation_angle_difference
+
+
+def build_bank(feats, mask=None):
+    """feats [n,P,D] fp32 (CUDA) -> bf16 [n, P*D]: every patch vector divided by its norm (the reference
+    normalises with F.normalize and divides by the norms again, :226,293,296) and, for frames, weighted by
+    mask[n,p] / sum_p mask[n,:] (the nearest-resized foreground mask, :290,294).  Templates: mask=None."""
+    if not feats.is_cuda:
+        raise _lib.DynhorError("dynhor_b200.dino_match needs CUDA tensors (no CPU fallback)")
+    f = feats.detach().contiguous().float()
+    n, P, D = f.shape
+    if (P * D) % 8 != 0:
+        raise ValueError("P*D must be a multiple of 8")
+    m = None
+    if mask is not None:
+        m = mask.detach().reshape(n, P).contiguous().float()
+        if bool((m.sum(1) <= 0).any()):
+            raise ValueError("every frame mask needs at least one foreground patch")
+    out = torch.empty(n, P * D, dtype=torch.bfloat16, device=f.device)
+    _lib.check(_lib.load().dh_dino_prescale(_lib.ptr(f), _lib.ptr(m), n, P, D, _lib.ptr(out), _lib.stream_ptr()),
+               "dh_dino_prescale")
+    return out
+
+
+def dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
+    """frame_bank [Fm,K] bf16, templ_bank [N,K] bf16 (from build_bank) -> (dino_cos [Fm,N] fp32 or None,
+    topk values [Fm,k], topk indices [Fm,k] int64), largest first like torch.topk(largest=True)."""
+    if not (frame_bank.is_cuda and templ_bank.is_cuda):
+        raise _lib.DynhorError("dynhor_b200.dino_match needs CUDA tensors (no CPU fallback)")
+    assert frame_bank.dtype == torch.bfloat16 and templ_bank.dtype == torch.bfloat16
+    assert frame_bank.is_contiguous() and templ_bank.is_contiguous()
+    Fm, K = frame_bank.shape
+    N, K2 = templ_bank.shape
+    assert K == K2, "banks disagree on P*D"
+    lib = _lib.load()
+    nbytes = ctypes.c_int64()
+    _lib.check(lib.dh_dino_workspace_bytes(N, Fm, K, ctypes.byref(nbytes)), "dh_dino_workspace_bytes")
+    dev = frame_bank.device
+    ws = torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=dev)
+    scores = torch.empty(Fm, N, dtype=torch.float32, device=dev) if return_scores else None
+    vals = torch.empty(Fm, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(Fm, k, dtype=torch.int32, device=dev)
+    _lib.check(lib.dh_dino_topk(_lib.ptr(templ_bank), _lib.ptr(frame_bank), N, Fm, K, int(k), _lib.ptr(scores),
+                                _lib.ptr(vals), _lib.ptr(idx), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+               "dh_dino_topk")
+    return scores, vals, idx.long()
+
+
+def select_view(dino_cos, topk_indices, render_rotations, rotations_init=None, former_max_idx=None, use_former=True):
+    """Candidate gating of pose_initializtion.py:298-321 for ONE frame, on the scores / top-k computed above.
+    dino_cos [N]; topk_indices [>=10] (largest first); render_rotations [N,3,3]; rotations_init [1,3,3] = the
+    previous frame's optimised rotation.  Returns max_idx (int, -1 = keep the previous rotation)."""
+    if not use_former or rotations_init is None:
+        return int(topk_indices[0])
+    rel_angle_full = rotation_angle_difference(rotations_init.clone(), render_rotations.transpose(1, 2).clone())
+    if former_max_idx != -1:
+        former_rel_angle_full = rotation_angle_difference(
+            render_rotations[former_max_idx:former_max_idx + 1].transpose(1, 2).clone(),
+            render_rotations.transpose(1, 2).clone())
+        cos_topk_num = 5
+    else:
+        former_rel_angle_full = torch.zeros_like(rel_angle_full)
+        cos_topk_num = 10
+    indices = topk_indices[:cos_topk_num]
+    rel_angle = rel_angle_full[indices]
+    max_idx = indices[torch.argmin(rel_angle)].item()
+    if rel_angle_full[max_idx] > 85.0 or former_rel_angle_full[max_idx] > 85.0:
+        max_idx = -1
+    if max_idx == -1 and torch.min(rel_angle_full) < 15.0:
+        max_idx = int(torch.argmin(rel_angle_full))
+        if (former_max_idx != -1 and former_rel_angle_full[max_idx].item() > 30.0) or \
+                dino_cos[max_idx] < (torch.max(dino_cos) - torch.std(dino_cos)):
+            max_idx = -1
+    return int(max_idx)

@@ -266,3 +266,25 @@ def to_object_parameters(seq):
             "verts": torch.from_numpy(seq["verts"]).unsqueeze(0),
         })
     return params
+
+
+# ----------------------------------------------------------------------------- DINO features
+def make_dino_features(N, Fm, P, D, seed=0, noise=0.5, mask_p=0.4, k=10, min_gap=1e-3, device="cpu"):
+    """Synthetic patch features shaped like DINOv2 tokens: templates i.i.d. N(0,1), L2-normalised per patch and
+    rounded to bf16 precision; each frame = normalise(template[pi(f)] + noise * N(0,1)) so a unique best match
+    exists; Bernoulli(mask_p) foreground masks with at least one patch.  Returned as torch fp32 tensors holding
+    bf16-representable values (both the oracle and the kernels see the same numbers).  `min_gap` is checked by
+    the callers that own an oracle (top-k is only well-posed when consecutive scores differ by more than the
+    accumulation noise)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    perm = torch.randperm(N, generator=g)[:Fm] if Fm <= N else torch.randint(0, N, (Fm,), generator=g)
+    gen = torch.Generator(device=device).manual_seed(seed + 1)
+    templ = torch.randn(N, P, D, generator=gen, device=device)
+    templ = torch.nn.functional.normalize(templ, dim=-1).bfloat16().float()
+    frames = templ[perm.to(device)] + noise * torch.nn.functional.normalize(
+        torch.randn(Fm, P, D, generator=gen, device=device), dim=-1)
+    frames = torch.nn.functional.normalize(frames, dim=-1).bfloat16().float()
+    masks = (torch.rand(Fm, P, generator=gen, device=device) < mask_p).float()
+    masks[:, 0] = torch.where(masks.sum(1) == 0, torch.ones_like(masks[:, 0]), masks[:, 0])
+    return {"templ": templ, "frames": frames, "masks": masks, "match": perm}
