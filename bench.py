@@ -321,6 +321,59 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_dino(args):
+    """Secondary workload (BASELINE configs[3]): DINO ViT-S/14 patch-feature matching, 1k templates x 300 frames,
+    bf16 similarity GEMM (K = 1369*384) + fused top-10.  One JSON line; `value` = template-frame pairs / second."""
+    from dynhor_b200 import synth
+    from dynhor_b200.dino_match import build_bank, dino_cos_topk
+    N, Fm, P, D, k = 1000, 300, 1369, 384, 10
+    torch.cuda.set_device(0)
+    d = synth.make_dino_features(N, Fm, P, D, seed=0, device="cuda")
+    tb = build_bank(d["templ"])
+    fb = build_bank(d["frames"], d["masks"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        dino_cos_topk(fb, tb, k)
+    times = []
+    for _ in range(args.steps):
+        flush.zero_()                      # 256 MB write: evicts the banks from the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s, v, i = dino_cos_topk(fb, tb, k)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    flops = 2.0 * N * Fm * P * D
+    bytes_ = 2.0 * P * D * (N + Fm)
+    hbm, kind = measured_peaks()
+    tf_peak = 1606.8
+    try:
+        tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    ok = bool(torch.equal(i[:, 0].cpu(), d["match"]))
+    # CPU baseline: the reference expression verbatim on a bounded sample of frames
+    from oracle import dino_oracle
+    nf = 2
+    t0 = time.perf_counter()
+    dino_oracle.dino_cos_topk(d["frames"][:nf].cpu(), d["masks"][:nf].cpu(), d["templ"].cpu(), k)
+    cpu_s = (time.perf_counter() - t0) / nf
+    print(json.dumps({
+        "metric": "DINO template-frame pairs scored / second (bf16 GEMM + fused top-k)", "value": N * Fm / (ms / 1e3),
+        "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "DINO ViT-S/14 patch-feature pose initialisation: 1000 templates x 300 frames, "
+                               "P=1369, D=384, top-10 (BASELINE configs[3])", "l2": "256 MB flush between steps"},
+        "roofline": {"bound": "hbm", "achieved": bytes_ / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": bytes_ / (ms / 1e3) / 1e9 / hbm, "peak_source": f"{kind} hbm_gbs",
+                     "tensor": {"achieved_tflops": flops / (ms / 1e3) / 1e12, "peak_tflops": tf_peak,
+                                "frac": flops / (ms / 1e3) / 1e12 / tf_peak}},
+        "cpu_baseline": {"value": N / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
+                         "sample": f"{nf} frames x 1000 templates, pose_initializtion.py:295-296 verbatim + topk"},
+        "planted_match_rank0": ok, "gpu_launches": 2 * args.steps}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,8 +382,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "dino":
+        run_dino(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         if not torch.cuda.is_available():
