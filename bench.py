@@ -216,7 +216,7 @@ def run_ours(args):
 
     # ---- device-resident throughput: K fused iterations, inputs already in HBM
     model = build_model(seq)
-    fused = FusedJointOpt(model, LW, LR, args.steps + args.warmup + 64, shard=shard)
+    fused = FusedJointOpt(model, LW, LR, args.steps + args.warmup + 64, shard=shard, halo=args.halo)
     fused.run(args.warmup, use_graph=True)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -307,6 +307,7 @@ def run_ours(args):
                                    f"({B_total} total) 480x640, 5k-vertex mesh (V={V}, F={F}), 256x256 ROI rendered "
                                    "512x512 + 2x2 pool, lw_sil 1 / lw_smooth 10, lr 1e-4 (BASELINE configs[1])",
                        "frames_per_gpu": Bl, "frames_total": B_total, "parallelism": f"frame-shard x{world}",
+                       "halo": fused.halo_mode,
                        "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": True},
             "roofline": roofline, "e2e": e2e, "clocks": clocks,
@@ -383,6 +384,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     if args.workload == "dino":
         run_dino(args)

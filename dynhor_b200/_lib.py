@@ -38,6 +38,7 @@ class DhJointOpt(ctypes.Structure):
         ("adam_mv_scale", c_p),
         ("step", c_p), ("hist", c_p), ("max_iters", c_i),
         ("halo_prev", c_p), ("halo_next", c_p),
+        ("mailbox", c_p), ("peer_prev", c_p), ("peer_next", c_p),
         ("B_total", c_i),
         ("keep_sum", c_d), ("lw_sil", c_d), ("lw_smooth", c_d), ("lr", c_d),
         ("optimize_scale", c_i),
@@ -66,6 +67,12 @@ SIGNATURES = {
     "dh_jointopt_grads": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_p, c_p, c_p]),
     "dh_jointopt_profile": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
     "dh_jointopt_release": (c_i, [ctypes.POINTER(DhJointOpt)]),
+    "dh_dev_alloc": (c_i, [ctypes.POINTER(c_p), c_l]),
+    "dh_dev_free": (c_i, [c_p]),
+    "dh_memcpy_d2d": (c_i, [c_p, c_p, c_l, c_p]),
+    "dh_ipc_export": (c_i, [c_p, c_p]),
+    "dh_ipc_open": (c_i, [c_p, ctypes.POINTER(c_p)]),
+    "dh_ipc_close": (c_i, [c_p]),
     "dh_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_l, c_d, c_i, c_p]),
     "dh_dino_workspace_bytes": (c_i, [c_i, c_i, c_l, ctypes.POINTER(c_l)]),
     "dh_dino_topk": (c_i, [c_p, c_p, c_i, c_i, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),

@@ -1,4 +1,6 @@
 // dh_api.cu -- version / error / device queries of libdynhor_b200.so
+#include <string.h>
+
 #include "dh_common.h"
 
 namespace dh {
@@ -24,6 +26,44 @@ int dh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (sm_count) *sm_count = prop.multiProcessorCount;
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
+    return DH_OK;
+}
+
+int dh_dev_alloc(void** ptr, int64_t bytes) {
+    DH_REQUIRE(ptr != nullptr && bytes > 0, "bad arguments");
+    DH_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    DH_CUDA(cudaMemset(*ptr, 0, (size_t)bytes));
+    return DH_OK;
+}
+
+int dh_dev_free(void* ptr) {
+    if (ptr != nullptr) DH_CUDA(cudaFree(ptr));
+    return DH_OK;
+}
+
+int dh_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
+    DH_REQUIRE(dst && src && bytes > 0, "bad arguments");
+    DH_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DH_OK;
+}
+
+int dh_ipc_export(const void* ptr, void* handle64_host) {
+    DH_REQUIRE(ptr && handle64_host, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DH_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64_host), const_cast<void*>(ptr)));
+    return DH_OK;
+}
+
+int dh_ipc_open(const void* handle64_host, void** ptr) {
+    DH_REQUIRE(ptr && handle64_host, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, sizeof(h));
+    DH_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DH_OK;
+}
+
+int dh_ipc_close(void* ptr) {
+    if (ptr != nullptr) DH_CUDA(cudaIpcCloseMemHandle(ptr));
     return DH_OK;
 }
 

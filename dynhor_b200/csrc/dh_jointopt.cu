@@ -809,6 +809,32 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ pose kernels
+// ---- peer-to-peer halo mailboxes (layout: include/dynhor_b200.h)
+__device__ __forceinline__ float* mb_slot(float* mb, int side, int parity) { return mb + (side * 2 + parity) * 16; }
+__device__ __forceinline__ volatile int* mb_flag(float* mb, int side, int parity) {
+    return reinterpret_cast<volatile int*>(mb + 64) + side * 2 + parity;
+}
+// wait until the neighbour has published the pose valid for iteration `it`, then copy it out (9 floats)
+__device__ void mb_wait_read(float* mb, int side, int it, float* out9) {
+    volatile int* flag = mb_flag(mb, side, it & 1);
+    const long long t0 = clock64();
+    while (*flag < it) {
+        if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s: a lost neighbour aborts instead of hanging the GPU
+        __nanosleep(64);
+    }
+    __threadfence_system();
+    const volatile float* src = mb_slot(mb, side, it & 1);
+    for (int i = 0; i < 9; i++) out9[i] = src[i];
+}
+// publish this rank's boundary pose for iteration `it` into a neighbour's mailbox
+__device__ void mb_publish(float* peer, int side, int it, const float* rot6d, const float* trans) {
+    volatile float* dst = mb_slot(peer, side, it & 1);
+    for (int i = 0; i < 6; i++) dst[i] = rot6d[i];
+    for (int i = 0; i < 3; i++) dst[6 + i] = trans[i];
+    __threadfence_system();
+    *mb_flag(peer, side, it & 1) = it;
+}
+
 __global__ void k_pose_prep(const dh_jointopt p) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = p.sil.B;
@@ -817,8 +843,23 @@ __global__ void k_pose_prep(const dh_jointopt p) {
     for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
     rot6d_to_R(r6, Rm);
     for (int i = 0; i < 9; i++) p.Rmat[9 * b + i] = Rm[i];
-    smooth_terms_frame(b, B, p.rot6d, p.trans, p.halo_prev, p.halo_next, p.scale[0], p.moments, p.sil.V, p.B_total,
-                       p.lw_smooth, p.smooth_terms + (size_t)b * 16);
+    const float* hp = p.halo_prev;
+    const float* hn = p.halo_next;
+    float hbuf[2][9];
+    if (p.mailbox != nullptr) {  // P2P mode: the neighbours' poses arrive in the mailbox
+        const int it = *p.step;
+        hp = hn = nullptr;
+        if (p.peer_prev != nullptr) {
+            if (b == 0) mb_wait_read(p.mailbox, 0, it, hbuf[0]);
+            hp = hbuf[0];
+        }
+        if (p.peer_next != nullptr) {
+            if (b == B - 1) mb_wait_read(p.mailbox, 1, it, hbuf[1]);
+            hn = hbuf[1];
+        }
+    }
+    smooth_terms_frame(b, B, p.rot6d, p.trans, hp, hn, p.scale[0], p.moments, p.sil.V, p.B_total, p.lw_smooth,
+                       p.smooth_terms + (size_t)b * 16);
 }
 
 // mode 0: Adam update in place.  mode 1: write gradients to (grad_rot6d, grad_trans), leave parameters alone.
@@ -871,6 +912,11 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
     for (int i = 0; i < 3; i++)
         adam_update(&p.trans[3 * b + i], &p.adam_m_trans[3 * b + i], &p.adam_v_trans[3 * b + i], (float)gT[i],
                     step_tr, bc2s);
+    // P2P halo: the updated boundary poses go straight into the neighbours' mailboxes, valid for iteration t
+    if (p.mailbox != nullptr) {
+        if (b == 0 && p.peer_prev != nullptr) mb_publish(p.peer_prev, 1, t, p.rot6d + 6 * b, p.trans + 3 * b);
+        if (b == p.sil.B - 1 && p.peer_next != nullptr) mb_publish(p.peer_next, 0, t, p.rot6d + 6 * b, p.trans + 3 * b);
+    }
 }
 
 // One CTA.  mode 0: history row + scale update + step++.  mode 1: history row only (grad_scale written).

@@ -81,7 +81,10 @@ class FusedJointOpt:
     """The fused iteration (dh_jointopt_run) bound to a Joint_Optimizer's parameters, updated in place."""
 
     def __init__(self, model, loss_weights, lr, max_iters, shard=None, group=None, nchunks=None, keep_sum=None,
-                 exchange=True):
+                 exchange=True, halo="p2p"):
+        """halo: how boundary poses travel between ranks when the sequence is sharded.  "p2p" (default): CUDA-IPC
+        mailboxes written by the update kernel itself over NVLink, no host work per iteration.  "nccl": one grouped
+        send/recv per iteration driven from the host (also the path the gloo CPU tests exercise)."""
         lib = _lib.load()
         self.model, self.group = model, group
         rot, tr = model.rotations_object, model.translations_object
@@ -153,7 +156,11 @@ class FusedJointOpt:
         (p.Rmat, p.smooth_terms, p.loss_counts, p.partials, p.frame_terms) = [b.data_ptr() for b in self.scratch]
         p.nchunks = self.nchunks
         self.p = p
+        self.halo_mode = halo if (self.shard.world > 1 and exchange) else "none"
+        self._mailbox, self._peers = None, []
         self._sync_halo()
+        if self.halo_mode == "p2p":
+            self._setup_p2p()
 
     # -- sharding ---------------------------------------------------------------------------------------------
     def _sync_halo(self):
@@ -167,11 +174,42 @@ class FusedJointOpt:
         self.edge[1, 6:] = tr[-1].reshape(3)
         exchange_halo(self.edge[0], self.edge[1], self.shard, self.halo[0], self.halo[1], self.group)
 
+    def _setup_p2p(self):
+        """Allocate this rank's mailbox, swap CUDA-IPC handles with the neighbours and seed parity-0 slots with
+        the initial halo (already exchanged once through the process group)."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        mb = ctypes.c_void_p()
+        _lib.check(lib.dh_dev_alloc(ctypes.byref(mb), 4 * 128), "dh_dev_alloc")
+        self._mailbox = mb
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.dh_ipc_export(mb, handle), "dh_ipc_export")
+        handles = [None] * self.shard.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+        st = _lib.stream_ptr()
+        # slot(side, parity 0): side 0 = pose of the frame before our first, side 1 = after our last
+        for side in (0, 1):
+            _lib.check(lib.dh_memcpy_d2d(ctypes.c_void_p(mb.value + side * 2 * 16 * 4), _lib.ptr(self.halo[side]),
+                                         9 * 4, st), "dh_memcpy_d2d")
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # every mailbox is seeded before anyone may publish into it
+        peers = {}
+        for name, r in (("peer_prev", self.shard.rank - 1), ("peer_next", self.shard.rank + 1)):
+            if 0 <= r < self.shard.world:
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.dh_ipc_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(ptr)),
+                           "dh_ipc_open")
+                peers[name] = ptr
+                self._peers.append(ptr)
+        self.p.mailbox = mb.value
+        self.p.peer_prev = peers["peer_prev"].value if "peer_prev" in peers else None
+        self.p.peer_next = peers["peer_next"].value if "peer_next" in peers else None
+
     # -- execution --------------------------------------------------------------------------------------------
     def run(self, n_iters, use_graph=True):
         """n_iters fused iterations on the current stream; no host synchronisation (single rank)."""
         lib = _lib.load()
-        if self.shard.world == 1 or not self.exchange:
+        if self.halo_mode != "nccl":
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), int(n_iters), int(use_graph), _lib.stream_ptr()),
                        "dh_jointopt_run")
             return
@@ -231,11 +269,21 @@ class FusedJointOpt:
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}
 
     def release(self):
-        _lib.load().dh_jointopt_release(ctypes.byref(self.p))
+        lib = _lib.load()
+        lib.dh_jointopt_release(ctypes.byref(self.p))
+        if self._mailbox is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody may still be publishing into a mailbox that is about to go
+            for ptr in self._peers:
+                lib.dh_ipc_close(ptr)
+            lib.dh_dev_free(self._mailbox)
+            self._mailbox, self._peers = None, []
+            self.p.mailbox = self.p.peer_prev = self.p.peer_next = None
 
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
-                   lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True):
+                   lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True, halo="p2p"):
     """jointopt.py:93-161.  Extra keyword `shard` (a sharding.FrameShard): when given (or when torch.distributed
     is initialised with more than one rank) `object_parameters` is the full sequence and this rank optimises its
     contiguous frame range; the returned model holds the gathered poses of ALL frames on every rank."""
@@ -257,7 +305,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
         translations_object=obj_trans, rotations_object=obj_rots, verts_object_og=verts_object_og,
         faces_object=faces_local, target_masks_object=obj_tar_masks, camintr_rois_object=obj_camintr_roi,
         int_scale_init=1, optimize_object_scale=optimize_object_scale)
-    fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard)
+    fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard, halo=halo)
     try:
         from tqdm.auto import tqdm
         loop = tqdm(total=num_iterations)

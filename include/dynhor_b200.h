@@ -106,6 +106,12 @@ typedef struct dh_jointopt {
     /* neighbours' boundary poses for the smoothness term (frame-range sharding) */
     const float* halo_prev;        /* [9] rot6d(6)+trans(3) of global frame first-1, or NULL at the start        */
     const float* halo_next;        /* [9] of global frame last+1, or NULL at the end                            */
+    /* Optional peer-to-peer halo (one process per GPU, CUDA IPC over NVLink).  When `mailbox` is set the halo_*
+     * pointers are ignored: after its Adam step each rank stores its boundary poses straight into its neighbours'
+     * mailboxes and raises a flag; the next iteration's pose kernel waits on the flag.  No host involvement. */
+    float* mailbox;                /* [DH_MAILBOX_FLOATS] this rank's mailbox (dh_dev_alloc), or NULL            */
+    float* peer_prev;              /* mailbox of rank-1 mapped into this process (dh_ipc_open), NULL if none     */
+    float* peer_next;              /* mailbox of rank+1, NULL if none                                           */
     int32_t B_total;               /* frames in the whole sequence (all ranks)                                  */
     double keep_sum;               /* sum over ALL ranks of keep-mask pixels      utils/losses.py:71             */
     double lw_sil, lw_smooth;      /* loss weights, 0 disables a term             jointopt.py:81,86,147-150      */
@@ -138,6 +144,19 @@ int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans
 int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_host, void* stream);
 /* drop cached graphs */
 int dh_jointopt_release(const dh_jointopt* p);
+
+/* Mailbox layout: slot(side, parity) = 16 floats at (side*2 + parity)*16, side 0 = pose of global frame first-1,
+ * side 1 = pose of global frame last+1; int32 flags at float offset 64 + side*2 + parity hold the iteration number
+ * the slot is valid for. */
+#define DH_MAILBOX_FLOATS 128
+/* device memory that can be exported to the other ranks of the box (a dedicated cudaMalloc, zero-filled) */
+int dh_dev_alloc(void** ptr, int64_t bytes);
+int dh_dev_free(void* ptr);
+int dh_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+/* CUDA IPC: export / open / close a dh_dev_alloc allocation (handle = 64 bytes of HOST memory) */
+int dh_ipc_export(const void* ptr, void* handle64_host);
+int dh_ipc_open(const void* handle64_host, void** ptr);
+int dh_ipc_close(void* ptr);
 
 /* torch.optim.Adam single step on a flat fp32 tensor (jointopt.py:135-141,160), t = 1-based step number */
 int dh_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, double lr, int32_t t,
