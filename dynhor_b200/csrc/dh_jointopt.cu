@@ -106,8 +106,11 @@ template <bool FROM_POSE>
 __global__ void __launch_bounds__(kThreads)
 k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const float* __restrict__ trans,
           const float* __restrict__ scale, const float* __restrict__ K, float orig, float4* __restrict__ proj,
-          int V, int32_t* __restrict__ bin_count, int nstrips, int32_t* __restrict__ loss_counts) {
+          int V, int32_t* __restrict__ bin_count, int nstrips, int32_t* __restrict__ loss_counts,
+          uint32_t* __restrict__ owned, int owned_words) {
     const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < owned_words; i += gridDim.x * blockDim.x)
+        owned[(size_t)b * owned_words + i] = 0u;
     if (blockIdx.x == 0) {
         if ((int)threadIdx.x < 2 * nstrips) bin_count[b * nstrips * 2 + threadIdx.x] = 0;
         if (loss_counts != nullptr && threadIdx.x < 4) loss_counts[b * 4 + threadIdx.x] = 0;
@@ -249,7 +252,10 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int strip = blockIdx.x, b = blockIdx.y;
     const int row0 = strip * kSH;
     const int tid = threadIdx.x;
+    const int owned_words = (2 * s.F + 31) >> 5;
+    uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
     for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    for (int i = tid; i < owned_words; i += kThreads) s_owned[i] = 0u;
     for (int i = tid; i < is; i += kThreads) s_ndc[i] = pix_to_ndc(i, is);
     if (tid == 0) s_next = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
@@ -364,7 +370,12 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     for (int i = tid; i < kSH * is; i += kThreads) {
         const unsigned long long key = zbuf[i];
         const bool cov = key != DH_ZKEY_EMPTY;
-        fidx[i] = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
+        const int fn = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
+        fidx[i] = fn;
+        // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the same
+        // face along a row set the bit once
+        const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
+        if (cov && ((tid & 31) == 0 || fn_left != fn)) atomicOr(&s_owned[fn >> 5], 1u << (fn & 31));
         const uint32_t word = __ballot_sync(0xffffffffu, cov);
         if ((tid & 31) == 0) {
             const int r = i / is, w = (i % is) >> 5;
@@ -374,6 +385,10 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     }
     __syncthreads();
 
+    for (int i = tid; i < owned_words; i += kThreads) {
+        const uint32_t w = s_owned[i];
+        if (w) atomicOr(&s.owned[(size_t)b * owned_words + i], w);
+    }
     // ---- epilogue 2: output-resolution cells of this strip (2x2 average pool + vertical flip)
     const int S = s.S;
     const int cell_rows = s.aa ? kSH / 2 : kSH;
@@ -671,9 +686,13 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             bool v0 = false, v1 = false;
             if (f < f1) {
                 const float4 a0 = P[s.faces[3 * f + 0]], a1 = P[s.faces[3 * f + 1]], a2 = P[s.faces[3 * f + 2]];
-                if (finite3(a0.x, a1.x, a2.x) && finite3(a0.y, a1.y, a2.y)) {
-                    v0 = !face_backside(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y);
-                    v1 = !face_backside(a2.x, a2.y, a1.x, a1.y, a0.x, a0.y);
+                // a face that owns no pixel of the frame contributes nothing: its out scans need the in-pixel to be
+                // its own, its in scans only visit its own pixels
+                const uint32_t* ow = s.owned + (size_t)b * ((2 * s.F + 31) >> 5);
+                const bool o0 = (ow[f >> 5] >> (f & 31)) & 1u, o1 = (ow[(f + s.F) >> 5] >> ((f + s.F) & 31)) & 1u;
+                if ((o0 || o1) && finite3(a0.x, a1.x, a2.x) && finite3(a0.y, a1.y, a2.y)) {
+                    v0 = o0 && !face_backside(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y);
+                    v1 = o1 && !face_backside(a2.x, a2.y, a1.x, a1.y, a0.x, a0.y);
                 }
             }
             const uint32_t m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
@@ -965,9 +984,13 @@ int check_sil(const dh_sil* s) {
         return fail(DH_ERR_UNSUPPORTED, "S=%d aa=%d: S must be a multiple of 32 and S*(aa?2:1) <= %d", s->S, s->aa,
                     kMaxIS);
     DH_REQUIRE(s->faces && s->K && s->proj && s->bin_count && s->bins && s->fidx && s->alpha_bits && s->pos_pool &&
-                   s->neg_pool && s->gmax, "dh_sil has a NULL buffer");
+                   s->neg_pool && s->gmax && s->owned, "dh_sil has a NULL buffer");
     DH_REQUIRE(s->B <= 65535, "B > 65535 frames per call (grid.y limit); shard the sequence");
     return DH_OK;
+}
+
+size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + face-owns-a-pixel bitmap
+    return (size_t)kSH * raster_size(s) * sizeof(unsigned long long) + (size_t)((2 * s.F + 31) / 32) * sizeof(uint32_t);
 }
 
 size_t bwd_smem_bytes(const dh_sil& s) {
@@ -1008,13 +1031,13 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         dim3 gv((s.V + kThreads - 1) / kThreads, B);
         k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
                                                   reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
-                                                  p.loss_counts);
+                                                  p.loss_counts, s.owned, (2 * s.F + 31) / 32);
         DH_LAUNCH_OK("k_project");
         DH_REC(2);
         int rc = launch_forward_common(s, st);
         if (rc) return rc;
         DH_REC(3);
-        const size_t zb = (size_t)kSH * is * sizeof(unsigned long long);
+        const size_t zb = raster_smem_bytes(s);
         rc = set_smem(k_raster<true>, zb);
         if (rc) return rc;
         // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
@@ -1077,6 +1100,7 @@ extern "C" {
 int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out8) {
     DH_REQUIRE(out8 != nullptr && B > 0 && V > 0 && F > 0 && S > 0, "bad arguments");
     out8[8] = (int64_t)B * 4;
+    out8[9] = (int64_t)B * ((2 * (int64_t)F + 31) / 32) * 4;
     const int64_t is = aa ? 2 * S : S;
     const int64_t nstrips = (is + kSH - 1) / kSH, wprp = (S + 31) / 32;
     out8[0] = (int64_t)B * V * 4 * 4;
@@ -1099,11 +1123,11 @@ int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* s
     dim3 gv((s->V + kThreads - 1) / kThreads, s->B);
     k_project<false><<<gv, kThreads, 0, st>>>(verts_cam, nullptr, nullptr, nullptr, s->K, s->orig_size,
                                                reinterpret_cast<float4*>(s->proj), s->V, s->bin_count, nstrips,
-                                               nullptr);
+                                               nullptr, s->owned, (2 * s->F + 31) / 32);
     DH_LAUNCH_OK("k_project");
     rc = launch_forward_common(*s, st);
     if (rc) return rc;
-    const size_t zb = (size_t)kSH * is * sizeof(unsigned long long);
+    const size_t zb = raster_smem_bytes(*s);
     rc = set_smem(k_raster<false>, zb);
     if (rc) return rc;
     k_raster<false><<<dim3(nstrips, s->B), kThreads, zb, st>>>(*s, nullptr, 0.0f, rend, nullptr);
@@ -1217,7 +1241,7 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         if (memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0) exec = e.exec;
     if (exec == nullptr) {
         // warm the function attributes outside capture
-        rc = set_smem(k_raster<true>, (size_t)kSH * raster_size(p->sil) * sizeof(unsigned long long));
+        rc = set_smem(k_raster<true>, raster_smem_bytes(p->sil));
         if (rc) return rc;
         rc = set_smem(k_backward<true>, bwd_smem_bytes(p->sil));
         if (rc) return rc;
