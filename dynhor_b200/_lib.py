@@ -24,7 +24,7 @@ class DhSil(ctypes.Structure):
         ("near_", c_f), ("far_", c_f), ("eps", c_f), ("orig_size", c_f),
         ("faces", c_p), ("K", c_p),
         ("proj", c_p), ("bin_count", c_p), ("bins", c_p), ("fidx", c_p), ("alpha_bits", c_p),
-        ("pos_pool", c_p), ("neg_pool", c_p), ("gpool", c_p), ("gmax", c_p), ("owned", c_p),
+        ("pos_pool", c_p), ("neg_pool", c_p), ("gpool", c_p), ("gmax", c_p), ("owned", c_p), ("negT", c_p), ("row_rng", c_p),
     ]
 
 

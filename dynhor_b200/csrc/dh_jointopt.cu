@@ -246,7 +246,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     __shared__ int s_start[kThreads / 32][32];         // first row-item of every face of the batch
     __shared__ int s_fn[kThreads / 32][32];
     __shared__ uint32_t s_queue[kThreads / 32][64];    // pending (lane slot, x, local row) hits
-    __shared__ int s_next;
+    __shared__ int s_next[2];
     const int is = raster_size(s);
     const int nstrips = is / kSH;
     const int strip = blockIdx.x, b = blockIdx.y;
@@ -257,7 +257,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
     for (int i = tid; i < owned_words; i += kThreads) s_owned[i] = 0u;
     for (int i = tid; i < is; i += kThreads) s_ndc[i] = pix_to_ndc(i, is);
-    if (tid == 0) s_next = 0;
+    if (tid < 2) s_next[tid] = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
     __syncthreads();
 
@@ -273,7 +273,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
         for (;;) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(&s_next, 32);
+            if (lane == 0) base = atomicAdd(&s_next[pass], 32);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= count) break;
             const int e = base + lane;
@@ -358,33 +358,34 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             if (lane < qn) raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
             __syncwarp();
         }
-        __syncthreads();
-        if (tid == 0) s_next = 0;
-        __syncthreads();
+        // no barrier between the passes: a warp that runs ahead into the reversed windings only makes the depth
+        // pre-test less effective, never wrong
     }
+    __syncthreads();
 
     // ---- epilogue 1: face index map + coverage bitmap (one warp = 32 consecutive pixels of a row)
     const int wpr = is >> 5;
     int32_t* fidx = s.fidx + (size_t)b * is * is + (size_t)row0 * is;
     uint32_t* abits_g = s.alpha_bits + ((size_t)b * is + row0) * wpr;
-    for (int i = tid; i < kSH * is; i += kThreads) {
-        const unsigned long long key = zbuf[i];
-        const bool cov = key != DH_ZKEY_EMPTY;
-        const int fn = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
-        fidx[i] = fn;
-        // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the same
-        // face along a row set the bit once
-        const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
-        if (cov && ((tid & 31) == 0 || fn_left != fn)) atomicOr(&s_owned[fn >> 5], 1u << (fn & 31));
-        const uint32_t word = __ballot_sync(0xffffffffu, cov);
-        if ((tid & 31) == 0) {
-            const int r = i / is, w = (i % is) >> 5;
-            abits[r][w] = word;
-            abits_g[r * wpr + w] = word;
+    for (int r = 0; r < kSH; r++) {
+        for (int c = tid; c < is; c += kThreads) {
+            const int i = r * is + c;
+            const unsigned long long key = zbuf[i];
+            const bool cov = key != DH_ZKEY_EMPTY;
+            const int fn = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
+            fidx[i] = fn;
+            // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the
+            // same face along a row set the bit once
+            const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
+            if (cov && ((tid & 31) == 0 || fn_left != fn)) atomicOr(&s_owned[fn >> 5], 1u << (fn & 31));
+            const uint32_t word = __ballot_sync(0xffffffffu, cov);
+            if ((tid & 31) == 0) {
+                abits[r][c >> 5] = word;
+                abits_g[r * wpr + (c >> 5)] = word;
+            }
         }
     }
     __syncthreads();
-
     for (int i = tid; i < owned_words; i += kThreads) {
         const uint32_t w = s_owned[i];
         if (w) atomicOr(&s.owned[(size_t)b * owned_words + i], w);
@@ -472,24 +473,71 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 //           independent of task order: bit-identical results run to run.
 //   tail    (lane = item): fixed point -> float, projection / rigid-transform backward, pose accumulators.
 constexpr int kBwdWarps = kThreads / 32;
-constexpr int kTaskCap = 96, kItemCap = 96;
+constexpr int kTaskCap = 96;
+constexpr int kChunkFaces = 2048;   // faces per backward CTA at most (item list: 2 windings x 2048 x u16 = 8 KB)
 
 struct BwdWarp {
     float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot
     int fn[32];
     unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
     uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9
-    uint32_t items[kItemCap];            // face | winding << 31
 };
 
 __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long long v) {
     if (v != 0) atomicAdd(a, (unsigned long long)v);
 }
 
+// Frame-level maps the backward needs, built once per frame instead of once per backward CTA:
+//   negT    column-major bitmap of "uncovered && dL/dpixel < 0" (32x32 bit-block transposes through ballots)
+//   row_rng first / last set pixel of every row of that bitmap
+// One CTA per (32-row band, frame).
+__global__ void __launch_bounds__(kThreads)
+k_neg_maps(const dh_sil s) {
+    __shared__ uint32_t words[32][kMaxIS / 32];
+    const int is = raster_size(s), S = s.S;
+    const int wpr = is >> 5, wprp = (S + 31) >> 5;
+    const int rb = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
+    const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
+    for (int i = tid; i < 32 * wpr; i += kThreads) {
+        const int r = i / wpr, w = i - r * wpr;
+        words[r][w] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, 32 * rb + r, w);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int lo = is, hi = -1;
+        for (int w = 0; w < wpr; w++) {
+            const uint32_t bits = words[tid][w];
+            if (bits) {
+                if (lo == is) lo = (w << 5) + ctz32(bits);
+                hi = (w << 5) + 31 - __clz((int)bits);
+            }
+        }
+        s.row_rng[((size_t)b * 2 + 0) * is + 32 * rb + tid] = (int16_t)lo;
+        s.row_rng[((size_t)b * 2 + 1) * is + 32 * rb + tid] = (int16_t)hi;
+    }
+    uint32_t* gT = s.negT + (size_t)b * is * wpr;
+    for (int cb = warp; cb < wpr; cb += kBwdWarps) {
+        const uint32_t word = words[lane][cb];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
+            if (lane == j) mine = colw;
+        }
+        gT[(32 * cb + lane) * wpr + rb] = mine;
+    }
+}
+
 // dL/d(raster pixel) at (r, c).  Fused path: rebuilt from the staged coverage bitmap exactly as k_raster's
 // epilogue computed it (gpool = gcoef * (k * 0.5), k = keep * (pop - 4 ref)), so the pixel loops never wait on
 // global memory.  `wanted` tells which sign bitmap selected the pixel: true -> k = pop - 4 (< 0, object missing),
 // false -> k = pop (> 0, object where background is wanted).  API path: the caller's gradient map.
+__device__ __forceinline__ float grad_from_pop(int pop, bool wanted, float gcoef, float gscale) {
+    const int k = wanted ? pop - 4 : pop;
+    return (gcoef * ((float)k * 0.5f)) * gscale;
+}
 template <bool FUSED>
 __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool wanted, float gcoef) {
     if (!FUSED) return grad_at(m, r, c);
@@ -501,11 +549,11 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
     } else {
         pop = 4 * (int)((m.alpha[r * m.wpr + (c >> 5)] >> (c & 31)) & 1u);
     }
-    const int k = wanted ? pop - 4 : pop;
-    return (gcoef * ((float)k * 0.5f)) * m.gscale;
+    return grad_from_pop(pop, wanted, gcoef, m.gscale);
 }
 
-// phase 2: one task per lane
+// phase 2: one task per lane.  The pixel loop accumulates its two terms in fp32 in pixel order (deterministic for
+// a given task, like the reference's per-face loop); only the task totals go through the fixed-point atomics.
 template <bool FUSED>
 __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale,
                                          float gcoef) {
@@ -524,7 +572,7 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
     edge_coefs(sp.p00, sp.p10, d0, ec);
     const bool pow2 = (is & (is - 1)) == 0;
     const float two_over_is = 2.0f / (float)is;
-    long long sa = 0, sb = 0;
+    float sa = 0.0f, sb = 0.0f;
     if (kind == 0) {
         const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
         if (m.fidx[r_in * is + c_in] == fn) {
@@ -537,17 +585,30 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
                 uint32_t bits = neg_line_word(m, axis, d0, w);
                 if (w == w_from) bits &= 0xFFFFFFFFu << (from & 31);
                 if (w == w_to) bits &= 0xFFFFFFFFu >> (31 - (to & 31));
+                // row scans of the fused anti-aliased path: the two coverage words of the pooled row pair serve
+                // all 32 pixels of this word
+                uint32_t aw0 = 0, aw1 = 0;
+                const bool row_fast = FUSED && axis == 1 && m.aa;
+                if (row_fast && bits) {
+                    aw0 = m.alpha[(d0 & ~1) * m.wpr + w];
+                    aw1 = m.alpha[(d0 | 1) * m.wpr + w];
+                }
                 while (bits) {
-                    const int d1 = (w << 5) + ctz32(bits);
+                    const int bpos = ctz32(bits);
+                    const int d1 = (w << 5) + bpos;
                     bits &= bits - 1;
-                    const float g = (axis == 0) ? grad_value<FUSED>(m, d1, d0, true, gcoef)
-                                                : grad_value<FUSED>(m, d0, d1, true, gcoef);
+                    float g;
+                    if (row_fast) {
+                        const int sh = bpos & 30;
+                        g = grad_from_pop(__popc((aw0 >> sh) & 3u) + __popc((aw1 >> sh) & 3u), true, gcoef, m.gscale);
+                    } else {
+                        g = (axis == 0) ? grad_value<FUSED>(m, d1, d0, true, gcoef)
+                                        : grad_value<FUSED>(m, d0, d1, true, gcoef);
+                    }
                     const float diff = (0.0f - 1.0f) * g;
                     if (diff <= 0.0f) continue;
-                    if (ec.ka != 0.0f)
-                        sa += __float2ll_rn(edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
-                    if (ec.kb != 0.0f)
-                        sb += __float2ll_rn(edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
+                    if (ec.ka != 0.0f) sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is);
+                    if (ec.kb != 0.0f) sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is);
                 }
             }
         }
@@ -561,14 +622,12 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
             if (m.fidx[r * is + c] != fn) continue;
             const float diff = (1.0f - 0.0f) * grad_value<FUSED>(m, r, c, false, gcoef);
             if (diff <= 0.0f) continue;
-            if (ec.ka != 0.0f)
-                sa += __float2ll_rn(edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
-            if (ec.kb != 0.0f)
-                sb += __float2ll_rn(edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is) * fpscale);
+            if (ec.ka != 0.0f) sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is);
+            if (ec.kb != 0.0f) sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is);
         }
     }
-    atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], sa);
-    atomic_add_fixed(&W.acc[((edge + 1) % 3) * 2 + (1 - axis)][slot], sb);
+    atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], __float2ll_rn(sa * fpscale));
+    atomic_add_fixed(&W.acc[((edge + 1) % 3) * 2 + (1 - axis)][slot], __float2ll_rn(sb * fpscale));
 }
 
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
@@ -580,54 +639,70 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
            float* __restrict__ grad_verts, int nchunks, float gcoef) {
     extern __shared__ uint32_t smw[];
     __shared__ float red[kBwdWarps][13];
-    __shared__ int16_t s_rng[4][kMaxIS];  // row_lo, row_hi, col_lo, col_hi
+    __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ BwdWarp s_warp[kBwdWarps];
+    __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
+    __shared__ int s_wcount[kBwdWarps], s_woff[kBwdWarps + 1];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
     uint32_t* s_negT = s_alpha + is * wpr;
-    uint32_t* s_pos = s_negT + is * wpr;
-    uint32_t* s_negp = s_pos + S * wprp;
+    uint32_t* s_negp = s_negT + is * wpr;
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const float gmax = s.gmax[b];
 
-    // ---- stage the frame's bitmaps
+    const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
+    const int per = (s.F + nchunks - 1) / nchunks;
+    const int f0 = chunk * per, f1 = min(s.F, f0 + per);
+
+    // ---- the chunk's front-facing, pixel-owning (face, winding) items, compacted in face order.  A face that owns
+    //      no pixel of the frame contributes nothing: out scans need the in-pixel to be the face's own, in scans
+    //      only visit its own pixels.  Each warp scans a contiguous range of faces, <= 8 faces per lane.
+    const int per_w = (((f1 - f0 + kBwdWarps - 1) / kBwdWarps) + 31) & ~31;
+    const int wf0 = f0 + warp * per_w, wf1 = min(f1, wf0 + per_w);
+    uint32_t flags = 0;  // bit 2g: given winding of this lane's g-th face is an item, bit 2g+1: reversed winding
+    int wcount = 0;
+    if (gmax > 0.0f) {
+        const uint32_t* ow = s.owned + (size_t)b * ((2 * s.F + 31) >> 5);
+        for (int g = 0, f = wf0 + lane; f - lane < wf1; g++, f += 32) {
+            bool v0 = false, v1 = false;
+            if (f < wf1) {
+                const bool o0 = (ow[f >> 5] >> (f & 31)) & 1u, o1 = (ow[(f + s.F) >> 5] >> ((f + s.F) & 31)) & 1u;
+                if (o0 || o1) {
+                    const float4 a0 = P[s.faces[3 * f + 0]], a1 = P[s.faces[3 * f + 1]], a2 = P[s.faces[3 * f + 2]];
+                    if (finite3(a0.x, a1.x, a2.x) && finite3(a0.y, a1.y, a2.y)) {
+                        v0 = o0 && !face_backside(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y);
+                        v1 = o1 && !face_backside(a2.x, a2.y, a1.x, a1.y, a0.x, a0.y);
+                    }
+                }
+            }
+            flags |= ((uint32_t)v0 << (2 * g)) | ((uint32_t)v1 << (2 * g + 1));
+            wcount += __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, v1));
+        }
+    }
+    if (lane == 0) s_wcount[warp] = wcount;
+
+    // ---- stage the frame's bitmaps (built per frame by k_raster / k_neg_maps)
     {
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
-        const uint32_t* gp = s.pos_pool + (size_t)b * S * wprp;
+        const uint32_t* gt = s.negT + (size_t)b * is * wpr;
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
-        for (int i = tid; i < is * wpr; i += kThreads) s_alpha[i] = ga[i];
-        for (int i = tid; i < S * wprp; i += kThreads) { s_pos[i] = gp[i]; s_negp[i] = gn[i]; }
+        for (int i = tid; i < is * wpr; i += kThreads) { s_alpha[i] = ga[i]; s_negT[i] = gt[i]; }
+        for (int i = tid; i < S * wprp; i += kThreads) s_negp[i] = gn[i];
+        for (int i = tid; i < is; i += kThreads) {
+            s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
+            s_rng[1][i] = s.row_rng[((size_t)b * 2 + 1) * is + i];
+        }
     }
     __syncthreads();
-    // column-major copy of the "uncovered && grad < 0" bitmap: 32x32 bit-block transposes through ballots
-    for (int blk = warp; blk < wpr * wpr; blk += kBwdWarps) {
-        const int rb = blk / wpr, cb = blk - rb * wpr;
-        const uint32_t word = neg_row_word(s_alpha, s_negp, is, s.aa, wpr, wprp, 32 * rb + lane, cb);
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
-            if (lane == j) mine = colw;
-        }
-        s_negT[(32 * cb + lane) * wpr + rb] = mine;
+    if (tid == 0) {
+        int o = 0;
+        for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
+        s_woff[kBwdWarps] = o;
     }
-    // first / last set pixel of every row
-    for (int r = tid; r < is; r += kThreads) {
-        int lo = is, hi = -1;
-        for (int w = 0; w < wpr; w++) {
-            const uint32_t bits = neg_row_word(s_alpha, s_negp, is, s.aa, wpr, wprp, r, w);
-            if (bits) {
-                if (lo == is) lo = (w << 5) + ctz32(bits);
-                hi = (w << 5) + 31 - __clz((int)bits);
-            }
-        }
-        s_rng[0][r] = (int16_t)lo;
-        s_rng[1][r] = (int16_t)hi;
-    }
-    __syncthreads();
-    for (int c = tid; c < is; c += kThreads) {
+    for (int c = tid; c < is; c += kThreads) {  // first / last set pixel of every column
         int lo = is, hi = -1;
         for (int w = 0; w < wpr; w++) {
             const uint32_t bits = s_negT[c * wpr + w];
@@ -640,9 +715,22 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         s_rng[3][c] = (int16_t)hi;
     }
     __syncthreads();
+    if (gmax > 0.0f) {
+        int pos = s_woff[warp];
+        for (int g = 0, f = wf0 + lane; f - lane < wf1; g++, f += 32) {
+            const bool v0 = (flags >> (2 * g)) & 1u, v1 = (flags >> (2 * g + 1)) & 1u;
+            const uint32_t m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
+            if (v0) s_items[pos + __popc(m0 & lt_mask)] = (uint16_t)(f - f0);
+            if (v1) s_items[pos + __popc(m0) + __popc(m1 & lt_mask)] = (uint16_t)((f - f0) | 0x8000);
+            pos += __popc(m0) + __popc(m1);
+        }
+    }
+    __syncthreads();
+    const int n_items = s_woff[kBwdWarps];
 
     BwdMaps m;
-    m.alpha = s_alpha; m.neg = nullptr; m.negT = s_negT; m.pos_pool = s_pos; m.neg_pool = s_negp;
+    m.alpha = s_alpha; m.neg = nullptr; m.negT = s_negT; m.neg_pool = s_negp;
+    m.pos_pool = s.pos_pool + (size_t)b * S * wprp;   // only the (rare, short) in scans read it: left in global
     m.row_lo = s_rng[0]; m.row_hi = s_rng[1]; m.col_lo = s_rng[2]; m.col_hi = s_rng[3];
     m.gpool = s.gpool + (size_t)b * S * S;
     m.fidx = s.fidx + (size_t)b * is * is;
@@ -650,7 +738,6 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     m.gscale = s.aa ? 0.25f : 1.0f;
 
     // fixed-point scale: |term| <= gmax / eps; 2^38 / that bound leaves 2^24 terms of headroom in 63 bits
-    const float gmax = s.gmax[b];
     float fpscale = 0.0f, fpinv = 0.0f;
     if (gmax > 0.0f) {
         int e;
@@ -671,145 +758,111 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     for (int i = 0; i < 13; i++) acc[i] = 0.0f;
 
     BwdWarp& W = s_warp[warp];
-    const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
-    const int per = (s.F + nchunks - 1) / nchunks;
-    const int f0 = chunk * per, f1 = min(s.F, f0 + per);
-    int n_items = 0;
-    // groups of 32 faces go to the warps round-robin (a STATIC assignment: the per-thread float accumulators of the
-    // tail then see the same faces in the same order every run, which keeps the result bit-reproducible)
-    int fbase = f0 + warp * 32 - kBwdWarps * 32;
-    for (bool more = gmax > 0.0f; more;) {
-        fbase += kBwdWarps * 32;
-        // ---- gather front-facing (face, winding) items of the next 32 faces
-        if (fbase < f1) {
-            const int f = fbase + lane;
-            bool v0 = false, v1 = false;
-            if (f < f1) {
-                const float4 a0 = P[s.faces[3 * f + 0]], a1 = P[s.faces[3 * f + 1]], a2 = P[s.faces[3 * f + 2]];
-                // a face that owns no pixel of the frame contributes nothing: its out scans need the in-pixel to be
-                // its own, its in scans only visit its own pixels
-                const uint32_t* ow = s.owned + (size_t)b * ((2 * s.F + 31) >> 5);
-                const bool o0 = (ow[f >> 5] >> (f & 31)) & 1u, o1 = (ow[(f + s.F) >> 5] >> ((f + s.F) & 31)) & 1u;
-                if ((o0 || o1) && finite3(a0.x, a1.x, a2.x) && finite3(a0.y, a1.y, a2.y)) {
-                    v0 = o0 && !face_backside(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y);
-                    v1 = o1 && !face_backside(a2.x, a2.y, a1.x, a1.y, a0.x, a0.y);
-                }
+    // batches of 32 items go to the warps round-robin: a STATIC assignment, so every thread's float accumulators
+    // see the same faces in the same order on every run (bit-reproducible results)
+    for (int batch = warp; batch * 32 < n_items; batch += kBwdWarps) {
+        const bool have = batch * 32 + lane < n_items;
+        float px[3], py[3];
+        int ids[3] = {0, 0, 0};
+        if (have) {
+            const uint32_t it = s_items[batch * 32 + lane];
+            const int fn = f0 + (int)(it & 0x7FFFu) + ((it >> 15) ? s.F : 0);
+            FaceSetup fs;
+            load_face(P, s.faces, fn, s.F, fs, ids);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                px[k] = ndc_to_pix(fs.x[k], is);
+                py[k] = ndc_to_pix(fs.y[k], is);
+                W.px[k][lane] = px[k];
+                W.py[k][lane] = py[k];
             }
-            const uint32_t m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
-            if (v0) W.items[n_items + __popc(m0 & lt_mask)] = (uint32_t)f;
-            if (v1) W.items[n_items + __popc(m0) + __popc(m1 & lt_mask)] = (uint32_t)f | 0x80000000u;
-            n_items += __popc(m0) + __popc(m1);
-            __syncwarp();
+            W.fn[lane] = fn;
         }
-        const bool last = fbase >= f1;
-        more = !last;
-        // ---- process full batches of 32 items (and the remainder at the very end)
-        while (n_items >= 32 || (last && n_items > 0)) {
-            const int nb = min(n_items, 32);
-            n_items -= nb;
-            const bool have = lane < nb;
-            float px[3], py[3];
-            int ids[3] = {0, 0, 0};
-            if (have) {
-                const uint32_t it = W.items[n_items + lane];
-                const int fn = (int)(it & 0x7FFFFFFFu) + ((it >> 31) ? s.F : 0);
-                FaceSetup fs;
-                load_face(P, s.faces, fn, s.F, fs, ids);
 #pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    px[k] = ndc_to_pix(fs.x[k], is);
-                    py[k] = ndc_to_pix(fs.y[k], is);
-                    W.px[k][lane] = px[k];
-                    W.py[k][lane] = py[k];
-                }
-                W.fn[lane] = fn;
-            }
-#pragma unroll
-            for (int k = 0; k < 6; k++) W.acc[k][lane] = 0ull;
-            __syncwarp();
-            // ---- phase 1: enumerate crossings, emit tasks
-            int n_tasks = 0;
-            int span_id = have ? 0 : 6, d0 = 0;
-            Span sp;
-            if (have) {
-                span_setup(px, py, 0, 0, is, sp);
-                d0 = sp.d0_from;
-            }
-            while (__any_sync(0xffffffffu, span_id < 6)) {
-                bool t_out = false, t_in = false;
-                uint32_t tw = 0;
-                if (span_id < 6) {
-                    if (d0 > sp.d0_to) {
-                        span_id++;
-                        if (span_id < 6) {
-                            span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
-                            d0 = sp.d0_from;
-                        }
-                    } else {
-                        const int axis = span_id & 1;
-                        float d1_cross;
-                        int d1_in, d1_out;
-                        if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) {
-                            int from, to;
-                            out_scan_range(sp.direction, d1_out, is, &from, &to);
-                            const int lo = (axis == 0) ? m.col_lo[d0] : m.row_lo[d0];
-                            const int hi = (axis == 0) ? m.col_hi[d0] : m.row_hi[d0];
-                            t_out = max(from, lo) <= min(to, hi);
-                            const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
-                            t_in = !alpha_at(m, r_out, c_out);
-                            tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
-                                 ((uint32_t)d0 << 9);
-                        }
-                        d0++;
+        for (int k = 0; k < 6; k++) W.acc[k][lane] = 0ull;
+        __syncwarp();
+        // ---- phase 1: enumerate crossings, emit tasks
+        int n_tasks = 0;
+        int span_id = have ? 0 : 6, d0 = 0;
+        Span sp;
+        if (have) {
+            span_setup(px, py, 0, 0, is, sp);
+            d0 = sp.d0_from;
+        }
+        while (__any_sync(0xffffffffu, span_id < 6)) {
+            bool t_out = false, t_in = false;
+            uint32_t tw = 0;
+            if (span_id < 6) {
+                if (d0 > sp.d0_to) {
+                    span_id++;
+                    if (span_id < 6) {
+                        span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
+                        d0 = sp.d0_from;
                     }
+                } else {
+                    const int axis = span_id & 1;
+                    float d1_cross;
+                    int d1_in, d1_out;
+                    if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) {
+                        int from, to;
+                        out_scan_range(sp.direction, d1_out, is, &from, &to);
+                        const int lo = (axis == 0) ? m.col_lo[d0] : m.row_lo[d0];
+                        const int hi = (axis == 0) ? m.col_hi[d0] : m.row_hi[d0];
+                        t_out = max(from, lo) <= min(to, hi);
+                        const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
+                        t_in = !alpha_at(m, r_out, c_out);
+                        tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
+                             ((uint32_t)d0 << 9);
+                    }
+                    d0++;
                 }
-                const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
-                if (t_out) W.tasks[n_tasks + __popc(mo & lt_mask)] = tw;
-                if (t_in) W.tasks[n_tasks + __popc(mo) + __popc(mi & lt_mask)] = tw | (1u << 8);
-                n_tasks += __popc(mo) + __popc(mi);
+            }
+            const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
+            if (t_out) W.tasks[n_tasks + __popc(mo & lt_mask)] = tw;
+            if (t_in) W.tasks[n_tasks + __popc(mo) + __popc(mi & lt_mask)] = tw | (1u << 8);
+            n_tasks += __popc(mo) + __popc(mi);
+            __syncwarp();
+            while (n_tasks >= 32) {
+                n_tasks -= 32;
+                bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
                 __syncwarp();
-                while (n_tasks >= 32) {
-                    n_tasks -= 32;
-                    bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
-                    __syncwarp();
-                }
             }
-            if (lane < n_tasks) bwd_task<FUSED>(W.tasks[lane], W, m, s.eps, fpscale, gcoef);
-            __syncwarp();
-            // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
-            if (have) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const float gu = -(float)((double)(long long)W.acc[2 * k][lane] * (double)fpinv);
-                    const float gv = -(float)((double)(long long)W.acc[2 * k + 1][lane] * (double)fpinv);
-                    if (gu == 0.0f && gv == 0.0f) continue;
-                    float c[3], vo[3], gc[3];
-                    if (FUSED) {
-                        for (int i = 0; i < 3; i++) vo[i] = verts_src[3 * ids[k] + i];
-                        transform_vertex(vo, s_abs, Rm, Tm, c);
-                    } else {
-                        const float* src = verts_src + ((size_t)b * s.V + ids[k]) * 3;
-                        c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
-                    }
-                    project_vertex_backward(c, Km, s.orig_size, gu, gv, gc);
-                    if (FUSED) {
-                        for (int j = 0; j < 3; j++) acc[j] += gc[j];
-                        for (int i = 0; i < 3; i++)
-                            for (int j = 0; j < 3; j++) acc[3 + 3 * i + j] += (s_abs * vo[i]) * gc[j];
-                        float dot = 0.0f;
-                        for (int j = 0; j < 3; j++)
-                            dot += (vo[0] * Rm[j] + vo[1] * Rm[3 + j] + vo[2] * Rm[6 + j]) * gc[j];
-                        acc[12] += dot;
-                    } else {
-                        float* dst = grad_verts + ((size_t)b * s.V + ids[k]) * 3;
-                        atomicAdd(dst + 0, gc[0]);
-                        atomicAdd(dst + 1, gc[1]);
-                        atomicAdd(dst + 2, gc[2]);
-                    }
-                }
-            }
-            __syncwarp();
         }
+        if (lane < n_tasks) bwd_task<FUSED>(W.tasks[lane], W, m, s.eps, fpscale, gcoef);
+        __syncwarp();
+        // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
+        if (have) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float gu = -(float)((double)(long long)W.acc[2 * k][lane] * (double)fpinv);
+                const float gv = -(float)((double)(long long)W.acc[2 * k + 1][lane] * (double)fpinv);
+                if (gu == 0.0f && gv == 0.0f) continue;
+                float c[3], vo[3], gc[3];
+                if (FUSED) {
+                    for (int i = 0; i < 3; i++) vo[i] = verts_src[3 * ids[k] + i];
+                    transform_vertex(vo, s_abs, Rm, Tm, c);
+                } else {
+                    const float* src = verts_src + ((size_t)b * s.V + ids[k]) * 3;
+                    c[0] = src[0]; c[1] = src[1]; c[2] = src[2];
+                }
+                project_vertex_backward(c, Km, s.orig_size, gu, gv, gc);
+                if (FUSED) {
+                    for (int j = 0; j < 3; j++) acc[j] += gc[j];
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++) acc[3 + 3 * i + j] += (s_abs * vo[i]) * gc[j];
+                    float dot = 0.0f;
+                    for (int j = 0; j < 3; j++)
+                        dot += (vo[0] * Rm[j] + vo[1] * Rm[3 + j] + vo[2] * Rm[6 + j]) * gc[j];
+                    acc[12] += dot;
+                } else {
+                    float* dst = grad_verts + ((size_t)b * s.V + ids[k]) * 3;
+                    atomicAdd(dst + 0, gc[0]);
+                    atomicAdd(dst + 1, gc[1]);
+                    atomicAdd(dst + 2, gc[2]);
+                }
+            }
+        }
+        __syncwarp();
     }
     if (FUSED) {
 #pragma unroll
@@ -984,7 +1037,7 @@ int check_sil(const dh_sil* s) {
         return fail(DH_ERR_UNSUPPORTED, "S=%d aa=%d: S must be a multiple of 32 and S*(aa?2:1) <= %d", s->S, s->aa,
                     kMaxIS);
     DH_REQUIRE(s->faces && s->K && s->proj && s->bin_count && s->bins && s->fidx && s->alpha_bits && s->pos_pool &&
-                   s->neg_pool && s->gmax && s->owned, "dh_sil has a NULL buffer");
+                   s->neg_pool && s->gmax && s->owned && s->negT && s->row_rng, "dh_sil has a NULL buffer");
     DH_REQUIRE(s->B <= 65535, "B > 65535 frames per call (grid.y limit); shard the sequence");
     return DH_OK;
 }
@@ -995,7 +1048,7 @@ size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + face-owns-a-pix
 
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(2 * is * (is / 32) + 2 * s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
+    return (size_t)(2 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
 }
 
 template <typename KernelT>
@@ -1046,6 +1099,8 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         DH_LAUNCH_OK("k_raster");
         DH_REC(4);
         if (mode != 2) {
+            k_neg_maps<<<dim3(is / 32, B), kThreads, 0, st>>>(s);
+            DH_LAUNCH_OK("k_neg_maps");
             const size_t sb = bwd_smem_bytes(s);
             rc = set_smem(k_backward<true>, sb);
             if (rc) return rc;
@@ -1077,7 +1132,8 @@ int check_plan(const dh_jointopt* p) {
                "dh_jointopt has a NULL Adam state pointer");
     DH_REQUIRE(p->Rmat && p->smooth_terms && p->loss_counts && p->partials && p->frame_terms,
                "dh_jointopt has a NULL scratch pointer");
-    DH_REQUIRE(p->nchunks >= 1 && p->nchunks <= 64, "nchunks must be in [1,64]");
+    DH_REQUIRE(p->nchunks >= 1 && (p->sil.F + p->nchunks - 1) / p->nchunks <= kChunkFaces,
+               "nchunks must be >= ceil(F / 2048)");
     DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
     DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
     return DH_OK;
@@ -1111,6 +1167,8 @@ int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa,
     out8[5] = (int64_t)B * S * wprp * 4;
     out8[6] = out8[5];
     out8[7] = (int64_t)B * S * S * 4;
+    out8[10] = (int64_t)B * is * (is / 32) * 4;
+    out8[11] = (int64_t)B * 2 * is * 2;
     return DH_OK;
 }
 
@@ -1149,6 +1207,8 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     DH_LAUNCH_OK("k_grad_signs");
     dh_sil t = *s;
     t.gpool = const_cast<float*>(grad_rend);
+    k_neg_maps<<<dim3(raster_size(t) / 32, t.B), kThreads, 0, st>>>(t);
+    DH_LAUNCH_OK("k_neg_maps");
     const size_t sb = bwd_smem_bytes(t);
     rc = set_smem(k_backward<false>, sb);
     if (rc) return rc;
@@ -1219,8 +1279,9 @@ int dh_jointopt_scratch_bytes(int32_t B, int32_t nchunks, int64_t* out5) {
 int dh_jointopt_default_chunks(int32_t B, int32_t F) {
     (void)B;
     int c = (F + 4 * kThreads - 1) / (4 * kThreads);  // ~4 faces per thread
+    const int cmin = (F + kChunkFaces - 1) / kChunkFaces;  // the CTA's item list holds kChunkFaces faces
+    if (c < cmin) c = cmin;
     if (c < 1) c = 1;
-    if (c > 64) c = 64;
     return c;
 }
 

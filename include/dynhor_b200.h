@@ -59,11 +59,13 @@ typedef struct dh_sil {
     float* gpool;                      /* [B,S,S] dL/drend (fused path writes it; API path copies grad_rend in)  */
     float* gmax;                       /* [B] max |dL/d(raster pixel)| per frame (scales the backward's fixed point) */
     uint32_t* owned;                   /* [B,ceil(2F/32)] bitmap: face fn owns at least one pixel of the frame       */
+    uint32_t* negT;                    /* [B,is,is/32] column-major bitmap: pixel uncovered && dL/dpixel < 0         */
+    int16_t* row_rng;                  /* [B,2,is] first / last set pixel of every row of that bitmap              */
 } dh_sil;
 
-/* bytes of each scratch array, out[10] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,
- * neg_pool, gpool, gmax, owned) */
-int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out10);
+/* bytes of each scratch array, out[12] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,
+ * neg_pool, gpool, gmax, owned, negT, row_rng) */
+int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out12);
 
 /* rend[B,S,S] = silhouettes of camera-space vertices verts_cam[B,V,3]  (forward of the renderer call). */
 int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* stream);
