@@ -474,13 +474,14 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 //   tail    (lane = item): fixed point -> float, projection / rigid-transform backward, pose accumulators.
 constexpr int kBwdWarps = kThreads / 32;
 constexpr int kTaskCap = 96;
-constexpr int kChunkFaces = 2048;   // faces per backward CTA at most (item list: 2 windings x 2048 x u16 = 8 KB)
+constexpr int kChunkFaces = 1024;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
+constexpr int kPairCap = 8;         // pixels one out-scan task handles before it re-queues its remainder
 
 struct BwdWarp {
     float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot
     int fn[32];
     unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
-    uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9
+    uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 | resume d1 << 19
 };
 
 __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long long v) {
@@ -554,10 +555,15 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 
 // phase 2: one task per lane.  The pixel loop accumulates its two terms in fp32 in pixel order (deterministic for
 // a given task, like the reference's per-face loop); only the task totals go through the fixed-point atomics.
+// Returns 0, or the task word of the remainder when an out scan stops after kPairCap contributing pixels: long
+// scans (a line running along the mismatch band) are cut into pieces so that the 32 lanes of a round do similar
+// amounts of work.
 template <bool FUSED>
-__device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale,
-                                         float gcoef) {
-    const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1, d0 = (int)(t >> 9);
+__device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale,
+                                             float gcoef) {
+    const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1;
+    const int d0 = (int)((t >> 9) & 1023u), resume = (int)(t >> 19);
+    uint32_t cont = 0;
     const int is = m.is;
     float px[3], py[3];
 #pragma unroll
@@ -578,10 +584,11 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
         if (m.fidx[r_in * is + c_in] == fn) {
             int from, to;
             out_scan_range(sp.direction, d1_out, is, &from, &to);
-            from = max(from, (int)((axis == 0) ? m.col_lo[d0] : m.row_lo[d0]));
+            from = max(max(from, (int)((axis == 0) ? m.col_lo[d0] : m.row_lo[d0])), resume);
             to = min(to, (int)((axis == 0) ? m.col_hi[d0] : m.row_hi[d0]));
             const int w_from = from >> 5, w_to = to >> 5;
-            for (int w = w_from; w <= w_to; w++) {
+            int budget = kPairCap;
+            for (int w = w_from; w <= w_to && cont == 0; w++) {
                 uint32_t bits = neg_line_word(m, axis, d0, w);
                 if (w == w_from) bits &= 0xFFFFFFFFu << (from & 31);
                 if (w == w_to) bits &= 0xFFFFFFFFu >> (31 - (to & 31));
@@ -596,6 +603,11 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
                 while (bits) {
                     const int bpos = ctz32(bits);
                     const int d1 = (w << 5) + bpos;
+                    if (budget == 0) {  // hand the rest of the line (from pixel d1 on) to a later round
+                        cont = (t & 0x7FFFFu) | ((uint32_t)d1 << 19);
+                        break;
+                    }
+                    budget--;
                     bits &= bits - 1;
                     float g;
                     if (row_fast) {
@@ -628,6 +640,7 @@ __device__ __forceinline__ void bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& 
     }
     atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], __float2ll_rn(sa * fpscale));
     atomic_add_fixed(&W.acc[((edge + 1) % 3) * 2 + (1 - axis)][slot], __float2ll_rn(sb * fpscale));
+    return cont;
 }
 
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
@@ -638,11 +651,12 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks, float gcoef) {
     extern __shared__ uint32_t smw[];
-    __shared__ float red[kBwdWarps][13];
     __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ BwdWarp s_warp[kBwdWarps];
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
+    __shared__ float s_bsum[2 * kChunkFaces / 32][13];  // pose-gradient partial sums, one row per batch of 32 items
     __shared__ int s_wcount[kBwdWarps], s_woff[kBwdWarps + 1];
+    __shared__ int s_next_batch;
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
@@ -683,6 +697,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         }
     }
     if (lane == 0) s_wcount[warp] = wcount;
+    if (tid == 0) s_next_batch = 0;
 
     // ---- stage the frame's bitmaps (built per frame by k_raster / k_neg_maps)
     {
@@ -753,14 +768,18 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         s_abs = fabsf(scale[0]);
     }
     for (int i = 0; i < 6; i++) Km[i] = s.K[9 * b + i];
-    float acc[13];
-#pragma unroll
-    for (int i = 0; i < 13; i++) acc[i] = 0.0f;
-
     BwdWarp& W = s_warp[warp];
-    // batches of 32 items go to the warps round-robin: a STATIC assignment, so every thread's float accumulators
-    // see the same faces in the same order on every run (bit-reproducible results)
-    for (int batch = warp; batch * 32 < n_items; batch += kBwdWarps) {
+    // Batches of 32 items are handed to the warps dynamically (balance), yet the result does not depend on who
+    // ran what: inside a batch every reduction has a fixed order, and each batch leaves its 13 pose-gradient sums
+    // in its own row of s_bsum, which are added up in batch order at the end (bit-reproducible results).
+    for (;;) {
+        int batch = 0;
+        if (lane == 0) batch = atomicAdd(&s_next_batch, 1);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch * 32 >= n_items) break;
+        float acc[13];
+#pragma unroll
+        for (int i = 0; i < 13; i++) acc[i] = 0.0f;
         const bool have = batch * 32 + lane < n_items;
         float px[3], py[3];
         int ids[3] = {0, 0, 0};
@@ -824,12 +843,25 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             __syncwarp();
             while (n_tasks >= 32) {
                 n_tasks -= 32;
-                bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
+                const uint32_t cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
+                __syncwarp();
+                const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
+                if (cont) W.tasks[n_tasks + __popc(mc & lt_mask)] = cont;
+                n_tasks += __popc(mc);
                 __syncwarp();
             }
         }
-        if (lane < n_tasks) bwd_task<FUSED>(W.tasks[lane], W, m, s.eps, fpscale, gcoef);
-        __syncwarp();
+        while (n_tasks > 0) {  // drain, including the remainders the drain itself produces
+            const int nt = min(n_tasks, 32);
+            n_tasks -= nt;
+            uint32_t cont = 0;
+            if (lane < nt) cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
+            __syncwarp();
+            const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
+            if (cont) W.tasks[n_tasks + __popc(mc & lt_mask)] = cont;
+            n_tasks += __popc(mc);
+            __syncwarp();
+        }
         // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
         if (have) {
 #pragma unroll
@@ -862,19 +894,21 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                 }
             }
         }
+        if (FUSED) {
+#pragma unroll
+            for (int i = 0; i < 13; i++) {
+                for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                if (lane == 0) s_bsum[batch][i] = acc[i];
+            }
+        }
         __syncwarp();
     }
     if (FUSED) {
-#pragma unroll
-        for (int i = 0; i < 13; i++)
-            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-        if (lane == 0)
-            for (int i = 0; i < 13; i++) red[warp][i] = acc[i];
         __syncthreads();
         if (tid < 16) {
             float t = 0.0f;
             if (tid < 13)
-                for (int w = 0; w < kBwdWarps; w++) t += red[w][tid];
+                for (int k = 0; k * 32 < n_items; k++) t += s_bsum[k][tid];
             partials[((size_t)b * nchunks + chunk) * 16 + tid] = t;
         }
     }
@@ -1133,7 +1167,7 @@ int check_plan(const dh_jointopt* p) {
     DH_REQUIRE(p->Rmat && p->smooth_terms && p->loss_counts && p->partials && p->frame_terms,
                "dh_jointopt has a NULL scratch pointer");
     DH_REQUIRE(p->nchunks >= 1 && (p->sil.F + p->nchunks - 1) / p->nchunks <= kChunkFaces,
-               "nchunks must be >= ceil(F / 2048)");
+               "nchunks must be >= ceil(F / 1024)");
     DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
     DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
     return DH_OK;
