@@ -84,7 +84,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// the same arrive delivered to the barrier at this offset in every CTA of `mask` (cluster multicast)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
+// CS = CTAs per cluster along the template (M) tiles.  CS > 1: the CTAs of a cluster work on the same K slice and
+// the same frame tile, so each loads 1/CS of the frame tile and multicasts it to the others -- the frame tile
+// crosses L2 -> SM once per cluster instead of once per CTA (map_b's box is then 320/CS rows).
+template <int CS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             float* __restrict__ partial, int kblocks_total, int kblocks_per_slice, int m_pad, int ldc) {
@@ -103,7 +123,7 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int i = 0; i < STAGES; i++) {
             mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, CS);   // every CTA of the cluster must have drained the stage
         }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -115,8 +135,12 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CS > 1) cluster_sync_all();          // peers' barriers are initialised before anything is multicast
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t cta_rank = 0;
+    if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const uint16_t mc_mask = (uint16_t)((1u << CS) - 1u);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one elected lane)
@@ -129,8 +153,14 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 mbar_expect_tx(full0 + 8 * st, STAGE_BYTES);
                 const int kc = (kb0 + kb) * BK;
                 tma_load_2d(dst, &map_a, full0 + 8 * st, kc, m0);
-                tma_load_2d(dst + A_BYTES, &map_b, full0 + 8 * st, kc, n0);
-                tma_load_2d(dst + A_BYTES + B_BYTES, &map_b, full0 + 8 * st, kc, n0 + BN);
+                if (CS == 1) {
+                    tma_load_2d(dst + A_BYTES, &map_b, full0 + 8 * st, kc, n0);
+                    tma_load_2d(dst + A_BYTES + B_BYTES, &map_b, full0 + 8 * st, kc, n0 + BN);
+                } else {
+                    constexpr int RP = NT * BN / CS;   // rows of the 320-row frame tile this CTA fetches
+                    tma_load_2d_mc(dst + A_BYTES + cta_rank * (RP * BK * 2), &map_b, full0 + 8 * st, kc,
+                                   n0 + (int)cta_rank * RP, mc_mask);
+                }
             }
         }
     } else if (warp == 1) {
@@ -152,7 +182,9 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         umma_bf16(tmem_base + t * BN, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(empty0 + 8 * st);   // frees the stage once these MMAs have read it
+                // frees the stage once these MMAs have read it (in every CTA of the cluster when multicasting)
+                if (CS == 1) umma_commit(empty0 + 8 * st);
+                else         umma_commit_mc(empty0 + 8 * st, mc_mask);
             }
             umma_commit(tfull);                 // accumulators complete
         }
@@ -187,6 +219,7 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CS > 1) cluster_sync_all();          // nobody leaves while peers may still multicast into its smem
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
@@ -283,14 +316,19 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t kdim, int
     return DH_OK;
 }
 
-struct Plan { int m_tiles, n_pairs, nslices, kblocks, kb_per_slice, m_pad, ldc; };
+struct Plan { int m_tiles, n_pairs, nslices, kblocks, kb_per_slice, m_pad, ldc, cs; };
 
 int make_plan(int32_t N, int32_t Fm, int64_t Kdim, Plan* pl) {
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     pl->m_tiles = (N + BM - 1) / BM;
+    // clusters of 4 template tiles share the frame tile by multicast; fewer than 4 tiles: no cluster
+    pl->cs = (pl->m_tiles >= 4) ? 4 : 1;
+    pl->m_tiles = (pl->m_tiles + pl->cs - 1) / pl->cs * pl->cs;
     pl->n_pairs = (Fm + NT * BN - 1) / (NT * BN);
     pl->kblocks = (int)((Kdim + BK - 1) / BK);
+    // clusters of 4 cannot use every SM (GPCs of 16/18/20 SMs hold 4/4/5 clusters): ~136 of 148 SMs
+    if (pl->cs > 1) sms = sms * 136 / 148;
     int ns = sms / (pl->m_tiles * pl->n_pairs);
     if (ns < 1) ns = 1;
     if (ns > pl->kblocks) ns = pl->kblocks;
@@ -331,11 +369,30 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, templ_bf16, N, Kdim, BM);
     if (rc) return rc;
-    rc = make_map(&map_b, frames_bf16, Fm, Kdim, BN);
+    rc = make_map(&map_b, frames_bf16, Fm, Kdim, pl.cs > 1 ? NT * BN / pl.cs : BN);
     if (rc) return rc;
-    DH_CUDA(cudaFuncSetAttribute(k_dino_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    k_dino_gemm<<<dim3(pl.m_tiles, pl.n_pairs, pl.nslices), GEMM_THREADS, SMEM_BYTES, st>>>(
-        map_a, map_b, (float*)workspace, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
+    float* ws = (float*)workspace;
+    if (pl.cs == 1) {
+        DH_CUDA(cudaFuncSetAttribute(k_dino_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        k_dino_gemm<1><<<dim3(pl.m_tiles, pl.n_pairs, pl.nslices), GEMM_THREADS, SMEM_BYTES, st>>>(
+            map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
+    } else {
+        DH_CUDA(cudaFuncSetAttribute(k_dino_gemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl.m_tiles, pl.n_pairs, pl.nslices);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DH_CUDA(cudaLaunchKernelEx(&cfg, k_dino_gemm<4>, map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad,
+                                   pl.ldc));
+    }
     DH_LAUNCH_OK("k_dino_gemm");
     const size_t sm = (size_t)N * sizeof(float);
     DH_CUDA(cudaFuncSetAttribute(k_dino_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

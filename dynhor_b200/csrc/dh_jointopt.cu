@@ -646,7 +646,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMa
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
 // else : scatter dL/d(camera-space vertices) into grad_verts [B,V,3] (float atomics).
 template <bool FUSED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks, float gcoef) {
