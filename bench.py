@@ -354,6 +354,10 @@ def run_dino(args):
     except Exception:
         pass
     ok = bool(torch.equal(i[:, 0].cpu(), d["match"]))
+    import ctypes
+    from dynhor_b200 import _lib
+    plan = (ctypes.c_int32 * 8)()
+    _lib.load().dh_dino_plan_info(N, Fm, P * D, plan)
     # CPU baseline: the reference expression verbatim on a bounded sample of frames
     from oracle import dino_oracle
     nf = 2
@@ -372,6 +376,8 @@ def run_dino(args):
                                 "frac": flops / (ms / 1e3) / 1e12 / tf_peak}},
         "cpu_baseline": {"value": N / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
                          "sample": f"{nf} frames x 1000 templates, pose_initializtion.py:295-296 verbatim + topk"},
+        "plan": dict(zip(["m_tiles", "n_pairs", "k_slices", "kblocks", "kb_per_slice", "cluster", "ctas_sized_for",
+                          "ldc"], list(plan))),
         "planted_match_rank0": ok, "gpu_launches": 2 * args.steps}))
 
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "dh_ipc_close": (c_i, [c_p]),
     "dh_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_l, c_d, c_i, c_p]),
     "dh_dino_workspace_bytes": (c_i, [c_i, c_i, c_l, ctypes.POINTER(c_l)]),
+    "dh_dino_plan_info": (c_i, [c_i, c_i, c_l, ctypes.POINTER(c_i)]),
     "dh_dino_topk": (c_i, [c_p, c_p, c_i, c_i, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "dh_dino_prescale": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
 }

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dh_common.h"
 
@@ -22,7 +23,7 @@ constexpr int BN = 160;        // frames per MMA (UMMA N), two such tiles per CT
 constexpr int NT = 2;
 constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = BN * BK * 2;           // 20 KB
 constexpr int STAGE_BYTES = A_BYTES + NT * B_BYTES;
@@ -316,7 +317,49 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t kdim, int
     return DH_OK;
 }
 
-struct Plan { int m_tiles, n_pairs, nslices, kblocks, kb_per_slice, m_pad, ldc, cs; };
+template <int CS>
+int launch_gemm_cluster(dim3 grid, cudaStream_t st, const CUtensorMap& map_a, const CUtensorMap& map_b, float* ws,
+                        int kblocks, int kb_per_slice, int m_pad, int ldc) {
+    DH_CUDA(cudaFuncSetAttribute(k_dino_gemm<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (CS == 8)
+        DH_CUDA(cudaFuncSetAttribute(k_dino_gemm<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DH_CUDA(cudaLaunchKernelEx(&cfg, k_dino_gemm<CS>, map_a, map_b, ws, kblocks, kb_per_slice, m_pad, ldc));
+    return DH_OK;
+}
+
+template <int CS>
+int max_cluster_ctas() {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    cudaFuncSetAttribute(k_dino_gemm<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_dino_gemm<CS>, &cfg) != cudaSuccess) nclusters = 0;
+    (void)cudaGetLastError();
+    return nclusters * CS;
+}
+
+struct Plan { int m_tiles, n_pairs, nslices, kblocks, kb_per_slice, m_pad, ldc, cs, max_ctas; };
 
 int make_plan(int32_t N, int32_t Fm, int64_t Kdim, Plan* pl) {
     int sms = 148, dev = 0;
@@ -324,11 +367,19 @@ int make_plan(int32_t N, int32_t Fm, int64_t Kdim, Plan* pl) {
     pl->m_tiles = (N + BM - 1) / BM;
     // clusters of 4 template tiles share the frame tile by multicast; fewer than 4 tiles: no cluster
     pl->cs = (pl->m_tiles >= 4) ? 4 : 1;
+    if (const char* e = getenv("DH_DINO_CLUSTER")) {   // tuning knob: 1, 2, 4 or 8
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) pl->cs = v;
+    }
     pl->m_tiles = (pl->m_tiles + pl->cs - 1) / pl->cs * pl->cs;
     pl->n_pairs = (Fm + NT * BN - 1) / (NT * BN);
     pl->kblocks = (int)((Kdim + BK - 1) / BK);
-    // clusters of 4 cannot use every SM (GPCs of 16/18/20 SMs hold 4/4/5 clusters): ~136 of 148 SMs
-    if (pl->cs > 1) sms = sms * 136 / 148;
+    // clusters cannot use every SM (they are placed inside one GPC): ask the driver how many fit at once
+    if (pl->cs > 1) {
+        const int c = pl->cs == 2 ? max_cluster_ctas<2>() : (pl->cs == 4 ? max_cluster_ctas<4>() : max_cluster_ctas<8>());
+        sms = c > 0 ? c : sms * 128 / 148;
+    }
+    pl->max_ctas = sms;
     int ns = sms / (pl->m_tiles * pl->n_pairs);
     if (ns < 1) ns = 1;
     if (ns > pl->kblocks) ns = pl->kblocks;
@@ -349,6 +400,15 @@ int dh_dino_workspace_bytes(int32_t N, int32_t Fm, int64_t Kdim, int64_t* bytes)
     Plan pl;
     make_plan(N, Fm, Kdim, &pl);
     *bytes = (int64_t)pl.nslices * pl.m_pad * pl.ldc * 4;
+    return DH_OK;
+}
+
+int dh_dino_plan_info(int32_t N, int32_t Fm, int64_t Kdim, int32_t* out8) {
+    DH_REQUIRE(out8 != nullptr && N > 0 && Fm > 0 && Kdim > 0, "bad arguments");
+    Plan pl;
+    make_plan(N, Fm, Kdim, &pl);
+    out8[0] = pl.m_tiles; out8[1] = pl.n_pairs; out8[2] = pl.nslices; out8[3] = pl.kblocks;
+    out8[4] = pl.kb_per_slice; out8[5] = pl.cs; out8[6] = pl.max_ctas; out8[7] = pl.ldc;
     return DH_OK;
 }
 
@@ -377,21 +437,11 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
         k_dino_gemm<1><<<dim3(pl.m_tiles, pl.n_pairs, pl.nslices), GEMM_THREADS, SMEM_BYTES, st>>>(
             map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
     } else {
-        DH_CUDA(cudaFuncSetAttribute(k_dino_gemm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pl.m_tiles, pl.n_pairs, pl.nslices);
-        cfg.blockDim = dim3(GEMM_THREADS);
-        cfg.dynamicSmemBytes = SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 4;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        DH_CUDA(cudaLaunchKernelEx(&cfg, k_dino_gemm<4>, map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad,
-                                   pl.ldc));
+        const dim3 grid(pl.m_tiles, pl.n_pairs, pl.nslices);
+        if (pl.cs == 2)      rc = launch_gemm_cluster<2>(grid, st, map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
+        else if (pl.cs == 4) rc = launch_gemm_cluster<4>(grid, st, map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
+        else                 rc = launch_gemm_cluster<8>(grid, st, map_a, map_b, ws, pl.kblocks, pl.kb_per_slice, pl.m_pad, pl.ldc);
+        if (rc) return rc;
     }
     DH_LAUNCH_OK("k_dino_gemm");
     const size_t sm = (size_t)N * sizeof(float);

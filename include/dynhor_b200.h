@@ -174,6 +174,9 @@ int dh_adam_step(float* param, const float* grad, float* m, float* v, int64_t n,
  * lowest index first on exact ties).
  * ------------------------------------------------------------------------------------------------ */
 int dh_dino_workspace_bytes(int32_t N, int32_t Fm, int64_t Kdim, int64_t* bytes);
+/* launch plan of dh_dino_topk: out8 = template tiles, frame tile pairs, K slices, k-blocks, k-blocks per slice,
+ * cluster size, co-resident CTAs the plan was sized for, workspace row pitch */
+int dh_dino_plan_info(int32_t N, int32_t Fm, int64_t Kdim, int32_t* out8);
 int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int32_t Fm, int64_t Kdim, int32_t k,
                  float* scores, float* topk_vals, int32_t* topk_idx, void* workspace, int64_t workspace_bytes,
                  void* stream);

@@ -91,3 +91,11 @@ def test_select_view_matches_reference_gating():
     prev = R[int(top[2])].T.unsqueeze(0).contiguous()
     idx = select_view(cos, top, R, prev, former_max_idx=int(top[2]))
     assert idx == int(top[2])
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "8"])
+def test_dino_cluster_variants(cluster, monkeypatch):
+    """The multicast GEMM with other cluster sizes than the default 4 (tuning knob DH_DINO_CLUSTER), including a
+    template count that needs padded tiles (N = 1100 -> 9 tiles -> 10/12/16 with clusters of 2/4/8)."""
+    monkeypatch.setenv("DH_DINO_CLUSTER", cluster)
+    _run(1100, 50, 24, 64, 5, seed=5)
