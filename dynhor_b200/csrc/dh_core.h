@@ -440,12 +440,19 @@ DH_HD void edge_coefs(float p00, float p10, int d0, EdgeCoef& c) {
     c.ka = (p10 != (float)d0) ? (p10 - p00) / (p10 - (float)d0) : 0.0f;
     c.kb = (p00 != (float)d0) ? (p10 - p00) / ((float)d0 - p00) : 0.0f;
 }
-DH_HD float edge_term_fast(float k, float diff, int d1, float d1_cross, float eps, float two_over_is, bool pow2,
-                           int is) {
-    const float t = k * ((float)d1 - d1_cross);
-    float dist = pow2 ? t * two_over_is : (t * 2.0f) / (float)is;
+// Branch-free: k == 0 (term skipped by the reference) yields 0.  dist = k (d1 - d1_cross) (2/is) +- eps never gets
+// below eps in magnitude, so the raw reciprocal approximation is safe.
+DH_HD float edge_term_fast(float k, float diff, int d1, float d1_cross, float eps, float two_over_is) {
+    float dist = (k * ((float)d1 - d1_cross)) * two_over_is;
     dist = (0.0f < dist) ? dist + eps : dist - eps;
-    return DH_APPROX_DIV(diff, dist);
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dist));
+    const float t = diff * r;
+#else
+    const float t = diff / dist;
+#endif
+    return (k != 0.0f) ? t : 0.0f;
 }
 
 // Pseudo-gradient of the loss w.r.t. the NDC (x,y) of the three vertices of face `fn`, one face per call (the

@@ -576,7 +576,6 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMa
     const int fn = W.fn[slot];
     EdgeCoef ec;
     edge_coefs(sp.p00, sp.p10, d0, ec);
-    const bool pow2 = (is & (is - 1)) == 0;
     const float two_over_is = 2.0f / (float)is;
     float sa = 0.0f, sb = 0.0f;
     if (kind == 0) {
@@ -619,8 +618,8 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMa
                     }
                     const float diff = (0.0f - 1.0f) * g;
                     if (diff <= 0.0f) continue;
-                    if (ec.ka != 0.0f) sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is);
-                    if (ec.kb != 0.0f) sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is);
+                    sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is);
+                    sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is);
                 }
             }
         }
@@ -634,8 +633,8 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMa
             if (m.fidx[r * is + c] != fn) continue;
             const float diff = (1.0f - 0.0f) * grad_value<FUSED>(m, r, c, false, gcoef);
             if (diff <= 0.0f) continue;
-            if (ec.ka != 0.0f) sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is, pow2, is);
-            if (ec.kb != 0.0f) sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is, pow2, is);
+            sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is);
+            sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is);
         }
     }
     atomic_add_fixed(&W.acc[edge * 2 + (1 - axis)][slot], __float2ll_rn(sa * fpscale));
