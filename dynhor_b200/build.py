@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
     objs = []
     for s in srcs:
         obj = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + ARCH + COMMON + SOURCES[s] + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [_nvcc()] + ARCH + COMMON + SOURCES[s] + os.environ.get("DH_EXTRA_NVCC_FLAGS", "").split() + \
+              (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             print(" ".join(cmd))

@@ -475,7 +475,10 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 constexpr int kBwdWarps = kThreads / 32;
 constexpr int kTaskCap = 96;
 constexpr int kChunkFaces = 1024;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
-constexpr int kPairCap = 8;         // pixels one out-scan task handles before it re-queues its remainder
+#ifndef DH_PAIR_CAP
+#define DH_PAIR_CAP 8
+#endif
+constexpr int kPairCap = DH_PAIR_CAP;  // pixels one out-scan task handles before it re-queues its remainder
 
 struct BwdWarp {
     float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot

@@ -129,6 +129,8 @@ class FusedJointOpt:
         self.hist = z(max(self.max_iters, 1), 4, dt=torch.float64)
         self.halo = z(2, 9)
         self.edge = z(2, 9)
+        import os
+        nchunks = nchunks or int(os.environ.get("DH_BWD_CHUNKS", "0"))  # tuning knob
         self.nchunks = int(nchunks) if nchunks else lib.dh_jointopt_default_chunks(B, self.sil.F)
         sizes = (ctypes.c_int64 * 5)()
         _lib.check(lib.dh_jointopt_scratch_bytes(B, self.nchunks, sizes), "dh_jointopt_scratch_bytes")

@@ -160,8 +160,59 @@ def geometry_case(ref):
     print("geometry ->", path)
 
 
+def stage1_case():
+    """ObjTracker.coarse_forward + the mode="coarse" loop of find_optimal_pose (pose_initializtion.py:143-155,
+    346-358), reference code unmodified.  pose_initializtion.py imports pytorch3d / detectron2 names at module
+    level (:17-30); they are only used by the textured `forward` path, so empty stand-in modules are enough."""
+    for name, attrs in {
+        "pytorch3d": [], "pytorch3d.renderer": ["PerspectiveCameras", "RasterizationSettings", "MeshRenderer",
+                                                "MeshRasterizer", "SoftPhongShader", "SoftSilhouetteShader",
+                                                "BlendParams"],
+        "pytorch3d.structures": ["Meshes"], "detectron2": [], "detectron2.structures": ["BitMasks", "BoxMode"],
+        "detectron2.layers": ["ROIAlign"], "detectron2.structures.boxes": ["BoxMode"],
+        "detectron2.layers.roi_align": ["ROIAlign"],
+    }.items():
+        m = types.ModuleType(name)
+        for a in attrs:
+            setattr(m, a, type(a, (), {"__init__": lambda self, *a, **k: None}))
+        sys.modules.setdefault(name, m)
+    import pose_initializtion as ref_pi  # noqa
+    B, size = 1, 128
+    seq = synth.make_sequence(3, mesh="ico3", seed=6, render_fn=oracle_render_fn, size=size)
+    f = 1  # one frame, like the reference's per-frame loop
+    K = torch.from_numpy(seq["K_roi"][f:f + 1].copy())
+    rot6d = torch.from_numpy(seq["rot6d_init"][f:f + 1].copy())
+    trans = torch.from_numpy(seq["T_init"][f:f + 1].copy())
+    model = ref_pi.ObjTracker(ref_image=seq["target_masks"][f], vertices=torch.from_numpy(seq["verts"]),
+                              faces=torch.from_numpy(seq["faces"])[None], textures=None, dino_model=None,
+                              gt_dino_feat=torch.zeros(1), rotation_init=rot6d, translation_init=trans,
+                              num_initializations=1, K=K)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    losses, ious = [], []
+    g0 = None
+    for it in range(6):
+        opt.zero_grad()
+        loss_dict, iou = model.coarse_forward()
+        total = sum(loss_dict.values()).sum()
+        total.backward()
+        if it == 0:
+            g0 = (model.rotations.grad.numpy().copy(), model.translations.grad.numpy().copy())
+        opt.step()
+        losses.append(float(total.detach()))
+        ious.append(iou.numpy().copy())
+    path = os.path.join(ROOT, "tests", "golden", "stage1_coarse.npz")
+    np.savez_compressed(path, verts=seq["verts"], faces=seq["faces"].astype(np.int32), K_roi=K.numpy(),
+                        target_mask=seq["target_masks"][f].astype(np.int8), rot6d_init=rot6d.numpy(),
+                        trans_init=trans.numpy(), lr=np.float64(0.01), ref_loss=np.asarray(losses),
+                        ref_iou=np.asarray(ious), ref_grad_rot=g0[0], ref_grad_trans=g0[1],
+                        ref_final_rot=model.rotations.detach().numpy(),
+                        ref_final_trans=model.translations.detach().numpy())
+    print("stage1_coarse ->", path, "loss", losses[0], "->", losses[-1], "iou", ious[0], "->", ious[-1])
+
+
 def main():
     ref = import_reference()
+    stage1_case()
     geometry_case(ref)
     lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}  # configs/custom_shoes.yaml:17-18
     run_case("s64_b5", ref, B=5, mesh="ico3", size=64, iters=8, lr=1e-4, lw=lw, seed=1)

@@ -397,3 +397,32 @@ def test_error_behaviour():
         f = torch.zeros(2, 5, 3, dtype=torch.int64).cuda()
         f[1, 0, 0] = 1
         shared_faces(f)
+
+
+def test_stage1_coarse_silhouette_term_vs_reference_run():
+    """the silhouette term of the per-frame pose initialisation (ObjTracker.coarse_forward, the
+    anti_aliasing=False renderer, 1 - IoU + off-screen penalty, Adam) against a run of the reference's own
+    pose_initializtion.py code (tests/golden/stage1_coarse.npz)."""
+    from dynhor_b200.pose_init import ObjTracker
+    g = np.load(os.path.join(GOLDEN, "stage1_coarse.npz"))
+    model = ObjTracker(ref_image=g["target_mask"].astype(np.float32), vertices=torch.from_numpy(g["verts"]),
+                       faces=torch.from_numpy(g["faces"].astype(np.int64))[None],
+                       rotation_init=torch.from_numpy(g["rot6d_init"]), translation_init=torch.from_numpy(g["trans_init"]),
+                       num_initializations=1, K=torch.from_numpy(g["K_roi"]))
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]))
+    losses, ious = [], []
+    for it in range(len(g["ref_loss"])):
+        opt.zero_grad()
+        loss_dict, iou = model.coarse_forward()
+        total = sum(loss_dict.values()).sum()
+        total.backward()
+        if it == 0:
+            assert rel_err(model.rotations.grad.cpu().numpy(), g["ref_grad_rot"]) < GRAD_RTOL
+            assert rel_err(model.translations.grad.cpu().numpy(), g["ref_grad_trans"]) < GRAD_RTOL
+        opt.step()
+        losses.append(float(total.detach()))
+        ious.append(iou.cpu().numpy())
+    assert abs(losses[0] - g["ref_loss"][0]) <= LOSS_RTOL * g["ref_loss"][0]
+    assert np.array_equal(ious[0], g["ref_iou"][0])          # IoU of identical coverage: exact
+    assert np.allclose(losses, g["ref_loss"], rtol=TRAJ_RTOL)
+    assert np.allclose(np.asarray(ious), g["ref_iou"], atol=1e-3)
