@@ -296,13 +296,17 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
     B_total = len(object_parameters)
     shard = detect_shard(B_total) if shard is None else shard
     verts_object_og = tensorify(objvertices).cuda()
-    faces_object = tensorify(objfaces).cuda()
+    # faces: run.py:158 stacks one face list per frame; only this rank's frames are uploaded and checked
+    faces_host = tensorify(objfaces)
+    faces_local = (faces_host[shard.start:shard.stop] if faces_host.ndim == 3 else faces_host).cuda()
     local = shard.slice(object_parameters)
-    obj_trans = torch.cat([obj["translations"] for obj in local])
-    obj_rots = torch.cat([obj["rotations"] for obj in local])
-    obj_tar_masks = torch.cat([obj["target_masks"] for obj in local])
-    obj_camintr_roi = torch.cat([obj["K_roi"][:, 0] for obj in local])
-    faces_local = faces_object[shard.start:shard.stop] if faces_object.ndim == 3 else faces_object
+    # Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors are accepted too: the small
+    # ones are concatenated on the host, the masks go up frame by frame (no 78 MB host-side concatenation) and the
+    # ref / keep masks are derived on the device.
+    obj_trans = torch.cat([obj["translations"] for obj in local]).cuda()
+    obj_rots = torch.cat([obj["rotations"] for obj in local]).cuda()
+    obj_camintr_roi = torch.cat([obj["K_roi"][:, 0] for obj in local]).cuda()
+    obj_tar_masks = torch.cat([obj["target_masks"].cuda(non_blocking=True) for obj in local])
     model = Joint_Optimizer(
         translations_object=obj_trans, rotations_object=obj_rots, verts_object_og=verts_object_og,
         faces_object=faces_local, target_masks_object=obj_tar_masks, camintr_rois_object=obj_camintr_roi,
