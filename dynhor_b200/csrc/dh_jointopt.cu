@@ -24,7 +24,11 @@ namespace {
 using namespace dh;
 
 constexpr int kSH = 16;            // strip height in raster rows
-constexpr int kThreads = 256;      // CTA size of the raster / backward / elementwise kernels
+constexpr int kThreads = 256;      // CTA size of the backward / elementwise kernels
+#ifndef DH_RASTER_THREADS
+#define DH_RASTER_THREADS 384
+#endif
+constexpr int kRasterThreads = DH_RASTER_THREADS;  // 12 warps x 2 CTAs/SM: the 64 KB z-buffer strip caps CTAs/SM at 2
 constexpr int kMaxIS = 512;        // largest raster resolution (bitmaps + z-buffer strip must fit shared memory)
 
 __host__ __device__ inline int raster_size(const dh_sil& s) { return s.aa ? 2 * s.S : s.S; }
@@ -233,19 +237,19 @@ __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32
 // FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
 // else : epilogue writes the pooled, flipped silhouette `rend` (the renderer's return value).
 template <bool FUSED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kRasterThreads)
 k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float* __restrict__ rend,
          int32_t* __restrict__ loss_counts) {
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
     __shared__ uint32_t abits[kSH][kMaxIS / 32];
-    __shared__ int red[3][kThreads / 32];
+    __shared__ int red[3][kRasterThreads / 32];
     __shared__ float s_ndc[kMaxIS];                    // NDC coordinate of every pixel centre
-    __shared__ float s_setup[kThreads / 32][13][32];   // per warp: inv[9], z[3], zcull of the batch's faces
-    __shared__ float s_geo[kThreads / 32][6][32];      // per warp: NDC x[3], y[3]
-    __shared__ uint32_t s_box[kThreads / 32][32];      // x_lo | x_hi << 10 | local first row << 20
-    __shared__ int s_start[kThreads / 32][32];         // first row-item of every face of the batch
-    __shared__ int s_fn[kThreads / 32][32];
-    __shared__ uint32_t s_queue[kThreads / 32][64];    // pending (lane slot, x, local row) hits
+    __shared__ float s_setup[kRasterThreads / 32][13][32];   // per warp: inv[9], z[3], zcull of the batch's faces
+    __shared__ float s_geo[kRasterThreads / 32][6][32];      // per warp: NDC x[3], y[3]
+    __shared__ uint32_t s_box[kRasterThreads / 32][32];      // x_lo | x_hi << 10 | local first row << 20
+    __shared__ int s_start[kRasterThreads / 32][32];         // first row-item of every face of the batch
+    __shared__ int s_fn[kRasterThreads / 32][32];
+    __shared__ uint32_t s_queue[kRasterThreads / 32][64];    // pending (lane slot, x, local row) hits
     __shared__ int s_next[2];
     const int is = raster_size(s);
     const int nstrips = is / kSH;
@@ -254,9 +258,9 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int tid = threadIdx.x;
     const int owned_words = (2 * s.F + 31) >> 5;
     uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
-    for (int i = tid; i < kSH * is; i += kThreads) zbuf[i] = DH_ZKEY_EMPTY;
-    for (int i = tid; i < owned_words; i += kThreads) s_owned[i] = 0u;
-    for (int i = tid; i < is; i += kThreads) s_ndc[i] = pix_to_ndc(i, is);
+    for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    for (int i = tid; i < owned_words; i += kRasterThreads) s_owned[i] = 0u;
+    for (int i = tid; i < is; i += kRasterThreads) s_ndc[i] = pix_to_ndc(i, is);
     if (tid < 2) s_next[tid] = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
     __syncthreads();
@@ -269,7 +273,11 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     // dynamically.  Per batch: (1) lane = face: set-up; (2) lane = (face, row): analytic x-span of the row, then
     // the exact edge tests pixel by pixel, survivors compacted into a per-warp queue; (3) whenever 32 hits are
     // pending, lane = hit: depth (the expensive IEEE divisions) and z-buffer update at full lane occupancy.
-    for (int pass = 0; pass < 2; pass++) {
+#ifndef DH_PASS_ORDER
+#define DH_PASS_ORDER 0
+#endif
+    for (int pass_i = 0; pass_i < 2; pass_i++) {
+        const int pass = pass_i ^ DH_PASS_ORDER;
         const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
         for (;;) {
             int base = 0;
@@ -368,7 +376,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     int32_t* fidx = s.fidx + (size_t)b * is * is + (size_t)row0 * is;
     uint32_t* abits_g = s.alpha_bits + ((size_t)b * is + row0) * wpr;
     for (int r = 0; r < kSH; r++) {
-        for (int c = tid; c < is; c += kThreads) {
+        for (int c = tid; c < is; c += kRasterThreads) {
             const int i = r * is + c;
             const unsigned long long key = zbuf[i];
             const bool cov = key != DH_ZKEY_EMPTY;
@@ -386,7 +394,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         }
     }
     __syncthreads();
-    for (int i = tid; i < owned_words; i += kThreads) {
+    for (int i = tid; i < owned_words; i += kRasterThreads) {
         const uint32_t w = s_owned[i];
         if (w) atomicOr(&s.owned[(size_t)b * owned_words + i], w);
     }
@@ -395,7 +403,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int cell_rows = s.aa ? kSH / 2 : kSH;
     const int wprp = (S + 31) >> 5;
     int sse = 0, inter = 0, uni = 0;
-    for (int ci = tid; ci < cell_rows * S; ci += kThreads) {
+    for (int ci = tid; ci < cell_rows * S; ci += kRasterThreads) {
         const int ly = ci / S, x = ci - ly * S;
         int pop, yo;
         if (s.aa) {
@@ -437,7 +445,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         __syncthreads();
         if (tid < 3) {
             int t = 0;
-            for (int w = 0; w < kThreads / 32; w++) t += red[tid][w];
+            for (int w = 0; w < kRasterThreads / 32; w++) t += red[tid][w];
             if (t) atomicAdd(&loss_counts[b * 4 + tid], t);
         }
     }
@@ -1131,7 +1139,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         if (rc) return rc;
         // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
         const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
-        k_raster<true><<<dim3(nstrips, B), kThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
+        k_raster<true><<<dim3(nstrips, B), kRasterThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
         DH_LAUNCH_OK("k_raster");
         DH_REC(4);
         if (mode != 2) {
@@ -1224,7 +1232,7 @@ int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* s
     const size_t zb = raster_smem_bytes(*s);
     rc = set_smem(k_raster<false>, zb);
     if (rc) return rc;
-    k_raster<false><<<dim3(nstrips, s->B), kThreads, zb, st>>>(*s, nullptr, 0.0f, rend, nullptr);
+    k_raster<false><<<dim3(nstrips, s->B), kRasterThreads, zb, st>>>(*s, nullptr, 0.0f, rend, nullptr);
     DH_LAUNCH_OK("k_raster");
     return DH_OK;
 }
