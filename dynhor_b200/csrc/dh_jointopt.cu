@@ -29,6 +29,7 @@ constexpr int kThreads = 256;      // CTA size of the backward / elementwise ker
 #define DH_RASTER_THREADS 384
 #endif
 constexpr int kRasterThreads = DH_RASTER_THREADS;  // 12 warps x 2 CTAs/SM: the 64 KB z-buffer strip caps CTAs/SM at 2
+constexpr int kOwnedSmemWords = 1024;
 constexpr int kMaxIS = 512;        // largest raster resolution (bitmaps + z-buffer strip must fit shared memory)
 
 __host__ __device__ inline int raster_size(const dh_sil& s) { return s.aa ? 2 * s.S : s.S; }
@@ -257,9 +258,14 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int row0 = strip * kSH;
     const int tid = threadIdx.x;
     const int owned_words = (2 * s.F + 31) >> 5;
+    // the face-owns-a-pixel bitmap is staged in shared memory when it is small (<= 4 KB, F <= 16384); for larger
+    // meshes the bits go straight to global memory so that the CTA still fits twice per SM
+    const bool owned_smem = owned_words <= kOwnedSmemWords;
     uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
+    uint32_t* g_owned = s.owned + (size_t)b * owned_words;
     for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
-    for (int i = tid; i < owned_words; i += kRasterThreads) s_owned[i] = 0u;
+    if (owned_smem)
+        for (int i = tid; i < owned_words; i += kRasterThreads) s_owned[i] = 0u;
     for (int i = tid; i < is; i += kRasterThreads) s_ndc[i] = pix_to_ndc(i, is);
     if (tid < 2) s_next[tid] = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
@@ -385,7 +391,8 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the
             // same face along a row set the bit once
             const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
-            if (cov && ((tid & 31) == 0 || fn_left != fn)) atomicOr(&s_owned[fn >> 5], 1u << (fn & 31));
+            if (cov && ((tid & 31) == 0 || fn_left != fn))
+                atomicOr(owned_smem ? &s_owned[fn >> 5] : &g_owned[fn >> 5], 1u << (fn & 31));
             const uint32_t word = __ballot_sync(0xffffffffu, cov);
             if ((tid & 31) == 0) {
                 abits[r][c >> 5] = word;
@@ -394,10 +401,11 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         }
     }
     __syncthreads();
-    for (int i = tid; i < owned_words; i += kRasterThreads) {
-        const uint32_t w = s_owned[i];
-        if (w) atomicOr(&s.owned[(size_t)b * owned_words + i], w);
-    }
+    if (owned_smem)
+        for (int i = tid; i < owned_words; i += kRasterThreads) {
+            const uint32_t w = s_owned[i];
+            if (w) atomicOr(&g_owned[i], w);
+        }
     // ---- epilogue 2: output-resolution cells of this strip (2x2 average pool + vertical flip)
     const int S = s.S;
     const int cell_rows = s.aa ? kSH / 2 : kSH;
@@ -1086,8 +1094,10 @@ int check_sil(const dh_sil* s) {
     return DH_OK;
 }
 
-size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + face-owns-a-pixel bitmap
-    return (size_t)kSH * raster_size(s) * sizeof(unsigned long long) + (size_t)((2 * s.F + 31) / 32) * sizeof(uint32_t);
+size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-owns-a-pixel bitmap
+    const int words = (2 * s.F + 31) / 32;
+    return (size_t)kSH * raster_size(s) * sizeof(unsigned long long) +
+           (size_t)(words <= kOwnedSmemWords ? words : 0) * sizeof(uint32_t);
 }
 
 size_t bwd_smem_bytes(const dh_sil& s) {

@@ -426,3 +426,30 @@ def test_stage1_coarse_silhouette_term_vs_reference_run():
     assert np.array_equal(ious[0], g["ref_iou"][0])          # IoU of identical coverage: exact
     assert np.allclose(losses, g["ref_loss"], rtol=TRAJ_RTOL)
     assert np.allclose(np.asarray(ious), g["ref_iou"], atol=1e-3)
+
+
+def test_20k_vertex_mesh_frame_vs_oracle():
+    """BASELINE configs[2] frame shape (kettle-like: 20k-vertex mesh, V=20002, F=40000; the 1080x1920 camera only
+    changes K_roi): one frame against the CPU oracle.  Exercises the large-mesh paths (40 backward chunks, owned-face
+    bitmap in global memory)."""
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import FusedJointOpt
+    from oracle import jointopt_oracle as jo
+    seq = synth.make_sequence(2, H=1080, W=1920, mesh="uv100x200", seed=9, render_fn=_gpu_render_fn, period=1000)
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    model = _model_from_seq(seq)
+    fused = FusedJointOpt(model, lw, 1e-4, 4)
+    ev = fused.evaluate()
+    g_rot, g_tr, _ = fused.grads()
+    orc = jo.JointOptOracle(seq["rot6d_init"], seq["T_init"], seq["verts"], seq["faces"], seq["K_roi"],
+                            seq["target_masks"], lr=1e-4)
+    with torch.no_grad():
+        rend_o = orc.render().numpy()
+        rend_g = model.losses.sil_renderer(model.get_verts_object(), model.faces_object, mode="silhouettes")
+    assert np.array_equal(rend_g.cpu().numpy(), rend_o)
+    out, grads = orc.loss_and_grads(lw)
+    assert abs(ev["loss_sil_obj"][0] - out["loss_sil_obj"]) <= LOSS_RTOL * out["loss_sil_obj"]
+    assert abs(ev["loss_smooth_obj"][0] - out["loss_smooth_obj"]) <= LOSS_RTOL * out["loss_smooth_obj"]
+    for b in range(2):
+        assert rel_err(g_rot[b].cpu().numpy(), grads["rot6d"][b]) < GRAD_RTOL, b
+        assert rel_err(g_tr[b].cpu().numpy(), grads["trans"][b]) < GRAD_RTOL, b
