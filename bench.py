@@ -385,7 +385,7 @@ def run_dino(args):
                          "sample": f"{nf} frames x 1000 templates, pose_initializtion.py:295-296 verbatim + topk"},
         "plan": dict(zip(["m_tiles", "n_pairs", "k_slices", "kblocks", "kb_per_slice", "cluster", "ctas_sized_for",
                           "ldc"], list(plan))),
-        "planted_match_rank0": ok, "gpu_launches": 2 * args.steps}))
+        "planted_match_rank0": ok, "gpu_launches": 3 * args.steps}))
 
 
 def main():

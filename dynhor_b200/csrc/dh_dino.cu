@@ -7,8 +7,9 @@
 //               tcgen05.mma (one elected thread, accumulators in TMEM) -> tcgen05.ld epilogue.  The output is only
 //               N x Fm (1000 x 300) while K is ~5e5, so the grid splits K: one CTA per (128-template tile, 320-frame
 //               tile, K slice), each streaming its slice once; partial tiles go to a small fp32 workspace.
-// k_dino_topk   per frame: sum of the K-slice partials (split-K reduction) fused with the top-k selection
-//               (torch.topk / argmax semantics of pose_initializtion.py:299,309; ties -> lowest index).
+// k_dino_reduce split-K reduction of the partial tiles into scores [Fm, N] (coalesced both ways via a smem transpose).
+// k_dino_topk   per frame: top-k selection (torch.topk / argmax semantics of pose_initializtion.py:299,309;
+//               ties -> lowest index).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -226,21 +227,38 @@ k_dino_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
 }
 
-// One CTA per frame: scores[f, n] = sum_slices partial[slice, n, f]; then k rounds of block-wide arg-max
-// (largest value, lowest index on ties), which is torch.topk(largest=True)'s order on tie-free data.
+// Split-K reduction: scores[f, n] = sum_slices partial[slice, n, f], through a 32x32 shared-memory transpose so that
+// both the partial reads (frames contiguous) and the score writes (templates contiguous) are coalesced.
 __global__ void __launch_bounds__(256)
-k_dino_topk(const float* __restrict__ partial, int nslices, int m_pad, int ldc, int N, int k,
-            float* __restrict__ scores, float* __restrict__ topk_vals, int32_t* __restrict__ topk_idx) {
+k_dino_reduce(const float* __restrict__ partial, int nslices, int m_pad, int ldc, int N, int Fm,
+              float* __restrict__ scores) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int nl = ty; nl < 32; nl += 8) {
+        float acc = 0.0f;
+        const int n = n0 + nl, f = f0 + tx;
+        if (n < N && f < Fm)
+            for (int s = 0; s < nslices; s++) acc += partial[((size_t)s * m_pad + n) * ldc + f];
+        tile[nl][tx] = acc;
+    }
+    __syncthreads();
+    for (int fl = ty; fl < 32; fl += 8) {
+        const int f = f0 + fl, n = n0 + tx;
+        if (f < Fm && n < N) scores[(size_t)f * N + n] = tile[tx][fl];
+    }
+}
+
+// One CTA per frame: k rounds of block-wide arg-max over scores[f, :] (largest value, lowest index on ties), which
+// is torch.topk(largest=True)'s order on tie-free data (pose_initializtion.py:299,309).
+__global__ void __launch_bounds__(256)
+k_dino_topk(const float* __restrict__ scores, int N, int k, float* __restrict__ topk_vals,
+            int32_t* __restrict__ topk_idx) {
     extern __shared__ float s_scores[];  // [N]
     __shared__ float s_bv[8];
     __shared__ int s_bi[8];
     const int f = blockIdx.x, tid = threadIdx.x;
-    for (int n = tid; n < N; n += 256) {
-        float acc = 0.0f;
-        for (int s = 0; s < nslices; s++) acc += partial[((size_t)s * m_pad + n) * ldc + f];
-        s_scores[n] = acc;
-        if (scores != nullptr) scores[(size_t)f * N + n] = acc;
-    }
+    for (int n = tid; n < N; n += 256) s_scores[n] = scores[(size_t)f * N + n];
     __syncthreads();
     for (int j = 0; j < k; j++) {
         float bv = -3.0e38f;
@@ -399,7 +417,8 @@ int dh_dino_workspace_bytes(int32_t N, int32_t Fm, int64_t Kdim, int64_t* bytes)
     DH_REQUIRE(bytes != nullptr && N > 0 && Fm > 0 && Kdim > 0, "bad arguments");
     Plan pl;
     make_plan(N, Fm, Kdim, &pl);
-    *bytes = (int64_t)pl.nslices * pl.m_pad * pl.ldc * 4;
+    // split-K partial tiles + a [Fm, N] score matrix (used when the caller does not ask for the scores)
+    *bytes = (int64_t)pl.nslices * pl.m_pad * pl.ldc * 4 + (int64_t)Fm * N * 4;
     return DH_OK;
 }
 
@@ -424,7 +443,9 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
     if ((size_t)N * sizeof(float) > 200 * 1024) return dh::fail(DH_ERR_UNSUPPORTED, "N > 51200 templates");
     Plan pl;
     make_plan(N, Fm, Kdim, &pl);
-    DH_REQUIRE(workspace_bytes >= (int64_t)pl.nslices * pl.m_pad * pl.ldc * 4, "workspace too small");
+    const int64_t part_bytes = (int64_t)pl.nslices * pl.m_pad * pl.ldc * 4;
+    DH_REQUIRE(workspace_bytes >= part_bytes + (int64_t)Fm * N * 4, "workspace too small");
+    float* score_buf = scores != nullptr ? scores : reinterpret_cast<float*>((char*)workspace + part_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap map_a, map_b;
     int rc = make_map(&map_a, templ_bf16, N, Kdim, BM);
@@ -444,10 +465,12 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
         if (rc) return rc;
     }
     DH_LAUNCH_OK("k_dino_gemm");
+    k_dino_reduce<<<dim3((N + 31) / 32, (Fm + 31) / 32), 256, 0, st>>>((const float*)workspace, pl.nslices, pl.m_pad,
+                                                                       pl.ldc, N, Fm, score_buf);
+    DH_LAUNCH_OK("k_dino_reduce");
     const size_t sm = (size_t)N * sizeof(float);
     DH_CUDA(cudaFuncSetAttribute(k_dino_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_dino_topk<<<Fm, 256, sm, st>>>((const float*)workspace, pl.nslices, pl.m_pad, pl.ldc, N, k, scores, topk_vals,
-                                     topk_idx);
+    k_dino_topk<<<Fm, 256, sm, st>>>(score_buf, N, k, topk_vals, topk_idx);
     DH_LAUNCH_OK("k_dino_topk");
     return DH_OK;
 }

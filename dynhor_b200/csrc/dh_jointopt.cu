@@ -501,6 +501,7 @@ struct BwdWarp {
     int fn[32];
     unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
     uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 | resume d1 << 19
+    float tcross[kTaskCap];              // d1_cross of the task's crossing (computed once, in phase 1)
 };
 
 __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long long v) {
@@ -578,20 +579,30 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 // scans (a line running along the mismatch band) are cut into pieces so that the 32 lanes of a round do similar
 // amounts of work.
 template <bool FUSED>
-__device__ __forceinline__ uint32_t bwd_task(uint32_t t, BwdWarp& W, const BwdMaps& m, float eps, float fpscale,
-                                             float gcoef) {
+__device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m, float eps,
+                                             float fpscale, float gcoef) {
     const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1;
     const int d0 = (int)((t >> 9) & 1023u), resume = (int)(t >> 19);
     uint32_t cont = 0;
     const int is = m.is;
-    float px[3], py[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { px[k] = W.px[k][slot]; py[k] = W.py[k][slot]; }
+    // the crossing itself (d1_cross) comes with the task; only the two end points of the edge along the scan
+    // axis are needed again for the out scans, the whole span only for the (rare) in scans
+    const int e1 = (edge + 1) % 3;
     Span sp;
-    span_setup(px, py, edge, axis, is, sp);
-    float d1_cross;
-    int d1_in, d1_out;
-    span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out);
+    sp.p00 = axis ? W.py[edge][slot] : W.px[edge][slot];
+    sp.p10 = axis ? W.py[e1][slot] : W.px[e1][slot];
+    if (axis == 0) sp.direction = (sp.p00 < sp.p10) ? -1 : 1;
+    else           sp.direction = (sp.p00 < sp.p10) ? 1 : -1;
+    int d1_in;
+    if (0 < sp.direction) d1_in = f2i_sat(floorf(d1_cross));
+    else                  d1_in = f2i_sat(ceilf(d1_cross));
+    const int d1_out = d1_in + sp.direction;
+    if (kind != 0) {
+        float px[3], py[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { px[k] = W.px[k][slot]; py[k] = W.py[k][slot]; }
+        span_setup(px, py, edge, axis, is, sp);
+    }
     const int fn = W.fn[slot];
     EdgeCoef ec;
     edge_coefs(sp.p00, sp.p10, d0, ec);
@@ -829,6 +840,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         while (__any_sync(0xffffffffu, span_id < 6)) {
             bool t_out = false, t_in = false;
             uint32_t tw = 0;
+            float tcross = 0.0f;
             if (span_id < 6) {
                 if (d0 > sp.d0_to) {
                     span_id++;
@@ -850,21 +862,35 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                         t_in = !alpha_at(m, r_out, c_out);
                         tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
                              ((uint32_t)d0 << 9);
+                        tcross = d1_cross;
                     }
                     d0++;
                 }
             }
             const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
-            if (t_out) W.tasks[n_tasks + __popc(mo & lt_mask)] = tw;
-            if (t_in) W.tasks[n_tasks + __popc(mo) + __popc(mi & lt_mask)] = tw | (1u << 8);
+            if (t_out) {
+                const int q = n_tasks + __popc(mo & lt_mask);
+                W.tasks[q] = tw;
+                W.tcross[q] = tcross;
+            }
+            if (t_in) {
+                const int q = n_tasks + __popc(mo) + __popc(mi & lt_mask);
+                W.tasks[q] = tw | (1u << 8);
+                W.tcross[q] = tcross;
+            }
             n_tasks += __popc(mo) + __popc(mi);
             __syncwarp();
             while (n_tasks >= 32) {
                 n_tasks -= 32;
-                const uint32_t cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
+                const float dc = W.tcross[n_tasks + lane];
+                const uint32_t cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], dc, W, m, s.eps, fpscale, gcoef);
                 __syncwarp();
                 const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
-                if (cont) W.tasks[n_tasks + __popc(mc & lt_mask)] = cont;
+                if (cont) {
+                    const int q = n_tasks + __popc(mc & lt_mask);
+                    W.tasks[q] = cont;
+                    W.tcross[q] = dc;
+                }
                 n_tasks += __popc(mc);
                 __syncwarp();
             }
@@ -873,10 +899,18 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             const int nt = min(n_tasks, 32);
             n_tasks -= nt;
             uint32_t cont = 0;
-            if (lane < nt) cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], W, m, s.eps, fpscale, gcoef);
+            float dc = 0.0f;
+            if (lane < nt) {
+                dc = W.tcross[n_tasks + lane];
+                cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], dc, W, m, s.eps, fpscale, gcoef);
+            }
             __syncwarp();
             const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
-            if (cont) W.tasks[n_tasks + __popc(mc & lt_mask)] = cont;
+            if (cont) {
+                const int q = n_tasks + __popc(mc & lt_mask);
+                W.tasks[q] = cont;
+                W.tcross[q] = dc;
+            }
             n_tasks += __popc(mc);
             __syncwarp();
         }
