@@ -488,7 +488,11 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 //           are accumulated in 64-bit fixed point (shared-memory atomics), which makes the sum exact and hence
 //           independent of task order: bit-identical results run to run.
 //   tail    (lane = item): fixed point -> float, projection / rigid-transform backward, pose accumulators.
-constexpr int kBwdWarps = kThreads / 32;
+#ifndef DH_BWD_THREADS
+#define DH_BWD_THREADS 288
+#endif
+constexpr int kBwdThreads = DH_BWD_THREADS;   // 9 warps x 2 CTAs/SM is what ~109 registers and ~112 KB smem allow
+constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kTaskCap = 96;
 constexpr int kChunkFaces = 1024;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
 #ifndef DH_PAIR_CAP
@@ -539,7 +543,7 @@ k_neg_maps(const dh_sil s) {
         s.row_rng[((size_t)b * 2 + 1) * is + 32 * rb + tid] = (int16_t)hi;
     }
     uint32_t* gT = s.negT + (size_t)b * is * wpr;
-    for (int cb = warp; cb < wpr; cb += kBwdWarps) {
+    for (int cb = warp; cb < wpr; cb += (kThreads / 32)) {
         const uint32_t word = words[lane][cb];
         uint32_t mine = 0;
 #pragma unroll
@@ -675,7 +679,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
 // else : scatter dL/d(camera-space vertices) into grad_verts [B,V,3] (float atomics).
 template <bool FUSED>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks, float gcoef) {
@@ -733,9 +737,9 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
         const uint32_t* gt = s.negT + (size_t)b * is * wpr;
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
-        for (int i = tid; i < is * wpr; i += kThreads) { s_alpha[i] = ga[i]; s_negT[i] = gt[i]; }
-        for (int i = tid; i < S * wprp; i += kThreads) s_negp[i] = gn[i];
-        for (int i = tid; i < is; i += kThreads) {
+        for (int i = tid; i < is * wpr; i += kBwdThreads) { s_alpha[i] = ga[i]; s_negT[i] = gt[i]; }
+        for (int i = tid; i < S * wprp; i += kBwdThreads) s_negp[i] = gn[i];
+        for (int i = tid; i < is; i += kBwdThreads) {
             s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
             s_rng[1][i] = s.row_rng[((size_t)b * 2 + 1) * is + i];
         }
@@ -746,7 +750,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
         s_woff[kBwdWarps] = o;
     }
-    for (int c = tid; c < is; c += kThreads) {  // first / last set pixel of every column
+    for (int c = tid; c < is; c += kBwdThreads) {  // first / last set pixel of every column
         int lo = is, hi = -1;
         for (int w = 0; w < wpr; w++) {
             const uint32_t bits = s_negT[c * wpr + w];
@@ -1192,7 +1196,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
             const size_t sb = bwd_smem_bytes(s);
             rc = set_smem(k_backward<true>, sb);
             if (rc) return rc;
-            k_backward<true><<<dim3(p.nchunks, B), kThreads, sb, st>>>(s, p.verts_og, p.Rmat, p.trans, p.scale,
+            k_backward<true><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(s, p.verts_og, p.Rmat, p.trans, p.scale,
                                                                         p.partials, nullptr, p.nchunks, gcoef);
             DH_LAUNCH_OK("k_backward");
         }
@@ -1301,7 +1305,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     rc = set_smem(k_backward<false>, sb);
     if (rc) return rc;
     const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
-    k_backward<false><<<dim3(nchunks, s->B), kThreads, sb, st>>>(t, verts_cam, nullptr, nullptr, nullptr, nullptr,
+    k_backward<false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(t, verts_cam, nullptr, nullptr, nullptr, nullptr,
                                                                   grad_verts, nchunks, 0.0f);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
