@@ -28,6 +28,14 @@ class DhSil(ctypes.Structure):
     ]
 
 
+class DhCorr(ctypes.Structure):
+    """struct dh_corr (include/dynhor_b200.h) -- builder-defined correspondence term."""
+    _fields_ = [
+        ("records", c_p), ("C", c_i), ("nslots", c_i), ("delta", c_f), ("pad_", c_f),
+        ("w_sum", c_d), ("lw_corr", c_d), ("partials", c_p),
+    ]
+
+
 class DhJointOpt(ctypes.Structure):
     """struct dh_jointopt (include/dynhor_b200.h)."""
     _fields_ = [
@@ -45,6 +53,7 @@ class DhJointOpt(ctypes.Structure):
         ("moments", c_p),
         ("Rmat", c_p), ("smooth_terms", c_p), ("loss_counts", c_p), ("partials", c_p), ("frame_terms", c_p),
         ("nchunks", c_i),
+        ("corr", DhCorr),
     ]
 
 
@@ -52,6 +61,7 @@ class DhJointOpt(ctypes.Structure):
 SIGNATURES = {
     "dh_version": (c_i, []),
     "dh_last_error": (ctypes.c_char_p, []),
+    "dh_struct_bytes": (c_i, [c_i]),
     "dh_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
     "dh_sil_scratch_bytes": (c_i, [c_i, c_i, c_i, c_i, c_i, ctypes.POINTER(c_l)]),
     "dh_sil_forward": (c_i, [ctypes.POINTER(DhSil), c_p, c_p, c_p]),
@@ -60,6 +70,8 @@ SIGNATURES = {
     "dh_transform_verts": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     "dh_masks_prepare": (c_i, [c_p, c_p, c_p, c_l, c_p]),
     "dh_mesh_moments": (c_i, [c_p, c_i, c_p, c_p]),
+    "dh_corr_plan": (c_i, [c_i, c_i, c_i, ctypes.POINTER(c_i)]),
+    "dh_corr_eval": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_f, c_p, c_i, c_p]),
     "dh_jointopt_scratch_bytes": (c_i, [c_i, c_i, ctypes.POINTER(c_l)]),
     "dh_jointopt_default_chunks": (c_i, [c_i, c_i]),
     "dh_jointopt_run": (c_i, [ctypes.POINTER(DhJointOpt), c_i, c_i, c_p]),
@@ -100,6 +112,10 @@ def load():
             fn = getattr(lib, name)  # AttributeError here = header and library out of sync
             fn.restype = res
             fn.argtypes = args
+        for which, struct in enumerate((DhSil, DhJointOpt, DhCorr)):
+            if lib.dh_struct_bytes(which) != ctypes.sizeof(struct):
+                raise DynhorError(f"{struct.__name__}: ctypes layout ({ctypes.sizeof(struct)} B) does not match "
+                                  f"the library's ({lib.dh_struct_bytes(which)} B)")
         _LIB = lib
     return _LIB
 

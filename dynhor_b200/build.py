@@ -17,6 +17,7 @@ SOURCES = {
     "dh_api.cu": [],
     "dh_jointopt.cu": ["--fmad=false"],
     "dh_dino.cu": [],
+    "dh_corr.cu": [],
 }
 
 

@@ -16,6 +16,15 @@ int dh_version(void) { return 100; }  // 0.1.0
 
 const char* dh_last_error(void) { return dh::err_buf(); }
 
+int dh_struct_bytes(int32_t which) {
+    switch (which) {
+        case 0: return (int)sizeof(dh_sil);
+        case 1: return (int)sizeof(dh_jointopt);
+        case 2: return (int)sizeof(dh_corr);
+        default: return dh::fail(DH_ERR_INVALID, "dh_struct_bytes: which must be 0, 1 or 2");
+    }
+}
+
 int dh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -38,4 +38,8 @@ inline int fail(int code, const char* fmt, ...) {
         if (!(cond)) return ::dh::fail(DH_ERR_INVALID, __VA_ARGS__);                                    \
     } while (0)
 
+// dh_corr.cu: memset of the partial sums + the streaming correspondence kernel, stream-ordered
+int launch_corr(const float* records, int B, int C, const float* Rmat, const float* trans, const float* scale,
+                const float* K, int S, float delta, float* partials, int nslots, cudaStream_t st);
+
 }  // namespace dh

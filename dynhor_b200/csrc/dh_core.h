@@ -623,6 +623,45 @@ DH_HD void smooth_terms_frame(int b, int B, const float* rot6d, const float* tra
     }
 }
 
+// ---------------------------------------------------------------------------------------------- correspondences
+// [BUILDER-DEFINED -- the reference has no such term, SURVEY.md section 0.3 / 8a]  Reprojection residual of one
+// dense correspondence under the frame's pose.  Record = (X[3] canonical mesh-space point, tu, tv target position
+// in ROI unit-image coordinates, w weight).  With c = (|s| X) R + T and p = K (c.x/zc, c.y/zc, 1), zc = c.z + 1e-9
+// (the renderer's projection before its flip, utils/camera.py:39-57), the residual in ROI pixels is
+// e = S (p - t) and the record contributes w * huber_delta(|e|) to the frame's loss.
+// acc[0..2]  += dL/dT,  acc[3..11] += X_i * dL/dc_j  (so dL/dR = |s| * acc[3..11], dL/d|s| = <R, acc[3..11]>),
+// acc[12] += w * huber.   Plain fp32, FMA contraction allowed (tolerance-based parity, not bit-exact).
+DH_HD void corr_record(const float* rec, const float* R, const float* T, float s_abs, const float* K, float S,
+                       float delta, float* acc) {
+    const float X0 = rec[0], X1 = rec[1], X2 = rec[2], w = rec[5];
+    const float s0 = s_abs * X0, s1 = s_abs * X1, s2 = s_abs * X2;
+    const float cx = s0 * R[0] + s1 * R[3] + s2 * R[6] + T[0];
+    const float cy = s0 * R[1] + s1 * R[4] + s2 * R[7] + T[1];
+    const float cz = s0 * R[2] + s1 * R[5] + s2 * R[8] + T[2];
+    const float iz = 1.0f / (cz + 1e-9f);
+    const float x_ = cx * iz, y_ = cy * iz;
+    const float eu = S * (K[0] * x_ + K[1] * y_ + K[2] - rec[3]);
+    const float ev = S * (K[3] * x_ + K[4] * y_ + K[5] - rec[4]);
+    const float r2 = eu * eu + ev * ev;
+    float rho, f;
+    if (r2 <= delta * delta) {
+        rho = 0.5f * r2;
+        f = 1.0f;
+    } else {
+        const float r = sqrtf(r2);
+        rho = delta * (r - 0.5f * delta);
+        f = delta / r;
+    }
+    const float gu = (w * f) * eu * S, gv = (w * f) * ev * S;
+    const float gx_ = gu * K[0] + gv * K[3], gy_ = gu * K[1] + gv * K[4];
+    const float g0 = gx_ * iz, g1 = gy_ * iz, g2 = -(gx_ * x_ + gy_ * y_) * iz;
+    acc[0] += g0; acc[1] += g1; acc[2] += g2;
+    acc[3] += X0 * g0; acc[4] += X0 * g1; acc[5] += X0 * g2;
+    acc[6] += X1 * g0; acc[7] += X1 * g1; acc[8] += X1 * g2;
+    acc[9] += X2 * g0; acc[10] += X2 * g1; acc[11] += X2 * g2;
+    acc[12] += w * rho;
+}
+
 // ---------------------------------------------------------------------------------------------- Adam
 // torch.optim.Adam, single-tensor path, defaults betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad
 // (jointopt.py:135-141).  bc1 = 1 - beta1^t, bc2s = sqrt(1 - beta2^t): python doubles, as torch computes them.

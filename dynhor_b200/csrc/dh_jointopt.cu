@@ -1027,7 +1027,7 @@ __global__ void k_pose_prep(const dh_jointopt p) {
 // mode 0: Adam update in place.  mode 1: write gradients to (grad_rot6d, grad_trans), leave parameters alone.
 // mode 2: per-frame loss terms only (forward-only evaluation; no backward ran, partials are not read).
 __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__ grad_rot6d,
-                              float* __restrict__ grad_trans, int with_sil) {
+                              float* __restrict__ grad_trans, int with_sil, int with_corr) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.sil.B) return;
     double G[9], gT[3], gs = 0.0;
@@ -1046,17 +1046,38 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
     for (int i = 0; i < 3; i++) gT[i] += st[i];
     for (int i = 0; i < 9; i++) G[i] += st[3 + i];
     gs += st[12];
+    // correspondence term (builder-defined, dh_corr.cu): slots summed in order, then lw / sum(w)
+    double corr_loss = 0.0;
+    if (with_corr) {
+        double q[13];
+        for (int i = 0; i < 13; i++) q[i] = 0.0;
+        for (int c = 0; c < p.corr.nslots; c++) {
+            const float* cp = p.corr.partials + ((size_t)b * p.corr.nslots + c) * 16;
+            for (int i = 0; i < 13; i++) q[i] += (double)cp[i];
+        }
+        const double coef = p.corr.lw_corr / p.corr.w_sum;
+        const double sc = (double)p.scale[0], s_abs = fabs(sc), sgn = (sc < 0.0) ? -1.0 : 1.0;
+        double dot = 0.0;
+        for (int i = 0; i < 3; i++) gT[i] += coef * q[i];
+        for (int i = 0; i < 9; i++) {
+            G[i] += coef * s_abs * q[3 + i];
+            dot += (double)p.Rmat[9 * b + i] * q[3 + i];
+        }
+        gs += coef * sgn * dot;
+        corr_loss = q[12];
+    }
     float r6[6];
     for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
     double g6[6];
     rot6d_backward(r6, G, g6);
 
-    double* ft = p.frame_terms + (size_t)b * 4;
+    double* ft = p.frame_terms + (size_t)b * 8;
     const int32_t* lc = p.loss_counts + b * 4;
     ft[0] = with_sil ? (double)lc[0] : 0.0;
     ft[1] = with_sil ? (double)(((float)lc[1] * 0.25f) / ((float)lc[2] * 0.25f + 0.000001f)) : 0.0;
     ft[2] = st[13];
     ft[3] = gs;
+    ft[4] = corr_loss;
 
     if (mode == 2) return;
     if (mode == 1) {
@@ -1084,19 +1105,19 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
 // One CTA.  mode 0: history row + scale update + step++.  mode 1: history row only (grad_scale written).
 // mode 2: history row only.
 __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int mode, float* __restrict__ grad_scale) {
-    __shared__ double red[kThreads / 32][4];
-    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    __shared__ double red[kThreads / 32][5];
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int b = threadIdx.x; b < p.sil.B; b += kThreads)
-        for (int i = 0; i < 4; i++) a[i] += p.frame_terms[(size_t)b * 4 + i];
-    for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 5; i++) a[i] += p.frame_terms[(size_t)b * 8 + i];
+    for (int i = 0; i < 5; i++)
         for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
     if ((threadIdx.x & 31) == 0)
-        for (int i = 0; i < 4; i++) red[threadIdx.x >> 5][i] = a[i];
+        for (int i = 0; i < 5; i++) red[threadIdx.x >> 5][i] = a[i];
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         for (int w = 0; w < kThreads / 32; w++)
-            for (int i = 0; i < 4; i++) t[i] += red[w][i];
+            for (int i = 0; i < 5; i++) t[i] += red[w][i];
         const int step = *p.step;
         if (step < p.max_iters) {
             double* h = p.hist + (size_t)step * 4;
@@ -1104,7 +1125,7 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int 
             h[0] = (p.B_total > 1) ? t[2] / N : 0.0;
             h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
             h[2] = t[1] / (double)p.B_total;
-            h[3] = t[3];
+            h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0) ? t[4] / p.corr.w_sum : 0.0;
         }
         if (mode == 1 && grad_scale != nullptr) grad_scale[0] = (float)t[3];
         if (mode == 0) {
@@ -1159,8 +1180,8 @@ int launch_forward_common(const dh_sil& s, cudaStream_t st) {
     return DH_OK;
 }
 
-// Optional per-kernel timing: 8 events bracket the 7 kernels of one iteration (dh_jointopt_profile).
-struct IterEvents { cudaEvent_t ev[8]; };
+// Optional per-kernel timing: 9 events bracket the kernels of one iteration (dh_jointopt_profile).
+struct IterEvents { cudaEvent_t ev[9]; };
 #define DH_REC(i) do { if (evs) cudaEventRecord(evs->ev[i], st); } while (0)
 
 int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
@@ -1172,6 +1193,13 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
     k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
     DH_LAUNCH_OK("k_pose_prep");
     DH_REC(1);
+    const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
+    if (with_corr) {
+        const int rc = launch_corr(p.corr.records, B, p.corr.C, p.Rmat, p.trans, p.scale, s.K, s.S, p.corr.delta,
+                                   p.corr.partials, p.corr.nslots, st);
+        if (rc) return rc;
+    }
+    DH_REC(8);
     if (with_sil) {
         dim3 gv((s.V + kThreads - 1) / kThreads, B);
         k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
@@ -1204,7 +1232,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         DH_REC(2); DH_REC(3); DH_REC(4);
     }
     DH_REC(5);
-    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0);
+    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
     DH_LAUNCH_OK("k_pose_update");
     DH_REC(6);
     k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
@@ -1228,6 +1256,10 @@ int check_plan(const dh_jointopt* p) {
                "nchunks must be >= ceil(F / 1024)");
     DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
     DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
+    if (p->corr.records != nullptr && p->corr.lw_corr > 0.0) {
+        DH_REQUIRE(p->corr.partials != nullptr && p->corr.C > 0 && p->corr.nslots > 0, "corr: bad plan");
+        DH_REQUIRE(p->corr.w_sum > 0.0 && p->corr.delta > 0.0f, "corr: w_sum and delta must be positive");
+    }
     return DH_OK;
 }
 
@@ -1364,7 +1396,7 @@ int dh_jointopt_scratch_bytes(int32_t B, int32_t nchunks, int64_t* out5) {
     out5[1] = (int64_t)B * 16 * 8;
     out5[2] = (int64_t)B * 4 * 4;
     out5[3] = (int64_t)B * nchunks * 16 * 4;
-    out5[4] = (int64_t)B * 4 * 8;
+    out5[4] = (int64_t)B * 8 * 8;
     return DH_OK;
 }
 
@@ -1441,20 +1473,22 @@ int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_hos
     DH_REQUIRE(n_iters > 0 && ms_out_host != nullptr, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     IterEvents evs;
-    for (int i = 0; i < 8; i++) DH_CUDA(cudaEventCreate(&evs.ev[i]));
-    for (int i = 0; i < 7; i++) ms_out_host[i] = 0.0f;
+    for (int i = 0; i < 9; i++) DH_CUDA(cudaEventCreate(&evs.ev[i]));
+    for (int i = 0; i < 8; i++) ms_out_host[i] = 0.0f;
+    // event order on the stream: 0 pose_prep 1 corr 8 project 2 setup_bin 3 raster 4 backward 5 pose_update 6 finalize 7
+    const int seg[8][2] = {{0, 1}, {8, 2}, {2, 3}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {1, 8}};
     for (int it = 0; it < n_iters; it++) {
         rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, st, &evs);
         if (rc) break;
         cudaError_t e = cudaEventSynchronize(evs.ev[7]);
         if (e != cudaSuccess) { rc = fail(DH_ERR_CUDA, "profile sync: %s", cudaGetErrorString(e)); break; }
-        for (int i = 0; i < 7; i++) {
+        for (int i = 0; i < 8; i++) {
             float ms = 0.0f;
-            cudaEventElapsedTime(&ms, evs.ev[i], evs.ev[i + 1]);
+            cudaEventElapsedTime(&ms, evs.ev[seg[i][0]], evs.ev[seg[i][1]]);
             ms_out_host[i] += ms / (float)n_iters;
         }
     }
-    for (int i = 0; i < 8; i++) cudaEventDestroy(evs.ev[i]);
+    for (int i = 0; i < 9; i++) cudaEventDestroy(evs.ev[i]);
     return rc;
 }
 

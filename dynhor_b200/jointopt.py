@@ -19,6 +19,7 @@ from torch import nn
 
 from . import _lib
 from .camera import compute_transformation_persp, tensorify
+from .corr import CorrespondenceTerm, plan as corr_plan
 from .geometry import matrix_to_rot6d, rot6d_to_matrix
 from .losses import Losses
 from .renderer import SilhouetteState, shared_faces
@@ -27,7 +28,10 @@ from .sharding import FrameShard, allgather_frames, allreduce_sum_, detect_shard
 
 class Joint_Optimizer(nn.Module):
     def __init__(self, translations_object, rotations_object, verts_object_og, faces_object, camintr_rois_object,
-                 target_masks_object, int_scale_init=1.0, optimize_object_scale=False):
+                 target_masks_object, int_scale_init=1.0, optimize_object_scale=False, correspondences=None,
+                 corr_delta=1.0):
+        """`correspondences` ([B,C,6], optional) and `corr_delta` belong to the builder-defined reprojection term
+        (dynhor_b200/corr.py); without them the module is the reference's (jointopt.py:16-62)."""
         super().__init__()
         translation_init = translations_object.detach().clone()
         self.translations_object = nn.Parameter(translation_init, requires_grad=True)
@@ -55,6 +59,11 @@ class Joint_Optimizer(nn.Module):
         self.cuda()
         self.losses = Losses(ref_mask_object=self.ref_mask_object, keep_mask_object=self.keep_mask_object,
                              camintr_rois_object=self.camintr_rois_object)
+        self.corr_delta = float(corr_delta)
+        self.corr_term = None
+        if correspondences is not None:
+            self.corr_term = CorrespondenceTerm(correspondences.cuda(), self.camintr_rois_object,
+                                                image_size=int(target_masks_object.shape[-1]), delta=corr_delta)
 
     def get_verts_object(self):
         rotations_object = rot6d_to_matrix(self.rotations_object)
@@ -74,6 +83,10 @@ class Joint_Optimizer(nn.Module):
                                                                           faces=self.faces_object)
             loss_dict.update(sil_loss_dict)
             metric_dict.update(sil_metric_dict)
+        if self.corr_term is not None and (loss_weights is None or loss_weights.get("lw_corr_obj", 0) > 0):
+            loss_dict["loss_corr_obj"] = self.corr_term.loss(rot6d_to_matrix(self.rotations_object),
+                                                             self.translations_object,
+                                                             self.int_scales_object.abs())
         return loss_dict, metric_dict
 
 
@@ -157,6 +170,22 @@ class FusedJointOpt:
         p.moments = self.moments.data_ptr()
         (p.Rmat, p.smooth_terms, p.loss_counts, p.partials, p.frame_terms) = [b.data_ptr() for b in self.scratch]
         p.nchunks = self.nchunks
+        # builder-defined correspondence term: on only with records AND a positive weight
+        lw_corr = float(loss_weights.get("lw_corr_obj", 0.0))
+        self.corr_on = getattr(model, "corr_term", None) is not None and lw_corr > 0
+        if self.corr_on:
+            ct = model.corr_term
+            w = ct.w_local.reshape(1).clone()
+            if exchange:
+                allreduce_sum_(w, self.shard, group)
+                self.corr_w_sum = float(w.item())
+            else:
+                self.corr_w_sum = ct.w_sum
+            cp = corr_plan(B, ct.records.shape[1])
+            self.corr_partials = z(B, cp["nslots"], 16)
+            p.corr.records, p.corr.C, p.corr.nslots = ct.records.data_ptr(), ct.records.shape[1], cp["nslots"]
+            p.corr.delta, p.corr.w_sum, p.corr.lw_corr = ct.delta, self.corr_w_sum, lw_corr
+            p.corr.partials = self.corr_partials.data_ptr()
         self.p = p
         self.halo_mode = halo if (self.shard.world > 1 and exchange) else "none"
         self._mailbox, self._peers = None, []
@@ -253,6 +282,9 @@ class FusedJointOpt:
                 evo["loss_sil_obj"].append(float(r[1]))
                 total += float(r[1]) * lw["lw_sil_obj"]
                 evo["iou_object"].append(float(r[2]))
+            if self.corr_on:
+                evo["loss_corr_obj"].append(float(r[3]))
+                total += float(r[3]) * lw["lw_corr_obj"]
             evo["loss"].append(total)
         return dict(evo)
 
@@ -261,7 +293,7 @@ class FusedJointOpt:
         n = int(self.step.item())
         return self._rows_to_dict(self.hist[:n])
 
-    KERNELS = ("pose_prep", "project", "setup_bin", "raster", "backward", "pose_update", "finalize")
+    KERNELS = ("pose_prep", "project", "setup_bin", "raster", "backward", "pose_update", "finalize", "corr")
 
     def profile(self, n_iters=5):
         """Average per-kernel milliseconds over n_iters real iterations (CUDA events on the launch stream)."""
@@ -285,7 +317,8 @@ class FusedJointOpt:
 
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
-                   lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True, halo="p2p"):
+                   lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True, halo="p2p",
+                   corr_delta=1.0):
     """jointopt.py:93-161.  Extra keyword `shard` (a sharding.FrameShard): when given (or when torch.distributed
     is initialised with more than one rank) `object_parameters` is the full sequence and this rank optimises its
     contiguous frame range; the returned model holds the gathered poses of ALL frames on every rank."""
@@ -307,10 +340,15 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
     obj_rots = torch.cat([obj["rotations"] for obj in local]).cuda()
     obj_camintr_roi = torch.cat([obj["K_roi"][:, 0] for obj in local]).cuda()
     obj_tar_masks = torch.cat([obj["target_masks"].cuda(non_blocking=True) for obj in local])
+    # optional per-frame key "correspondences" [1,C,6] (builder-defined term, corr.py); absent -> reference behaviour
+    corr = None
+    if all("correspondences" in obj for obj in local) and loss_weights.get("lw_corr_obj", 0) > 0:
+        corr = torch.cat([obj["correspondences"].cuda(non_blocking=True) for obj in local])
     model = Joint_Optimizer(
         translations_object=obj_trans, rotations_object=obj_rots, verts_object_og=verts_object_og,
         faces_object=faces_local, target_masks_object=obj_tar_masks, camintr_rois_object=obj_camintr_roi,
-        int_scale_init=1, optimize_object_scale=optimize_object_scale)
+        int_scale_init=1, optimize_object_scale=optimize_object_scale, correspondences=corr,
+        corr_delta=corr_delta)
     fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard, halo=halo)
     try:
         from tqdm.auto import tqdm
@@ -331,7 +369,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
             loop.set_description(f"Loss {loss_evolution['loss'][-1]:.4f}")
         loop.close()
     if board is not None:
-        for k in ("loss_smooth_obj", "loss_sil_obj"):
+        for k in ("loss_smooth_obj", "loss_sil_obj", "loss_corr_obj"):
             for step, val in enumerate(loss_evolution.get(k, [])):
                 board.add_scalar(k, val, step)
     fused.release()

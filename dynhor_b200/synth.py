@@ -251,6 +251,42 @@ def make_sequence(B, H=480, W=640, mesh="uv50x100", seed=0, render_fn=None, size
     return out
 
 
+def make_correspondences(seq, C, seed=0, noise_px=0.5, outliers=0.05, size=REND_SIZE):
+    """[BUILDER-DEFINED, SURVEY.md 8d]  Synthetic DKM-style dense correspondences for the reprojection term
+    (dynhor_b200/corr.py): per frame b, C records (X[3], t[2], w) where X is a surface point of the canonical
+    mesh facing the camera in the previous frame's ground-truth pose (the "source" frame of the pair), t its
+    ground-truth projection into frame b in ROI unit-image coordinates plus N(0, noise_px^2) pixel noise, and w a
+    DKM-like certainty in (0.5, 1]; a fraction `outliers` of the targets is replaced by uniform positions.
+    Returns float32 [B,C,6]."""
+    rng = np.random.default_rng(seed + 3)
+    verts, faces = seq["verts"].astype(np.float64), seq["faces"]
+    R, T, K = seq["R_gt"].astype(np.float64), seq["T_gt"].astype(np.float64).reshape(-1, 3), seq["K_roi"]
+    B = len(R)
+    tri = verts[faces]                                           # [F,3,3]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    out = np.empty((B, C, 6), np.float32)
+    for b in range(B):
+        src = max(b - 1, 0)
+        nc = nrm @ R[src]                                        # normals in the source frame's camera space
+        cen = tri.mean(1) @ R[src] + T[src]
+        vis = np.nonzero((nc * cen).sum(-1) < 0)[0]              # faces turned towards the camera
+        f = vis[rng.integers(0, len(vis), size=C)]
+        u, v = rng.random(C), rng.random(C)
+        flip = u + v > 1.0
+        u[flip], v[flip] = 1.0 - u[flip], 1.0 - v[flip]
+        X = tri[f, 0] + u[:, None] * (tri[f, 1] - tri[f, 0]) + v[:, None] * (tri[f, 2] - tri[f, 0])
+        c = X @ R[b] + T[b]
+        x_, y_ = c[:, 0] / c[:, 2], c[:, 1] / c[:, 2]
+        Kb = K[b].astype(np.float64)
+        t = np.stack([Kb[0, 0] * x_ + Kb[0, 1] * y_ + Kb[0, 2], Kb[1, 0] * x_ + Kb[1, 1] * y_ + Kb[1, 2]], -1)
+        t += rng.normal(size=t.shape) * (noise_px / float(size))
+        bad = rng.random(C) < outliers
+        t[bad] = rng.random((int(bad.sum()), 2))
+        w = rng.uniform(0.5, 1.0, size=C)
+        out[b] = np.concatenate([X, t, w[:, None]], -1).astype(np.float32)
+    return out
+
+
 def to_object_parameters(seq):
     """List of per-frame dicts in the layout find_optimal_poses returns (pose_initializtion.py:460-471),
     as torch CPU tensors; the caller moves them to the device like stage 1 does."""
@@ -265,6 +301,8 @@ def to_object_parameters(seq):
             "target_masks": torch.from_numpy(seq["target_masks"][b:b + 1].copy()),     # [1,S,S]
             "verts": torch.from_numpy(seq["verts"]).unsqueeze(0),
         })
+        if "correspondences" in seq:
+            params[-1]["correspondences"] = torch.from_numpy(seq["correspondences"][b:b + 1].copy())  # [1,C,6]
     return params
 
 

@@ -34,6 +34,8 @@ typedef enum dh_status {
 
 int dh_version(void);
 const char* dh_last_error(void);
+/* sizeof of the ABI structs as compiled (0 dh_sil, 1 dh_jointopt, 2 dh_corr): lets a binding check its layout */
+int dh_struct_bytes(int32_t which);
 /* sm count, compute capability of the current device */
 int dh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -89,6 +91,42 @@ int dh_masks_prepare(const float* target_masks, int8_t* tri, unsigned long long*
 int dh_mesh_moments(const float* verts, int32_t V, double* out12, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * [BUILDER-DEFINED] Dense-correspondence reprojection term.  BASELINE.json's north_star names "reprojection
+ * residuals of the DKM dense correspondences"; the reference has NO such code (SURVEY.md section 0.3 -- only a
+ * data-folder comment, README.md:43), so there is nothing to be at parity with except this build's own oracle
+ * (oracle/corr_oracle.py).  Off by default: configs/custom_shoes.yaml has no lw_corr_obj, and the reference's
+ * weighting rule (jointopt.py:147-150, loss name -> "lw" name) is what switches it on.
+ *   record   = 6 floats: X[3] point in canonical mesh coordinates (lifted once from the source frame's pixel),
+ *              t[2] target position in the frame's ROI unit-image coordinates (what K_roi maps into), w weight
+ *   residual e = S * (K_roi (c.x/zc, c.y/zc, 1) - t),  c = (|s| X) R_b + T_b,  zc = c.z + 1e-9   [ROI pixels]
+ *   loss_corr_obj = sum_{b,c} w * huber_delta(|e|) / sum_{b,c} w
+ * One streaming pass over the records per iteration (24 B / record, HBM-bound): cp.async.bulk (TMA) tiles into a
+ * shared-memory ring, 13 accumulators per thread, fixed-order CTA reduction -> partials (bit-reproducible).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dh_corr {
+    const float* records;          /* [B,C,6]; C must be even (16-byte tiles); pad with zero-weight records       */
+    int32_t C;                     /* records per frame                                                          */
+    int32_t nslots;                /* partial-sum rows per frame (dh_corr_plan)                                  */
+    float delta;                   /* Huber threshold in ROI pixels                                              */
+    float pad_;
+    double w_sum;                  /* sum of the weights over ALL ranks                                          */
+    double lw_corr;                /* loss weight, 0 disables the term                                           */
+    float* partials;               /* [B,nslots,16] scratch: dT(3), X (x) dc (9), loss (1), pad(3)               */
+} dh_corr;
+
+/* Launch plan of the streaming kernel: the B*ceil(C/1024) record tiles are cut into `grid` contiguous, equal
+ * ranges (one persistent CTA each, 3 per SM), so a frame is seen by at most `nslots` CTAs.
+ * out3 = grid, nslots, tiles per frame.  sm_count 0 = ask the current device (148 if there is none). */
+int dh_corr_plan(int32_t B, int32_t C, int32_t sm_count, int32_t* out3);
+/* Un-normalised partial sums for the poses (Rmat [B,9], trans [B,3], scale [1]) and intrinsics K [B,9]:
+ * partials[b,slot,0..2] = sum w dhuber/dc, [3..11] = sum X_i * (w dhuber/dc)_j, [12] = sum w huber; unused slots
+ * are zeroed.  The caller sums over slots and applies lw_corr / w_sum; dL/dR = |s| * [3..11],
+ * dL/d|s| = <R, [3..11]>.  partials: [B,nslots,16] with nslots from dh_corr_plan(B, C, 0). */
+int dh_corr_eval(const float* records, int32_t B, int32_t C, const float* Rmat, const float* trans,
+                 const float* scale, const float* K, int32_t S, float delta, float* partials, int32_t nslots,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused joint optimisation:  jointopt.py:144-160 (zero_grad, forward, weighting, backward, Adam step)
  * for the local frame range of one GPU.
  * ------------------------------------------------------------------------------------------------ */
@@ -104,7 +142,7 @@ typedef struct dh_jointopt {
     float* adam_mv_scale;          /* [2] */
     int32_t* step;                 /* [1] device iteration counter (0 before the first step)                   */
     double* hist;                  /* [max_iters,4] per-iteration partial sums of this rank:                     */
-                                   /*   loss_smooth_obj, loss_sil_obj, iou_object, (unused)                      */
+                                   /*   loss_smooth_obj, loss_sil_obj, iou_object, loss_corr_obj                 */
     int32_t max_iters;
     /* neighbours' boundary poses for the smoothness term (frame-range sharding) */
     const float* halo_prev;        /* [9] rot6d(6)+trans(3) of global frame first-1, or NULL at the start        */
@@ -126,8 +164,9 @@ typedef struct dh_jointopt {
     double* smooth_terms;          /* [B,16]: gT(3) gR(9) gs(1) pair_sse(1) pad(2)                               */
     int32_t* loss_counts;          /* [B,4]: 16*SSE, 4*inter, 4*union, pad                                       */
     float* partials;               /* [B,nchunks,16] per-CTA pose-gradient partial sums                          */
-    double* frame_terms;           /* [B,4]: 16*SSE, iou, pair_sse, scale-grad                                   */
+    double* frame_terms;           /* [B,8]: 16*SSE, iou, pair_sse, scale-grad, corr loss sum, pad(3)            */
     int32_t nchunks;
+    dh_corr corr;                  /* optional correspondence term (corr.records == NULL or lw_corr == 0: off)   */
 } dh_jointopt;
 
 /* bytes of the dh_jointopt scratch arrays: out[5] = Rmat, smooth_terms, loss_counts, partials, frame_terms */
@@ -142,8 +181,9 @@ int dh_jointopt_eval(const dh_jointopt* p, void* stream);
 /* gradients of the weighted loss w.r.t. rot6d [B,6] and trans [B,3] (and scale [1]) for the current
  * parameters, without an optimiser step (parity tests; also the backward of Joint_Optimizer.forward). */
 int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans, float* grad_scale, void* stream);
-/* run n_iters iterations eagerly with CUDA events around each of the 7 kernels; ms_out_host[7] (HOST memory) =
- * average milliseconds of pose_prep, project, setup_bin, raster, backward, pose_update, finalize.  Synchronises. */
+/* run n_iters iterations eagerly with CUDA events around each kernel; ms_out_host[8] (HOST memory) = average
+ * milliseconds of pose_prep, project, setup_bin, raster, backward (incl. its per-frame map kernel), pose_update,
+ * finalize, corr.  Synchronises. */
 int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_host, void* stream);
 /* drop cached graphs */
 int dh_jointopt_release(const dh_jointopt* p);

@@ -61,7 +61,12 @@ class JointOptOracle:
     """Same state and update rule as jointopt.py:15-62,125-141 on CPU."""
 
     def __init__(self, rot6d, trans, verts_og, faces, K_roi, target_masks, lr=1e-4, image_size=REND_SIZE,
-                 anti_aliasing=True, optimize_object_scale=False, int_scale_init=1.0):
+                 anti_aliasing=True, optimize_object_scale=False, int_scale_init=1.0, correspondences=None,
+                 corr_delta=1.0):
+        # correspondences / corr_delta: the builder-defined reprojection term (oracle/corr_oracle.py); absent in
+        # the reference, off unless given together with loss_weights["lw_corr_obj"] > 0
+        self.correspondences = None if correspondences is None else torch.as_tensor(correspondences).float()
+        self.corr_delta, self.image_size = float(corr_delta), int(image_size)
         self.translations_object = torch.nn.Parameter(torch.as_tensor(trans).float().reshape(-1, 1, 3).clone())
         self.rotations_object = torch.nn.Parameter(torch.as_tensor(rot6d).float().reshape(-1, 3, 2).clone())
         self.B = self.translations_object.shape[0]
@@ -101,6 +106,11 @@ class JointOptOracle:
             l_m = torch.sum((image - self.ref_mask_object) ** 2) / self.keep_mask_object.sum()
             loss_dict["loss_sil_obj"] = (torch.zeros(1) + l_m) / len(verts)
             metric_dict["iou_object"] = batch_mask_iou(image, self.ref_mask_object).mean().item()
+        if self.correspondences is not None and (loss_weights is None or loss_weights.get("lw_corr_obj", 0) > 0):
+            from . import corr_oracle
+            loss_dict["loss_corr_obj"] = corr_oracle.corr_loss(
+                self.correspondences, rot6d_to_matrix(self.rotations_object), self.translations_object,
+                self.int_scales_object.abs(), self.camintr_rois_object, self.image_size, self.corr_delta)
         return loss_dict, metric_dict
 
     def loss_and_grads(self, loss_weights):

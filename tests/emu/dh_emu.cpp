@@ -244,4 +244,19 @@ void emu_adam(float* p, const float* g, float* m, float* v, long long n, double 
     for (long long i = 0; i < n; i++) adam_update(&p[i], &m[i], &v[i], g[i], step_size, bc2s);
 }
 
+// k_corr (dh_corr.cu): per-frame sums of the correspondence term, thread-strided like the kernel
+// (256 "threads", each walking its records in order, then summed in thread order).  sums [B,16].
+void emu_corr_frames(const float* records, int B, int C, const float* Rmat, const float* trans, float s_abs,
+                     const float* K, float S, float delta, float* sums) {
+    for (int b = 0; b < B; b++) {
+        std::vector<float> acc(256 * 13, 0.f);
+        for (int c = 0; c < C; c++)
+            corr_record(records + ((size_t)b * C + c) * 6, Rmat + 9 * b, trans + 3 * b, s_abs, K + 9 * b, S, delta,
+                        &acc[(c % 256) * 13]);
+        for (int j = 0; j < 16; j++) sums[b * 16 + j] = 0.f;
+        for (int t = 0; t < 256; t++)
+            for (int j = 0; j < 13; j++) sums[b * 16 + j] += acc[t * 13 + j];
+    }
+}
+
 }  // extern "C"

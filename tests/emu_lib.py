@@ -123,6 +123,18 @@ def smooth_terms(rot6d, trans, scale, moments, V, B_total, lw_smooth, halo_prev=
     return st
 
 
+def corr_frames(records, R, T, s_abs, K, S, delta):
+    records = np.ascontiguousarray(records, np.float32)
+    B, C = records.shape[:2]
+    R = np.ascontiguousarray(R, np.float32).reshape(-1, 9)
+    T = np.ascontiguousarray(T, np.float32).reshape(-1, 3)
+    K = np.ascontiguousarray(K, np.float32).reshape(-1, 9)
+    sums = np.zeros((B, 16), np.float32)
+    lib().emu_corr_frames(_p(records), B, C, _p(R), _p(T), ctypes.c_float(s_abs), _p(K), ctypes.c_float(S),
+                          ctypes.c_float(delta), _p(sums))
+    return sums
+
+
 def adam(p, g, m, v, lr, t):
     lib().emu_adam(_p(p), _p(np.ascontiguousarray(g, np.float32)), _p(m), _p(v), ctypes.c_longlong(p.size),
                    ctypes.c_double(lr), t)

@@ -29,6 +29,8 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.DhSil) == 40 + 14 * 8
     assert ctypes.sizeof(_lib.DhJointOpt) % 8 == 0
     lib = _lib.load()
+    for which, struct in enumerate((_lib.DhSil, _lib.DhJointOpt, _lib.DhCorr)):
+        assert lib.dh_struct_bytes(which) == ctypes.sizeof(struct)
     out = (ctypes.c_int64 * 12)()
     assert lib.dh_sil_scratch_bytes(2, 10, 20, 64, 1, out) == 0
     assert out[3] == 2 * 128 * 128 * 4 and out[4] == 2 * 128 * 4 * 4
