@@ -27,6 +27,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 LW = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}   # configs/custom_shoes.yaml:17-18
+LW_CORR = 0.01                                    # builder-defined correspondence term (dynhor_b200/corr.py)
 LR = 1e-4                                         # configs/custom_shoes.yaml:15
 MESH = "uv50x100"                                 # V=5002, F=10000 ("5k-vertex mesh")
 H, W, S = 480, 640, 256
@@ -34,15 +35,17 @@ METRIC = "jointopt frame-iters/sec (fwd+bwd+Adam)"
 UNIT = "frame-iters/s"
 
 
-def algorithmic_bytes_per_frame(V, S=256):
-    """SURVEY.md 8(d) kernel-boundary model, per frame-iteration, split by kernel (fp32, u8 coverage, i32 index)."""
+def algorithmic_bytes_per_frame(V, S=256, C=0):
+    """SURVEY.md 8(d) kernel-boundary model, per frame-iteration, split by kernel (fp32, u8 coverage, i32 index);
+    + 24 bytes per correspondence record."""
     SS = 2 * S
     return {
+        "corr": 24 * C,
         "project": 12 * V,                          # writes projected vertices
         "raster": 12 * V + 5 * SS * SS + SS * SS + 8 * S * S,  # raster fwd + the loss kernel fused into it
         "backward": 5 * SS * SS + 8 * S * S + 12 * V + 12 * V,
         "pose_update": 12 * V + 288,
-        "total": 60 * V + 11 * SS * SS + 16 * S * S + 288,
+        "total": 60 * V + 11 * SS * SS + 16 * S * S + 288 + 24 * C,
     }
 
 
@@ -123,12 +126,18 @@ def oracle_render_fn(vc, faces, K, size):
     return r(torch.from_numpy(vc), torch.from_numpy(faces)[None].repeat(B, 1, 1), mode="silhouettes").numpy()
 
 
+def loss_weights(C):
+    return dict(LW, lw_corr_obj=LW_CORR) if C > 0 else dict(LW)
+
+
 def build_model(seq):
     from dynhor_b200 import synth
     from dynhor_b200.jointopt import Joint_Optimizer
     params = synth.to_object_parameters(seq)
     B = len(params)
+    corr = torch.from_numpy(seq["correspondences"]) if "correspondences" in seq else None
     return Joint_Optimizer(
+        correspondences=corr,
         translations_object=torch.cat([p["translations"] for p in params]),
         rotations_object=torch.cat([p["rotations"] for p in params]),
         verts_object_og=torch.from_numpy(seq["verts"]),
@@ -139,7 +148,7 @@ def build_model(seq):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_baseline(frames=None, iters=1):
+def cpu_baseline(frames=None, iters=1, C=0):
     """The CPU oracle (kind "port": the reference cannot run on CPU) on a bounded sample of
     the same workload: `frames` custom_shoes-shaped frames x `iters` full iterations, all host threads."""
     from dynhor_b200 import synth
@@ -148,15 +157,17 @@ def cpu_baseline(frames=None, iters=1):
     torch.set_num_threads(cores)
     frames = frames or max(2, min(cores, 64))
     seq = synth.make_sequence(frames, H, W, mesh=MESH, seed=0, render_fn=oracle_render_fn, period=300)
+    corr = synth.make_correspondences(seq, C, seed=0) if C > 0 else None
     orc = jo.JointOptOracle(seq["rot6d_init"], seq["T_init"], seq["verts"], seq["faces"], seq["K_roi"],
-                            seq["target_masks"], lr=LR)
+                            seq["target_masks"], lr=LR, correspondences=corr)
+    lw = loss_weights(C)
     t0 = time.perf_counter()
     for _ in range(iters):
-        orc.step(LW)
+        orc.step(lw)
     dt = time.perf_counter() - t0
     return {"value": frames * iters / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{frames} frames x {iters} iteration(s) of the N=1 workload (5k-vertex mesh, 512x512 AA "
-                      f"raster), {dt:.1f} s of CPU work, OpenMP + torch threads = {cores}"}, dt
+                      f"raster, {C} correspondences/frame), {dt:.1f} s of CPU work, OpenMP + torch threads = {cores}"}, dt
 
 
 def run_reference(args):
@@ -168,10 +179,10 @@ def run_reference(args):
     frames = max(2, min(cores // 2, 32))
     cb_rows = []
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(frames=2, iters=1)
+        cpu_baseline(frames=2, iters=1, C=args.corr)
     t_total = 0.0
     for _ in range(steps):
-        cb, dt = cpu_baseline(frames=frames, iters=1)
+        cb, dt = cpu_baseline(frames=frames, iters=1, C=args.corr)
         cb_rows.append(cb)
         t_total += dt
     value = frames * steps / t_total
@@ -183,8 +194,9 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "custom_shoes-shaped joint optimisation (BASELINE configs[1] frame shape): "
                                f"{frames}-frame bounded sample per step, 480x640, 5k-vertex mesh, 256x256 ROI at "
-                               "512x512 AA; CPU oracle port of the reference path (reference itself is CUDA-only)",
-                   "frames_per_step": frames},
+                               f"512x512 AA, {args.corr} correspondences per frame; CPU oracle port of the reference "
+                               "path (reference itself is CUDA-only)",
+                   "frames_per_step": frames, "correspondences_per_frame": args.corr},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,6 +223,10 @@ def run_ours(args):
     seq = synth.make_sequence(Bl, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=B_total,
                               frame_offset=shard.start)
     V, F = len(seq["verts"]), len(seq["faces"])
+    C = args.corr
+    lw = loss_weights(C)
+    if C > 0:
+        seq["correspondences"] = synth.make_correspondences(seq, C, seed=shard.start)
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,7 +236,7 @@ def run_ours(args):
 
     # ---- device-resident throughput: K fused iterations, inputs already in HBM
     model = build_model(seq)
-    fused = FusedJointOpt(model, LW, LR, args.steps + args.warmup + 64, shard=shard, halo=args.halo)
+    fused = FusedJointOpt(model, lw, LR, args.steps + args.warmup + 64, shard=shard, halo=args.halo)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -245,8 +261,8 @@ def run_ours(args):
     # ---- per-kernel times (CUDA events on the launch stream) -> roofline of the dominant kernel
     prof = fused.profile(5)
     fused.release()
-    ab = algorithmic_bytes_per_frame(V, S)
-    top = max(("project", "raster", "backward", "pose_update"), key=lambda k: prof[k])
+    ab = algorithmic_bytes_per_frame(V, S, C)
+    top = max(("project", "raster", "backward", "pose_update", "corr"), key=lambda k: prof[k])
     peak, peak_kind = measured_peaks()
     achieved = ab[top] * Bl / (prof[top] / 1000.0) / 1e9
     traffic = None
@@ -261,6 +277,8 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": f"{peak_kind} hbm_gbs",
                 "algorithmic_bytes_per_launch": ab[top] * Bl, "kernel_ms": prof[top],
                 "kernel_ms_all": prof,
+                "kernel_gbs_all": {k: ab[k] * Bl / (prof[k] / 1000.0) / 1e9
+                                   for k in ("project", "raster", "backward", "pose_update", "corr") if prof[k] > 0},
                 "whole_step": {"algorithmic_bytes": ab["total"] * Bl,
                                "achieved": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9,
                                "frac": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9 / peak}}
@@ -275,19 +293,22 @@ def run_ours(args):
         dist.all_gather(ms_all, m_local)
         full = synth.make_sequence(B_total, H, W, mesh=MESH, seed=0, render_fn=None, period=B_total)
         full["target_masks"] = torch.cat(ms_all).cpu().numpy()
+        if C > 0:  # only this rank's frames are read by joint_optimize; the others are placeholders
+            full["correspondences"] = np.zeros((B_total, C, 6), np.float32)
+            full["correspondences"][shard.start:shard.stop] = seq["correspondences"]
     params = synth.to_object_parameters(full)
+    keys = ("rotations", "translations", "K_roi", "target_masks") + (("correspondences",) if C > 0 else ())
     for p in params:
-        for k in ("rotations", "translations", "K_roi", "target_masks"):
+        for k in keys:
             p[k] = p[k].pin_memory()
     faces_b = np.stack([full["faces"]] * B_total)
     e2e_iters = args.steps
-    h2d = sum(p[k].numel() * p[k].element_size() for p in params[shard.start:shard.stop]
-              for k in ("rotations", "translations", "K_roi", "target_masks"))
+    h2d = sum(p[k].numel() * p[k].element_size() for p in params[shard.start:shard.stop] for k in keys)
     h2d += full["verts"].nbytes + faces_b.nbytes
-    joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=LW, num_iterations=2, lr=LR)
+    joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=lw, num_iterations=2, lr=LR)
     barrier()
     t0 = time.perf_counter()
-    model2, evo = joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=LW,
+    model2, evo = joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=lw,
                                  num_iterations=e2e_iters, lr=LR, board=None)
     rot_h = model2.rotations_object.detach().cpu()
     tr_h = model2.translations_object.detach().cpu()
@@ -304,7 +325,7 @@ def run_ours(args):
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline()
+        cb, _ = cpu_baseline(C=C)
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -312,13 +333,15 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"custom_shoes-shaped joint pose optimisation, {Bl} frames per GPU "
                                    f"({B_total} total) 480x640, 5k-vertex mesh (V={V}, F={F}), 256x256 ROI rendered "
-                                   "512x512 + 2x2 pool, lw_sil 1 / lw_smooth 10, lr 1e-4 (BASELINE configs[1])",
-                       "frames_per_gpu": Bl, "frames_total": B_total, "parallelism": f"frame-shard x{world}",
+                                   f"512x512 + 2x2 pool, {C} correspondences per frame, lw_sil 1 / lw_smooth 10"
+                                   + (f" / lw_corr {LW_CORR}" if C > 0 else "") + ", lr 1e-4 (BASELINE configs[1])",
+                       "frames_per_gpu": Bl, "frames_total": B_total, "correspondences_per_frame": C,
+                       "parallelism": f"frame-shard x{world}",
                        "halo": fused.halo_mode,
                        "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": True},
             "roofline": roofline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": (8 + (1 if C > 0 else 0)) * args.steps,
             "loss_first_last": [hist["loss"][0], hist["loss"][-1]],
             "iou_first_last": [hist["iou_object"][0], hist["iou_object"][-1]],
         }
@@ -395,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=300)
+    ap.add_argument("--corr", type=int, default=10000,
+                    help="correspondences per frame (builder-defined reprojection term; 0 = the reference's two terms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
