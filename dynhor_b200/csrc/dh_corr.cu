@@ -21,10 +21,16 @@ using namespace dh;
 
 constexpr int kCorrThreads = 256;
 constexpr int kCorrTile = 1024;                       // records per stage
-constexpr int kCorrStages = 3;
+#ifndef DH_CORR_STAGES
+#define DH_CORR_STAGES 3
+#endif
+#ifndef DH_CORR_CTAS
+#define DH_CORR_CTAS 3
+#endif
+constexpr int kCorrStages = DH_CORR_STAGES;
 constexpr int kRecBytes = 24;
 constexpr int kStageBytes = kCorrTile * kRecBytes;    // 24 KB
-constexpr int kCorrCtasPerSm = 3;                     // 3 x 72 KB of shared memory per SM
+constexpr int kCorrCtasPerSm = DH_CORR_CTAS;          // 3 x 72 KB of shared memory per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -75,7 +81,64 @@ __device__ __forceinline__ void tile_span(long long t, int tpf, int C, const flo
     *nrec = min(kCorrTile, C - k * kCorrTile);
 }
 
-__global__ void __launch_bounds__(kCorrThreads)
+// ---- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): one instruction works on two records
+__device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Per-frame constants of the pair kernel, every value duplicated into both halves of a float2.
+struct CorrPose {
+    float2 Rs[9];   // |s| R
+    float2 T[3];
+    float2 SK[6];   // S * K (first two rows)
+    float2 nS;      // -S
+};
+
+// dh_core.h::corr_record for two records at once (lanes .x / .y), approximate reciprocal / rsqrt (relative error
+// 2^-22, far inside the 1e-4 / 1e-3 parity bars) and a branch-free Huber.  acc: 13 float2 accumulators.
+__device__ __forceinline__ void corr_pair(const float4 v0, const float4 v1, const float4 v2, const CorrPose& P,
+                                          float delta, float2* acc) {
+    const float2 X0 = make_float2(v0.x, v1.z), X1 = make_float2(v0.y, v1.w), X2 = make_float2(v0.z, v2.x);
+    const float2 tu = make_float2(v0.w, v2.y), tv = make_float2(v1.x, v2.z), w = make_float2(v1.y, v2.w);
+    const float2 cx = fma2(X0, P.Rs[0], fma2(X1, P.Rs[3], fma2(X2, P.Rs[6], P.T[0])));
+    const float2 cy = fma2(X0, P.Rs[1], fma2(X1, P.Rs[4], fma2(X2, P.Rs[7], P.T[1])));
+    const float2 cz = fma2(X0, P.Rs[2], fma2(X1, P.Rs[5], fma2(X2, P.Rs[8], P.T[2])));
+    const float2 iz = make_float2(rcp_fast(cz.x + 1e-9f), rcp_fast(cz.y + 1e-9f));
+    const float2 x_ = mul2(cx, iz), y_ = mul2(cy, iz);
+    const float2 eu = fma2(x_, P.SK[0], fma2(y_, P.SK[1], fma2(tu, P.nS, P.SK[2])));
+    const float2 ev = fma2(x_, P.SK[3], fma2(y_, P.SK[4], fma2(tv, P.nS, P.SK[5])));
+    const float2 r2 = fma2(eu, eu, mul2(ev, ev));
+    const float d2 = delta * delta, hd = 0.5f * delta;
+    const float rsx = rsqrt_fast(fmaxf(r2.x, 1e-30f)), rsy = rsqrt_fast(fmaxf(r2.y, 1e-30f));
+    const bool qx = r2.x <= d2, qy = r2.y <= d2;
+    const float2 f = make_float2(qx ? 1.0f : delta * rsx, qy ? 1.0f : delta * rsy);
+    const float2 rho = make_float2(qx ? 0.5f * r2.x : delta * (r2.x * rsx - hd),
+                                   qy ? 0.5f * r2.y : delta * (r2.y * rsy - hd));
+    const float2 wf = mul2(w, f);
+    const float2 gu = mul2(wf, eu), gv = mul2(wf, ev);
+    const float2 gx_ = fma2(gu, P.SK[0], mul2(gv, P.SK[3])), gy_ = fma2(gu, P.SK[1], mul2(gv, P.SK[4]));
+    const float2 g0 = mul2(gx_, iz), g1 = mul2(gy_, iz);
+    const float2 t = fma2(gx_, x_, mul2(gy_, y_));
+    const float2 g2 = mul2(t, make_float2(-iz.x, -iz.y));
+    acc[0] = add2(acc[0], g0); acc[1] = add2(acc[1], g1); acc[2] = add2(acc[2], g2);
+    acc[3] = fma2(X0, g0, acc[3]); acc[4] = fma2(X0, g1, acc[4]); acc[5] = fma2(X0, g2, acc[5]);
+    acc[6] = fma2(X1, g0, acc[6]); acc[7] = fma2(X1, g1, acc[7]); acc[8] = fma2(X1, g2, acc[8]);
+    acc[9] = fma2(X2, g0, acc[9]); acc[10] = fma2(X2, g1, acc[10]); acc[11] = fma2(X2, g2, acc[11]);
+    acc[12] = fma2(w, rho, acc[12]);
+}
+
+__global__ void __launch_bounds__(kCorrThreads, kCorrCtasPerSm)
 k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, const float* __restrict__ Rmat,
        const float* __restrict__ trans, const float* __restrict__ scale, const float* __restrict__ K, float S,
        float delta, float* __restrict__ partials) {
@@ -100,7 +163,9 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
         }
     }
     const float s_abs = fabsf(scale[0]);
-    float acc[13], Rm[9], Tm[3], Km[6];
+    float2 acc[13];
+    CorrPose P;
+    P.nS = bc(-S);
     int cur_b = -1;
     for (int i = 0; i < ntiles; i++) {
         const long long t = t0 + i;
@@ -108,26 +173,23 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
         if (b != cur_b) {  // first tile of a frame segment: its pose and intrinsics
             cur_b = b;
 #pragma unroll
-            for (int j = 0; j < 13; j++) acc[j] = 0.0f;
+            for (int j = 0; j < 13; j++) acc[j] = bc(0.0f);
 #pragma unroll
-            for (int j = 0; j < 9; j++) Rm[j] = Rmat[9 * b + j];
+            for (int j = 0; j < 9; j++) P.Rs[j] = bc(s_abs * Rmat[9 * b + j]);
 #pragma unroll
-            for (int j = 0; j < 3; j++) Tm[j] = trans[3 * b + j];
+            for (int j = 0; j < 3; j++) P.T[j] = bc(trans[3 * b + j]);
 #pragma unroll
-            for (int j = 0; j < 6; j++) Km[j] = K[9 * b + j];
+            for (int j = 0; j < 6; j++) P.SK[j] = bc(S * K[9 * b + j]);
         }
         const int stage = i % kCorrStages;
         mbar_wait(smem_u32(&bars[stage]), (uint32_t)(i / kCorrStages) & 1u);
-        const int nrec = min(kCorrTile, C - k * kCorrTile);
-        const float2* tile = reinterpret_cast<const float2*>(ring + stage * kStageBytes);
+        const int npairs = min(kCorrTile, C - k * kCorrTile) >> 1;       // C is even
+        // a pair of records = 48 bytes = three 16-byte shared-memory loads; lanes 48 B apart are conflict-free
+        const float4* tile = reinterpret_cast<const float4*>(ring + stage * kStageBytes);
 #pragma unroll
-        for (int j = 0; j < kCorrTile / kCorrThreads; j++) {
-            const int r = tid + j * kCorrThreads;
-            if (r < nrec) {
-                const float2 a = tile[3 * r], c = tile[3 * r + 1], e = tile[3 * r + 2];
-                const float rec[6] = {a.x, a.y, c.x, c.y, e.x, e.y};
-                corr_record(rec, Rm, Tm, s_abs, Km, S, delta, acc);
-            }
+        for (int j = 0; j < kCorrTile / 2 / kCorrThreads; j++) {
+            const int p = tid + j * kCorrThreads;
+            if (p < npairs) corr_pair(tile[3 * p], tile[3 * p + 1], tile[3 * p + 2], P, delta, acc);
         }
         __syncthreads();  // every thread is done with this stage: it may be refilled
         if (tid == 0 && i + kCorrStages < ntiles) {
@@ -140,7 +202,7 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
         if (i == ntiles - 1 || k == tpf - 1) {
 #pragma unroll
             for (int j = 0; j < 13; j++) {
-                float v = acc[j];
+                float v = acc[j].x + acc[j].y;
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (lane == 0) red[warp][j] = v;
             }

@@ -186,6 +186,6 @@ def test_full_size_round_trip_property():
     err1 = np.abs(model.translations_object.detach().cpu().numpy() - seq["T_gt"]).mean()
     gt = dict(seq, R_init=seq["R_gt"], T_init=seq["T_gt"], rot6d_init=np.ascontiguousarray(seq["R_gt"][:, :, :2]))
     l_gt = FusedJointOpt(_model(gt), lw, 1e-3, 2).evaluate()["loss_corr_obj"][0]
-    assert l_gt < l1 < l_gt + 0.1 * (l0 - l_gt), (l0, l1, l_gt)
+    assert 0.9 * l_gt < l1 < l_gt + 0.1 * (l0 - l_gt), (l0, l1, l_gt)   # may fit the noise slightly below l_gt
     assert err1 < 0.3 * err0, (err0, err1)
     fused.release()
