@@ -25,6 +25,7 @@ class DhSil(ctypes.Structure):
         ("faces", c_p), ("K", c_p),
         ("proj", c_p), ("bin_count", c_p), ("bins", c_p), ("fidx", c_p), ("alpha_bits", c_p),
         ("pos_pool", c_p), ("neg_pool", c_p), ("gpool", c_p), ("gmax", c_p), ("owned", c_p), ("negT", c_p), ("row_rng", c_p),
+        ("neg_lists", c_p),
     ]
 
 

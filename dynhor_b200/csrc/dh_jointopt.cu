@@ -513,45 +513,114 @@ __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long lon
 }
 
 // Frame-level maps the backward needs, built once per frame instead of once per backward CTA:
-//   negT    column-major bitmap of "uncovered && dL/dpixel < 0" (32x32 bit-block transposes through ballots)
-//   row_rng first / last set pixel of every row of that bitmap
-// One CTA per (32-row band, frame).
-__global__ void __launch_bounds__(kThreads)
-k_neg_maps(const dh_sil s) {
-    __shared__ uint32_t words[32][kMaxIS / 32];
+//   negT      column-major bitmap of "uncovered && dL/dpixel < 0" (32x32 bit-block transposes through ballots)
+//   row_rng   first / last set pixel of every row of that bitmap
+//   neg_lists (fused path) the same pixels as two compressed line lists -- one entry per pixel, grouped by row
+//             (axis 1) and by column (axis 0), ascending along the line -- so that an out scan walks the handful of
+//             contributing pixels of its line instead of searching bitmap words.  Per (frame, axis): kNLStart u16
+//             line starts (start[is] = total, 0xFFFF = more than kNLCap pixels: the frame takes the bitmap path),
+//             then kNLCap u16 entries: position along the line | (4 - covered sub-pixels of the pooled cell) << 10.
+// One CTA per frame.
+constexpr int kNegThreads = 512;
+constexpr int kNLStart = 520;              // >= kMaxIS + 1, keeps the entries 16-byte aligned
+constexpr int kNLAxis = 8192;              // u16 per (frame, axis)
+constexpr int kNLCap = kNLAxis - kNLStart;
+constexpr uint32_t kNLOverflow = 0xFFFFu;
+
+__device__ __forceinline__ int block_exclusive_scan_512(int v, int* s_wsum, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_wsum may still be read from the previous call
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < kNegThreads / 32; w++) {
+        const int t = s_wsum[w];
+        if (w < warp) base += t;
+        tot += t;
+    }
+    *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kNegThreads)
+k_neg_maps(const dh_sil s, int build_lists) {
+    extern __shared__ uint32_t nm_words[];  // [is][wpr] row-major, then [is][wpr] column-major
+    __shared__ int s_wsum[kNegThreads / 32];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
-    const int rb = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    uint32_t* words = nm_words;
+    uint32_t* wordsT = nm_words + is * wpr;
     const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
     const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
-    for (int i = tid; i < 32 * wpr; i += kThreads) {
+    for (int i = tid; i < is * wpr; i += kNegThreads) {
         const int r = i / wpr, w = i - r * wpr;
-        words[r][w] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, 32 * rb + r, w);
+        words[i] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, r, w);
     }
     __syncthreads();
-    if (tid < 32) {
-        int lo = is, hi = -1;
-        for (int w = 0; w < wpr; w++) {
-            const uint32_t bits = words[tid][w];
-            if (bits) {
-                if (lo == is) lo = (w << 5) + ctz32(bits);
-                hi = (w << 5) + 31 - __clz((int)bits);
-            }
-        }
-        s.row_rng[((size_t)b * 2 + 0) * is + 32 * rb + tid] = (int16_t)lo;
-        s.row_rng[((size_t)b * 2 + 1) * is + 32 * rb + tid] = (int16_t)hi;
-    }
-    uint32_t* gT = s.negT + (size_t)b * is * wpr;
-    for (int cb = warp; cb < wpr; cb += (kThreads / 32)) {
-        const uint32_t word = words[lane][cb];
+    for (int blk = warp; blk < wpr * wpr; blk += kNegThreads / 32) {
+        const int rb = blk / wpr, cb = blk - rb * wpr;
+        const uint32_t word = words[(32 * rb + lane) * wpr + cb];
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
             if (lane == j) mine = colw;
         }
-        gT[(32 * cb + lane) * wpr + rb] = mine;
+        wordsT[(32 * cb + lane) * wpr + rb] = mine;
+    }
+    __syncthreads();
+    uint32_t* gT = s.negT + (size_t)b * is * wpr;
+    for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[i];
+    for (int axis = 0; axis < 2; axis++) {
+        // axis 0: lines are columns (words of wordsT), axis 1: lines are rows
+        const uint32_t* W = axis ? words : wordsT;
+        int cnt = 0, lo = is, hi = -1;
+        if (tid < is) {
+            for (int w = 0; w < wpr; w++) {
+                const uint32_t bits = W[tid * wpr + w];
+                if (bits) {
+                    if (lo == is) lo = (w << 5) + ctz32(bits);
+                    hi = (w << 5) + 31 - __clz((int)bits);
+                    cnt += __popc(bits);
+                }
+            }
+            if (axis == 1) {
+                s.row_rng[((size_t)b * 2 + 0) * is + tid] = (int16_t)lo;
+                s.row_rng[((size_t)b * 2 + 1) * is + tid] = (int16_t)hi;
+            }
+        }
+        if (!build_lists) continue;
+        int total;
+        const int start = block_exclusive_scan_512(cnt, s_wsum, &total);
+        uint16_t* L = s.neg_lists + ((size_t)b * 2 + axis) * kNLAxis;
+        const bool over = total > kNLCap;
+        if (tid < is) L[tid] = (uint16_t)(over ? 0 : start);
+        if (tid == 0) L[is] = (uint16_t)(over ? kNLOverflow : (uint32_t)total);
+        if (over || tid >= is) continue;
+        uint16_t* E = L + kNLStart + start;
+        for (int w = 0; w < wpr; w++) {
+            uint32_t bits = W[tid * wpr + w];
+            while (bits) {
+                const int d1 = (w << 5) + ctz32(bits);
+                bits &= bits - 1;
+                const int r = axis ? tid : d1, c = axis ? d1 : tid;
+                int pop = 0;
+                if (s.aa) {
+                    const int sh = c & 30;
+                    const uint32_t w0 = __ldg(&ga[(r & ~1) * wpr + (c >> 5)]), w1 = __ldg(&ga[(r | 1) * wpr + (c >> 5)]);
+                    pop = __popc((w0 >> sh) & 3u) + __popc((w1 >> sh) & 3u);
+                }
+                *E++ = (uint16_t)((uint32_t)d1 | ((uint32_t)(4 - pop) << 10));
+            }
+        }
     }
 }
 
@@ -582,11 +651,15 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 // Returns 0, or the task word of the remainder when an out scan stops after kPairCap contributing pixels: long
 // scans (a line running along the mismatch band) are cut into pieces so that the 32 lanes of a round do similar
 // amounts of work.
-template <bool FUSED>
-__device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m, float eps,
-                                             float fpscale, float gcoef) {
+// LISTS: the out scan walks the line's compressed pixel list (k_neg_maps) instead of bitmap words; task word
+//        slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 (9 bits) | (resume list index + 1) << 18.
+struct NegLists { const uint16_t* start[2]; const uint16_t* ent[2]; };
+template <bool FUSED, bool LISTS>
+__device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m,
+                                             const NegLists& nl, float eps, float fpscale, float gcoef) {
     const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1;
-    const int d0 = (int)((t >> 9) & 1023u), resume = (int)(t >> 19);
+    const int d0 = LISTS ? (int)((t >> 9) & 511u) : (int)((t >> 9) & 1023u);
+    const int resume = LISTS ? (int)(t >> 18) : (int)(t >> 19);
     uint32_t cont = 0;
     const int is = m.is;
     // the crossing itself (d1_cross) comes with the task; only the two end points of the edge along the scan
@@ -614,7 +687,32 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
     float sa = 0.0f, sb = 0.0f;
     if (kind == 0) {
         const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
-        if (m.fidx[r_in * is + c_in] == fn) {
+        if (LISTS) {
+            if (m.fidx[r_in * is + c_in] == fn) {
+                // pixels beyond the edge: a suffix (direction +) or prefix (direction -) of the line's sorted list
+                const int ls = nl.start[axis][d0], le = nl.start[axis][d0 + 1];
+                const uint16_t* E = nl.ent[axis];
+                const int step = (0 < sp.direction) ? -1 : 1;
+                int i = resume ? resume - 1 : ((0 < sp.direction) ? le - 1 : ls);
+                const float dunit = (gcoef * 0.5f) * m.gscale;  // -dL/dpixel of a wanted pixel = code * dunit
+                int budget = kPairCap;
+                while (ls <= i && i < le) {
+                    const uint32_t e = E[i];
+                    const int d1 = (int)(e & 1023u);
+                    if ((0 < sp.direction) ? (d1 < d1_out) : (d1_out < d1)) break;
+                    if (budget == 0) {  // hand the rest of the line to a later round
+                        cont = (t & 0x3FFFFu) | ((uint32_t)(i + 1) << 18);
+                        break;
+                    }
+                    budget--;
+                    i += step;
+                    const float diff = (float)(e >> 10) * dunit;
+                    if (diff <= 0.0f) continue;
+                    sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is);
+                    sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is);
+                }
+            }
+        } else if (m.fidx[r_in * is + c_in] == fn) {
             int from, to;
             out_scan_range(sp.direction, d1_out, is, &from, &to);
             from = max(max(from, (int)((axis == 0) ? m.col_lo[d0] : m.row_lo[d0])), resume);
@@ -678,12 +776,14 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
 
 // FUSED: accumulate dL/d(T, R, s) of the frame into partials[b][chunk][16].
 // else : scatter dL/d(camera-space vertices) into grad_verts [B,V,3] (float atomics).
-template <bool FUSED>
+// LISTS (fused path only): out scans read the per-line pixel lists of k_neg_maps; frames whose lists overflowed
+//        are left to the bitmap kernel, which is launched behind it with only_overflow = 1.
+template <bool FUSED, bool LISTS>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
-           float* __restrict__ grad_verts, int nchunks, float gcoef) {
-    extern __shared__ uint32_t smw[];
+           float* __restrict__ grad_verts, int nchunks, float gcoef, int only_overflow) {
+    extern __shared__ __align__(16) uint32_t smw[];
     __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ BwdWarp s_warp[kBwdWarps];
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
@@ -693,11 +793,17 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     uint32_t* s_alpha = smw;
-    uint32_t* s_negT = s_alpha + is * wpr;
+    uint32_t* s_negT = s_alpha + is * wpr;                  // bitmap path
     uint32_t* s_negp = s_negT + is * wpr;
+    uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha + is * wpr);  // list path: 2 x (starts, entries)
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint16_t* g_lists = s.neg_lists + (size_t)b * 2 * kNLAxis;
+    if (LISTS || only_overflow) {
+        const bool over = g_lists[is] == kNLOverflow;
+        if (over == LISTS) return;
+    }
     const float gmax = s.gmax[b];
 
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
@@ -733,7 +839,23 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     if (tid == 0) s_next_batch = 0;
 
     // ---- stage the frame's bitmaps (built per frame by k_raster / k_neg_maps)
-    {
+    NegLists nl;
+    if (LISTS) {
+        // coverage bitmap + the two line lists (16-byte copies; only the entries in use)
+        const uint4* ga4 = reinterpret_cast<const uint4*>(s.alpha_bits + (size_t)b * is * wpr);
+        uint4* sa4 = reinterpret_cast<uint4*>(s_alpha);
+        for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
+        const int n_ent = g_lists[is];
+        const int n16 = (kNLStart + n_ent + 7) >> 3;
+#pragma unroll
+        for (int axis = 0; axis < 2; axis++) {
+            const uint4* g4 = reinterpret_cast<const uint4*>(g_lists + axis * kNLAxis);
+            uint4* s4 = reinterpret_cast<uint4*>(s_lists + axis * kNLAxis);
+            for (int i = tid; i < n16; i += kBwdThreads) s4[i] = g4[i];
+            nl.start[axis] = s_lists + axis * kNLAxis;
+            nl.ent[axis] = s_lists + axis * kNLAxis + kNLStart;
+        }
+    } else {
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
         const uint32_t* gt = s.negT + (size_t)b * is * wpr;
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
@@ -743,6 +865,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
             s_rng[1][i] = s.row_rng[((size_t)b * 2 + 1) * is + i];
         }
+        nl.start[0] = nl.start[1] = nl.ent[0] = nl.ent[1] = nullptr;
     }
     __syncthreads();
     if (tid == 0) {
@@ -750,17 +873,28 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
         s_woff[kBwdWarps] = o;
     }
-    for (int c = tid; c < is; c += kBwdThreads) {  // first / last set pixel of every column
-        int lo = is, hi = -1;
-        for (int w = 0; w < wpr; w++) {
-            const uint32_t bits = s_negT[c * wpr + w];
-            if (bits) {
-                if (lo == is) lo = (w << 5) + ctz32(bits);
-                hi = (w << 5) + 31 - __clz((int)bits);
-            }
+    if (LISTS) {
+        for (int i = tid; i < 2 * is; i += kBwdThreads) {  // first / last listed pixel of every row and column
+            const int axis = i >= is, line = axis ? i - is : i;   // axis of the LIST: 0 = columns, 1 = rows
+            const int ls = nl.start[axis][line], le = nl.start[axis][line + 1];
+            const int lo = ls < le ? (int)(nl.ent[axis][ls] & 1023u) : is;
+            const int hi = ls < le ? (int)(nl.ent[axis][le - 1] & 1023u) : -1;
+            s_rng[axis ? 0 : 2][line] = (int16_t)lo;
+            s_rng[axis ? 1 : 3][line] = (int16_t)hi;
         }
-        s_rng[2][c] = (int16_t)lo;
-        s_rng[3][c] = (int16_t)hi;
+    } else {
+        for (int c = tid; c < is; c += kBwdThreads) {  // first / last set pixel of every column
+            int lo = is, hi = -1;
+            for (int w = 0; w < wpr; w++) {
+                const uint32_t bits = s_negT[c * wpr + w];
+                if (bits) {
+                    if (lo == is) lo = (w << 5) + ctz32(bits);
+                    hi = (w << 5) + 31 - __clz((int)bits);
+                }
+            }
+            s_rng[2][c] = (int16_t)lo;
+            s_rng[3][c] = (int16_t)hi;
+        }
     }
     __syncthreads();
     if (gmax > 0.0f) {
@@ -777,7 +911,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     const int n_items = s_woff[kBwdWarps];
 
     BwdMaps m;
-    m.alpha = s_alpha; m.neg = nullptr; m.negT = s_negT; m.neg_pool = s_negp;
+    m.alpha = s_alpha; m.neg = nullptr; m.negT = LISTS ? nullptr : s_negT; m.neg_pool = LISTS ? nullptr : s_negp;
     m.pos_pool = s.pos_pool + (size_t)b * S * wprp;   // only the (rare, short) in scans read it: left in global
     m.row_lo = s_rng[0]; m.row_hi = s_rng[1]; m.col_lo = s_rng[2]; m.col_hi = s_rng[3];
     m.gpool = s.gpool + (size_t)b * S * S;
@@ -887,7 +1021,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             while (n_tasks >= 32) {
                 n_tasks -= 32;
                 const float dc = W.tcross[n_tasks + lane];
-                const uint32_t cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], dc, W, m, s.eps, fpscale, gcoef);
+                const uint32_t cont = bwd_task<FUSED, LISTS>(W.tasks[n_tasks + lane], dc, W, m, nl, s.eps, fpscale, gcoef);
                 __syncwarp();
                 const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
                 if (cont) {
@@ -906,7 +1040,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             float dc = 0.0f;
             if (lane < nt) {
                 dc = W.tcross[n_tasks + lane];
-                cont = bwd_task<FUSED>(W.tasks[n_tasks + lane], dc, W, m, s.eps, fpscale, gcoef);
+                cont = bwd_task<FUSED, LISTS>(W.tasks[n_tasks + lane], dc, W, m, nl, s.eps, fpscale, gcoef);
             }
             __syncwarp();
             const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
@@ -1148,7 +1282,8 @@ int check_sil(const dh_sil* s) {
         return fail(DH_ERR_UNSUPPORTED, "S=%d aa=%d: S must be a multiple of 32 and S*(aa?2:1) <= %d", s->S, s->aa,
                     kMaxIS);
     DH_REQUIRE(s->faces && s->K && s->proj && s->bin_count && s->bins && s->fidx && s->alpha_bits && s->pos_pool &&
-                   s->neg_pool && s->gmax && s->owned && s->negT && s->row_rng, "dh_sil has a NULL buffer");
+                   s->neg_pool && s->gmax && s->owned && s->negT && s->row_rng && s->neg_lists,
+               "dh_sil has a NULL buffer");
     DH_REQUIRE(s->B <= 65535, "B > 65535 frames per call (grid.y limit); shard the sequence");
     return DH_OK;
 }
@@ -1162,6 +1297,14 @@ size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-ow
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
     return (size_t)(2 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
+}
+size_t bwd_lists_smem_bytes(const dh_sil& s) {
+    const int is = raster_size(s);
+    return (size_t)(is * (is / 32)) * sizeof(uint32_t) + (size_t)2 * kNLAxis * sizeof(uint16_t);
+}
+size_t neg_maps_smem_bytes(const dh_sil& s) {
+    const int is = raster_size(s);
+    return (size_t)(2 * is * (is / 32)) * sizeof(uint32_t);
 }
 
 template <typename KernelT>
@@ -1219,14 +1362,22 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         DH_LAUNCH_OK("k_raster");
         DH_REC(4);
         if (mode != 2) {
-            k_neg_maps<<<dim3(is / 32, B), kThreads, 0, st>>>(s);
-            DH_LAUNCH_OK("k_neg_maps");
-            const size_t sb = bwd_smem_bytes(s);
-            rc = set_smem(k_backward<true>, sb);
+            rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
             if (rc) return rc;
-            k_backward<true><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(s, p.verts_og, p.Rmat, p.trans, p.scale,
-                                                                        p.partials, nullptr, p.nchunks, gcoef);
-            DH_LAUNCH_OK("k_backward");
+            k_neg_maps<<<B, kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1);
+            DH_LAUNCH_OK("k_neg_maps");
+            const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
+            rc = set_smem(k_backward<true, true>, sl);
+            if (rc) return rc;
+            rc = set_smem(k_backward<true, false>, sb);
+            if (rc) return rc;
+            k_backward<true, true><<<dim3(p.nchunks, B), kBwdThreads, sl, st>>>(
+                s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0);
+            DH_LAUNCH_OK("k_backward<lists>");
+            // frames with more contributing pixels than the lists hold (only these CTAs do any work)
+            k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
+                s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1);
+            DH_LAUNCH_OK("k_backward<bitmaps>");
         }
     } else {
         DH_REC(2); DH_REC(3); DH_REC(4);
@@ -1277,22 +1428,23 @@ std::vector<GraphEntry>& graph_cache() {
 // ================================================================================================ C ABI
 extern "C" {
 
-int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out8) {
-    DH_REQUIRE(out8 != nullptr && B > 0 && V > 0 && F > 0 && S > 0, "bad arguments");
-    out8[8] = (int64_t)B * 4;
-    out8[9] = (int64_t)B * ((2 * (int64_t)F + 31) / 32) * 4;
+int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out13) {
+    DH_REQUIRE(out13 != nullptr && B > 0 && V > 0 && F > 0 && S > 0, "bad arguments");
+    out13[8] = (int64_t)B * 4;
+    out13[9] = (int64_t)B * ((2 * (int64_t)F + 31) / 32) * 4;
     const int64_t is = aa ? 2 * S : S;
     const int64_t nstrips = (is + kSH - 1) / kSH, wprp = (S + 31) / 32;
-    out8[0] = (int64_t)B * V * 4 * 4;
-    out8[1] = (int64_t)B * nstrips * 2 * 4;
-    out8[2] = (int64_t)B * nstrips * 2 * F * 4;
-    out8[3] = (int64_t)B * is * is * 4;
-    out8[4] = (int64_t)B * is * (is / 32) * 4;
-    out8[5] = (int64_t)B * S * wprp * 4;
-    out8[6] = out8[5];
-    out8[7] = (int64_t)B * S * S * 4;
-    out8[10] = (int64_t)B * is * (is / 32) * 4;
-    out8[11] = (int64_t)B * 2 * is * 2;
+    out13[0] = (int64_t)B * V * 4 * 4;
+    out13[1] = (int64_t)B * nstrips * 2 * 4;
+    out13[2] = (int64_t)B * nstrips * 2 * F * 4;
+    out13[3] = (int64_t)B * is * is * 4;
+    out13[4] = (int64_t)B * is * (is / 32) * 4;
+    out13[5] = (int64_t)B * S * wprp * 4;
+    out13[6] = out13[5];
+    out13[7] = (int64_t)B * S * S * 4;
+    out13[10] = (int64_t)B * is * (is / 32) * 4;
+    out13[11] = (int64_t)B * 2 * is * 2;
+    out13[12] = (int64_t)B * 2 * kNLAxis * 2;
     return DH_OK;
 }
 
@@ -1331,14 +1483,16 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     DH_LAUNCH_OK("k_grad_signs");
     dh_sil t = *s;
     t.gpool = const_cast<float*>(grad_rend);
-    k_neg_maps<<<dim3(raster_size(t) / 32, t.B), kThreads, 0, st>>>(t);
+    rc = set_smem(k_neg_maps, neg_maps_smem_bytes(t));
+    if (rc) return rc;
+    k_neg_maps<<<t.B, kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sb = bwd_smem_bytes(t);
-    rc = set_smem(k_backward<false>, sb);
+    rc = set_smem(k_backward<false, false>, sb);
     if (rc) return rc;
     const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
-    k_backward<false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(t, verts_cam, nullptr, nullptr, nullptr, nullptr,
-                                                                  grad_verts, nchunks, 0.0f);
+    k_backward<false, false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(
+        t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
 }
@@ -1428,7 +1582,11 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         // warm the function attributes outside capture
         rc = set_smem(k_raster<true>, raster_smem_bytes(p->sil));
         if (rc) return rc;
-        rc = set_smem(k_backward<true>, bwd_smem_bytes(p->sil));
+        rc = set_smem(k_backward<true, false>, bwd_smem_bytes(p->sil));
+        if (rc) return rc;
+        rc = set_smem(k_backward<true, true>, bwd_lists_smem_bytes(p->sil));
+        if (rc) return rc;
+        rc = set_smem(k_neg_maps, neg_maps_smem_bytes(p->sil));
         if (rc) return rc;
         cudaStream_t cs;
         DH_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));

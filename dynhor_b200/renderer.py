@@ -65,7 +65,7 @@ class SilhouetteState:
             raise ValueError("face indices out of range")
         self.faces = faces_i32
         self.K = K.detach().reshape(-1, 3, 3).expand(B, 3, 3).contiguous().float()
-        sizes = (ctypes.c_int64 * 12)()
+        sizes = (ctypes.c_int64 * 13)()
         _lib.check(lib.dh_sil_scratch_bytes(self.B, self.V, self.F, self.S, self.aa, sizes), "dh_sil_scratch_bytes")
         self.buffers = [torch.empty(int(n), dtype=torch.uint8, device=dev) for n in sizes]
         c = _lib.DhSil()
@@ -73,7 +73,7 @@ class SilhouetteState:
         c.near_, c.far_, c.eps, c.orig_size = float(near), float(far), float(eps), float(orig_size)
         c.faces, c.K = self.faces.data_ptr(), self.K.data_ptr()
         (c.proj, c.bin_count, c.bins, c.fidx, c.alpha_bits, c.pos_pool, c.neg_pool, c.gpool, c.gmax,
-         c.owned, c.negT, c.row_rng) = [
+         c.owned, c.negT, c.row_rng, c.neg_lists) = [
             b.data_ptr() for b in self.buffers]
         self.c = c
         self.version = 0

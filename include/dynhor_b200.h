@@ -63,11 +63,12 @@ typedef struct dh_sil {
     uint32_t* owned;                   /* [B,ceil(2F/32)] bitmap: face fn owns at least one pixel of the frame       */
     uint32_t* negT;                    /* [B,is,is/32] column-major bitmap: pixel uncovered && dL/dpixel < 0         */
     int16_t* row_rng;                  /* [B,2,is] first / last set pixel of every row of that bitmap              */
+    uint16_t* neg_lists;               /* [B,2,8192] the same pixels as per-column / per-row lists (fused backward)  */
 } dh_sil;
 
-/* bytes of each scratch array, out[12] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,
- * neg_pool, gpool, gmax, owned, negT, row_rng) */
-int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out12);
+/* bytes of each scratch array, out[13] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,
+ * neg_pool, gpool, gmax, owned, negT, row_rng, neg_lists) */
+int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa, int64_t* out13);
 
 /* rend[B,S,S] = silhouettes of camera-space vertices verts_cam[B,V,3]  (forward of the renderer call). */
 int dh_sil_forward(const dh_sil* s, const float* verts_cam, float* rend, void* stream);

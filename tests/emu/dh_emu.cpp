@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../dynhor_b200/csrc/dh_core.h"
@@ -228,6 +229,91 @@ void emu_backward(const float* proj, const int32_t* faces, const int32_t* fidx, 
             }
         }
     }
+}
+
+// Work counters of the edge-scan backward of one frame (tools/bwd_stats.py): how many items, crossings, tasks,
+// bitmap words and contributing pixels the kernel's stages see.  out[16] (long long).
+void emu_backward_stats(const float* proj, const int32_t* faces, const int32_t* fidx, const uint32_t* alpha_bits,
+                        const uint32_t* neg_pool, int V, int F, int S, int aa, long long* out) {
+    const int is = aa ? 2 * S : S, wpr = is / 32, wprp = (S + 31) / 32;
+    std::vector<uint32_t> s_neg((size_t)is * wpr), s_negT((size_t)is * wpr, 0u);
+    std::vector<int> rlo(is, is), rhi(is, -1), clo(is, is), chi(is, -1);
+    long long n_neg = 0;
+    for (int i = 0; i < is * wpr; i++) {
+        const int r = i / wpr, w = i - r * wpr;
+        s_neg[i] = neg_row_word(alpha_bits, neg_pool, is, aa, wpr, wprp, r, w);
+    }
+    for (int r = 0; r < is; r++)
+        for (int c = 0; c < is; c++)
+            if ((s_neg[(size_t)r * wpr + (c >> 5)] >> (c & 31)) & 1u) {
+                s_negT[(size_t)c * wpr + (r >> 5)] |= 1u << (r & 31);
+                n_neg++;
+                if (c < rlo[r]) rlo[r] = c;
+                if (c > rhi[r]) rhi[r] = c;
+                if (r < clo[c]) clo[c] = r;
+                if (r > chi[c]) chi[c] = r;
+            }
+    std::vector<char> owned((size_t)2 * F, 0);
+    for (int i = 0; i < is * is; i++) if (fidx[i] >= 0) owned[fidx[i]] = 1;
+    long long items = 0, crossings = 0, t_out = 0, t_out_owner = 0, words = 0, words_nz = 0, pairs = 0, t_in = 0,
+              in_px = 0, in_pairs = 0, max_pairs_task = 0, span_iters = 0, front = 0;
+    for (int fn = 0; fn < 2 * F; fn++) {
+        FaceSetup fs;
+        int ids[3];
+        load_face(proj, faces, fn, F, fs, ids);
+        if (!finite3(fs.x[0], fs.x[1], fs.x[2]) || !finite3(fs.y[0], fs.y[1], fs.y[2])) continue;
+        if (face_backside(fs.x[0], fs.y[0], fs.x[1], fs.y[1], fs.x[2], fs.y[2])) continue;
+        front++;
+        if (!owned[fn]) continue;
+        items++;
+        float px[3], py[3];
+        for (int k = 0; k < 3; k++) { px[k] = ndc_to_pix(fs.x[k], is); py[k] = ndc_to_pix(fs.y[k], is); }
+        for (int edge = 0; edge < 3; edge++)
+            for (int axis = 0; axis < 2; axis++) {
+                Span sp;
+                span_setup(px, py, edge, axis, is, sp);
+                span_iters++;
+                for (int d0 = sp.d0_from; d0 <= sp.d0_to; d0++) {
+                    span_iters++;
+                    float d1_cross;
+                    int d1_in, d1_out;
+                    if (!span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) continue;
+                    crossings++;
+                    int from, to;
+                    out_scan_range(sp.direction, d1_out, is, &from, &to);
+                    const int lo = axis == 0 ? clo[d0] : rlo[d0], hi = axis == 0 ? chi[d0] : rhi[d0];
+                    const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
+                    const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
+                    if (std::max(from, lo) <= std::min(to, hi)) {
+                        t_out++;
+                        if (fidx[r_in * is + c_in] == fn) {
+                            t_out_owner++;
+                            from = std::max(from, lo); to = std::min(to, hi);
+                            long long np = 0;
+                            for (int w = from >> 5; w <= (to >> 5); w++) {
+                                uint32_t bits = axis == 0 ? s_negT[(size_t)d0 * wpr + w] : s_neg[(size_t)d0 * wpr + w];
+                                if (w == (from >> 5)) bits &= 0xFFFFFFFFu << (from & 31);
+                                if (w == (to >> 5)) bits &= 0xFFFFFFFFu >> (31 - (to & 31));
+                                words++;
+                                if (bits) words_nz++;
+                                np += __builtin_popcount(bits);
+                            }
+                            pairs += np;
+                            if (np > max_pairs_task) max_pairs_task = np;
+                        }
+                    }
+                    if (!((alpha_bits[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u)) {
+                        t_in++;
+                        int f2, t2;
+                        in_scan_range(sp, d0, d1_in, is, &f2, &t2);
+                        in_px += std::max(0, t2 - f2 + 1);
+                    }
+                }
+            }
+    }
+    long long o[16] = {front, items, span_iters, crossings, t_out, t_out_owner, words, words_nz, pairs, t_in, in_px,
+                       in_pairs, max_pairs_task, n_neg, 0, 0};
+    memcpy(out, o, sizeof(o));
 }
 
 // k_pose_prep: st [B,16]

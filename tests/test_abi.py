@@ -26,12 +26,12 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     from dynhor_b200 import _lib
     # dh_sil: 5 int32 + 4 float + 10 pointers; dh_jointopt embeds it
-    assert ctypes.sizeof(_lib.DhSil) == 40 + 14 * 8
+    assert ctypes.sizeof(_lib.DhSil) == 40 + 15 * 8
     assert ctypes.sizeof(_lib.DhJointOpt) % 8 == 0
     lib = _lib.load()
     for which, struct in enumerate((_lib.DhSil, _lib.DhJointOpt, _lib.DhCorr)):
         assert lib.dh_struct_bytes(which) == ctypes.sizeof(struct)
-    out = (ctypes.c_int64 * 12)()
+    out = (ctypes.c_int64 * 13)()
     assert lib.dh_sil_scratch_bytes(2, 10, 20, 64, 1, out) == 0
     assert out[3] == 2 * 128 * 128 * 4 and out[4] == 2 * 128 * 4 * 4
     assert lib.dh_sil_scratch_bytes(0, 10, 20, 64, 1, out) != 0
