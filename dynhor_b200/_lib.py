@@ -64,6 +64,7 @@ SIGNATURES = {
     "dh_last_error": (ctypes.c_char_p, []),
     "dh_struct_bytes": (c_i, [c_i]),
     "dh_device_info": (c_i, [ctypes.POINTER(c_i)] * 3),
+    "dh_tune_set": (c_i, [c_i, c_i]),
     "dh_sil_scratch_bytes": (c_i, [c_i, c_i, c_i, c_i, c_i, ctypes.POINTER(c_l)]),
     "dh_sil_forward": (c_i, [ctypes.POINTER(DhSil), c_p, c_p, c_p]),
     "dh_sil_backward": (c_i, [ctypes.POINTER(DhSil), c_p, c_p, c_p, c_p]),

@@ -491,10 +491,19 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_BWD_THREADS
 #define DH_BWD_THREADS 288
 #endif
+#ifndef DH_BWD_MIN_CTAS
+#define DH_BWD_MIN_CTAS 2
+#endif
+#ifndef DH_PREFETCH_OWNER
+#define DH_PREFETCH_OWNER 0
+#endif
 constexpr int kBwdThreads = DH_BWD_THREADS;   // 9 warps x 2 CTAs/SM is what ~109 registers and ~112 KB smem allow
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kTaskCap = 96;
-constexpr int kChunkFaces = 1024;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
+#ifndef DH_CHUNK_FACES
+#define DH_CHUNK_FACES 1024
+#endif
+constexpr int kChunkFaces = DH_CHUNK_FACES;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
 #ifndef DH_PAIR_CAP
 #define DH_PAIR_CAP 8
 #endif
@@ -508,8 +517,16 @@ struct BwdWarp {
     float tcross[kTaskCap];              // d1_cross of the task's crossing (computed once, in phase 1)
 };
 
+// 64-bit fixed-point accumulation in shared memory as two native 32-bit atomics (a 64-bit shared atomicAdd is a
+// compare-and-swap loop): the low words add up modulo 2^32, and every add that wraps carries one into the high
+// word.  The number of wraps does not depend on the order of the adds, so the total is exact once all are done.
 __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long long v) {
-    if (v != 0) atomicAdd(a, (unsigned long long)v);
+    if (v == 0) return;
+    uint32_t* p = reinterpret_cast<uint32_t*>(a);
+    const uint32_t lo = (uint32_t)(unsigned long long)v, hi = (uint32_t)((unsigned long long)v >> 32);
+    const uint32_t old = atomicAdd(p, lo);
+    const uint32_t h = hi + (((uint32_t)(old + lo) < lo) ? 1u : 0u);
+    if (h) atomicAdd(p + 1, h);
 }
 
 // Frame-level maps the backward needs, built once per frame instead of once per backward CTA:
@@ -521,9 +538,12 @@ __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long lon
 //             line starts (start[is] = total, 0xFFFF = more than kNLCap pixels: the frame takes the bitmap path),
 //             then kNLCap u16 entries: position along the line | (4 - covered sub-pixels of the pooled cell) << 10.
 // One CTA per frame.
+#ifndef DH_LISTS_GLOBAL
+#define DH_LISTS_GLOBAL 1   // 1: the backward reads the pixel lists from global memory through L1; 0: staged in smem
+#endif
 constexpr int kNegThreads = 512;
 constexpr int kNLStart = 520;              // >= kMaxIS + 1, keeps the entries 16-byte aligned
-constexpr int kNLAxis = 8192;              // u16 per (frame, axis)
+constexpr int kNLAxis = DH_LISTS_GLOBAL ? 32768 : 8192;  // u16 per (frame, axis)
 constexpr int kNLCap = kNLAxis - kNLStart;
 constexpr uint32_t kNLOverflow = 0xFFFFu;
 
@@ -549,7 +569,7 @@ __device__ __forceinline__ int block_exclusive_scan_512(int v, int* s_wsum, int*
 }
 
 __global__ void __launch_bounds__(kNegThreads)
-k_neg_maps(const dh_sil s, int build_lists) {
+k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
     extern __shared__ uint32_t nm_words[];  // [is][wpr] row-major, then [is][wpr] column-major
     __shared__ int s_wsum[kNegThreads / 32];
     const int is = raster_size(s), S = s.S;
@@ -601,7 +621,7 @@ k_neg_maps(const dh_sil s, int build_lists) {
         int total;
         const int start = block_exclusive_scan_512(cnt, s_wsum, &total);
         uint16_t* L = s.neg_lists + ((size_t)b * 2 + axis) * kNLAxis;
-        const bool over = total > kNLCap;
+        const bool over = total > list_cap;
         if (tid < is) L[tid] = (uint16_t)(over ? 0 : start);
         if (tid == 0) L[is] = (uint16_t)(over ? kNLOverflow : (uint32_t)total);
         if (over || tid >= is) continue;
@@ -688,29 +708,43 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
     if (kind == 0) {
         const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
         if (LISTS) {
-            if (m.fidx[r_in * is + c_in] == fn) {
-                // pixels beyond the edge: a suffix (direction +) or prefix (direction -) of the line's sorted list
-                const int ls = nl.start[axis][d0], le = nl.start[axis][d0 + 1];
-                const uint16_t* E = nl.ent[axis];
-                const int step = (0 < sp.direction) ? -1 : 1;
-                int i = resume ? resume - 1 : ((0 < sp.direction) ? le - 1 : ls);
-                const float dunit = (gcoef * 0.5f) * m.gscale;  // -dL/dpixel of a wanted pixel = code * dunit
-                int budget = kPairCap;
-                while (ls <= i && i < le) {
+            // Pixels beyond the edge = a suffix (direction +, walked downwards) or a prefix (direction -, walked
+            // upwards) of the line's sorted list.  Along an out scan d1 - d1_cross has the sign of the direction, so
+            // the sign of dist = k (d1 - d1_cross) (2/is) -- and with it the sign of eps -- is fixed per task, and
+            // a skipped term (k == 0) becomes 1 / inf.  -dL/dpixel = code * dunit; dunit multiplies the task's sums.
+            const int own = m.fidx[r_in * is + c_in];
+            const int ls = nl.start[axis][d0], le = nl.start[axis][d0 + 1];
+            const uint16_t* E = nl.ent[axis];
+            const bool up = sp.direction < 0;
+            const int step = up ? 1 : -1;
+            const int i_end = up ? le : ls - 1;
+            const int lim = d1_out * step;
+            int i = resume ? resume - 1 : (up ? ls : le - 1);
+            const int left = (i_end - i) * step;
+            const int i_stop = (left > kPairCap) ? i + step * kPairCap : i_end;
+            const float dunit = (gcoef * 0.5f) * m.gscale;
+            const float ka2 = ec.ka * two_over_is, kb2 = ec.kb * two_over_is;
+            const float dirf = (float)sp.direction;
+            const float inf = __int_as_float(0x7f800000);
+            const float ea = (ec.ka == 0.0f) ? inf : ((0.0f < ka2 * dirf) ? eps : -eps);
+            const float eb = (ec.kb == 0.0f) ? inf : ((0.0f < kb2 * dirf) ? eps : -eps);
+            if (own == fn && 0.0f < dunit && (ec.ka != 0.0f || ec.kb != 0.0f)) {
+                while (i != i_stop) {
                     const uint32_t e = E[i];
                     const int d1 = (int)(e & 1023u);
-                    if ((0 < sp.direction) ? (d1 < d1_out) : (d1_out < d1)) break;
-                    if (budget == 0) {  // hand the rest of the line to a later round
-                        cont = (t & 0x3FFFFu) | ((uint32_t)(i + 1) << 18);
-                        break;
-                    }
-                    budget--;
+                    if (lim < d1 * step) { i = i_end; break; }  // past d1_out against the walking direction
+                    const float x = (float)d1 - d1_cross;
+                    const float cf = (float)(e >> 10);
+                    float ra, rb;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(fmaf(ka2, x, ea)));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(fmaf(kb2, x, eb)));
+                    sa = fmaf(cf, ra, sa);
+                    sb = fmaf(cf, rb, sb);
                     i += step;
-                    const float diff = (float)(e >> 10) * dunit;
-                    if (diff <= 0.0f) continue;
-                    sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is);
-                    sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is);
                 }
+                if (i != i_end) cont = (t & 0x3FFFFu) | ((uint32_t)(i + 1) << 18);  // rest of the line: a later round
+                sa *= dunit;
+                sb *= dunit;
             }
         } else if (m.fidx[r_in * is + c_in] == fn) {
             int from, to;
@@ -779,7 +813,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
 // LISTS (fused path only): out scans read the per-line pixel lists of k_neg_maps; frames whose lists overflowed
 //        are left to the bitmap kernel, which is launched behind it with only_overflow = 1.
 template <bool FUSED, bool LISTS>
-__global__ void __launch_bounds__(kBwdThreads, 2)
+__global__ void __launch_bounds__(kBwdThreads, DH_BWD_MIN_CTAS)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks, float gcoef, int only_overflow) {
@@ -845,6 +879,13 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint4* ga4 = reinterpret_cast<const uint4*>(s.alpha_bits + (size_t)b * is * wpr);
         uint4* sa4 = reinterpret_cast<uint4*>(s_alpha);
         for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
+#if DH_LISTS_GLOBAL
+#pragma unroll
+        for (int axis = 0; axis < 2; axis++) {   // the lists stay in global memory (L1-cached reads)
+            nl.start[axis] = g_lists + axis * kNLAxis;
+            nl.ent[axis] = g_lists + axis * kNLAxis + kNLStart;
+        }
+#else
         const int n_ent = g_lists[is];
         const int n16 = (kNLStart + n_ent + 7) >> 3;
 #pragma unroll
@@ -855,6 +896,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             nl.start[axis] = s_lists + axis * kNLAxis;
             nl.ent[axis] = s_lists + axis * kNLAxis + kNLStart;
         }
+#endif
     } else {
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
         const uint32_t* gt = s.negT + (size_t)b * is * wpr;
@@ -996,6 +1038,12 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                         const int lo = (axis == 0) ? m.col_lo[d0] : m.row_lo[d0];
                         const int hi = (axis == 0) ? m.col_hi[d0] : m.row_hi[d0];
                         t_out = max(from, lo) <= min(to, hi);
+#if DH_PREFETCH_OWNER
+                        if (t_out) {  // the ownership test of phase 2 reads this pixel of the face-index map
+                            const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(m.fidx + r_in * is + c_in));
+                        }
+#endif
                         const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
                         t_in = !alpha_at(m, r_out, c_out);
                         tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
@@ -1294,13 +1342,17 @@ size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-ow
            (size_t)(words <= kOwnedSmemWords ? words : 0) * sizeof(uint32_t);
 }
 
+// pixels per frame the list path takes (dh_tune_set knob 0 lowers it: the tests force the bitmap path with it)
+int g_neg_list_cap = kNLCap;
+int neg_list_cap() { return g_neg_list_cap < kNLCap ? (g_neg_list_cap < 0 ? 0 : g_neg_list_cap) : kNLCap; }
+
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
     return (size_t)(2 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
 }
 size_t bwd_lists_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(is * (is / 32)) * sizeof(uint32_t) + (size_t)2 * kNLAxis * sizeof(uint16_t);
+    return (size_t)(is * (is / 32)) * sizeof(uint32_t) + (DH_LISTS_GLOBAL ? 0 : (size_t)2 * kNLAxis * sizeof(uint16_t));
 }
 size_t neg_maps_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
@@ -1364,7 +1416,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         if (mode != 2) {
             rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
             if (rc) return rc;
-            k_neg_maps<<<B, kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1);
+            k_neg_maps<<<B, kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
             DH_LAUNCH_OK("k_neg_maps");
             const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
             rc = set_smem(k_backward<true, true>, sl);
@@ -1485,7 +1537,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     t.gpool = const_cast<float*>(grad_rend);
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(t));
     if (rc) return rc;
-    k_neg_maps<<<t.B, kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0);
+    k_neg_maps<<<t.B, kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0, 0);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sb = bwd_smem_bytes(t);
     rc = set_smem(k_backward<false, false>, sb);
@@ -1494,6 +1546,12 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     k_backward<false, false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(
         t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0);
     DH_LAUNCH_OK("k_backward");
+    return DH_OK;
+}
+
+int dh_tune_set(int32_t knob, int32_t value) {
+    DH_REQUIRE(knob == 0, "dh_tune_set: unknown knob");
+    g_neg_list_cap = value < 0 ? kNLCap : value;  // < 0 restores the default
     return DH_OK;
 }
 

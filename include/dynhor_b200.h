@@ -38,6 +38,10 @@ const char* dh_last_error(void);
 int dh_struct_bytes(int32_t which);
 /* sm count, compute capability of the current device */
 int dh_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* tuning / test knobs.  knob 0: contributing pixels per frame up to which the fused backward uses its per-line
+ * pixel lists (default 32248; frames above take the bitmap kernel; value < 0 restores the default).  Takes effect
+ * for launches and graph captures made after the call. */
+int dh_tune_set(int32_t knob, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------
  * Silhouette renderer state.  Replaces nr.renderer.Renderer(image_size=S, K, R=I, t=0, orig_size,
@@ -63,7 +67,7 @@ typedef struct dh_sil {
     uint32_t* owned;                   /* [B,ceil(2F/32)] bitmap: face fn owns at least one pixel of the frame       */
     uint32_t* negT;                    /* [B,is,is/32] column-major bitmap: pixel uncovered && dL/dpixel < 0         */
     int16_t* row_rng;                  /* [B,2,is] first / last set pixel of every row of that bitmap              */
-    uint16_t* neg_lists;               /* [B,2,8192] the same pixels as per-column / per-row lists (fused backward)  */
+    uint16_t* neg_lists;               /* [B,2,32768] the same pixels as per-column / per-row lists (fused backward) */
 } dh_sil;
 
 /* bytes of each scratch array, out[13] in the struct's order (proj, bin_count, bins, fidx, alpha_bits, pos_pool,

@@ -234,7 +234,7 @@ void emu_backward(const float* proj, const int32_t* faces, const int32_t* fidx, 
 // Work counters of the edge-scan backward of one frame (tools/bwd_stats.py): how many items, crossings, tasks,
 // bitmap words and contributing pixels the kernel's stages see.  out[16] (long long).
 void emu_backward_stats(const float* proj, const int32_t* faces, const int32_t* fidx, const uint32_t* alpha_bits,
-                        const uint32_t* neg_pool, int V, int F, int S, int aa, long long* out) {
+                        const uint32_t* neg_pool, int V, int F, int S, int aa, long long* out, int* span_len) {
     const int is = aa ? 2 * S : S, wpr = is / 32, wprp = (S + 31) / 32;
     std::vector<uint32_t> s_neg((size_t)is * wpr), s_negT((size_t)is * wpr, 0u);
     std::vector<int> rlo(is, is), rhi(is, -1), clo(is, is), chi(is, -1);
@@ -273,6 +273,7 @@ void emu_backward_stats(const float* proj, const int32_t* faces, const int32_t* 
                 Span sp;
                 span_setup(px, py, edge, axis, is, sp);
                 span_iters++;
+                if (span_len) span_len[(items - 1) * 6 + edge * 2 + axis] = std::max(0, sp.d0_to - sp.d0_from + 1);
                 for (int d0 = sp.d0_from; d0 <= sp.d0_to; d0++) {
                     span_iters++;
                     float d1_cross;

@@ -274,6 +274,36 @@ def test_reference_size_frames_vs_oracle(big_seq):
         assert rel_err(g_tr[b].cpu().numpy(), grads["trans"][b]) < GRAD_RTOL, b
 
 
+def test_backward_list_path_and_bitmap_path_agree(big_seq):
+    """The fused backward walks per-line pixel lists; frames with more contributing pixels than the lists hold take
+    the bitmap kernel.  Forcing every frame onto the bitmap path (dh_tune_set knob 0) must give the same gradients,
+    and a mixed launch (some frames over the cap, some under) as well."""
+    from dynhor_b200 import _lib
+    from dynhor_b200.jointopt import FusedJointOpt
+    lib = _lib.load()
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    fused = FusedJointOpt(_model_from_seq(big_seq), lw, 1e-4, 4)
+    g_rot, g_tr, _ = [t.clone() if t is not None else None for t in fused.grads()]
+    assert float(g_rot.abs().max()) > 0
+    # contributing pixels per frame, from the lists' totals
+    B = len(big_seq["R_init"])
+    lists = fused.sil.buffers[12].view(torch.int16).view(B, 2, -1)
+    totals = (lists[:, 0, 512].to(torch.int32) & 0xFFFF).cpu().numpy()
+    assert (totals > 0).all() and (totals < 0xFFFF).all()
+    try:
+        for cap in (0, int(np.sort(totals)[B // 2])):   # everything on the bitmap path; about half of the frames
+            _lib.check(lib.dh_tune_set(0, cap), "dh_tune_set")
+            r2, t2, _ = fused.grads()
+            lists = fused.sil.buffers[12].view(torch.int16).view(B, 2, -1)
+            over = ((lists[:, 0, 512].to(torch.int32) & 0xFFFF) == 0xFFFF).cpu().numpy()
+            assert over.sum() == (totals > cap).sum() and over.any()
+            for b in range(B):
+                assert rel_err(r2[b].cpu().numpy(), g_rot[b].cpu().numpy()) < 1e-4, (cap, b)
+                assert rel_err(t2[b].cpu().numpy(), g_tr[b].cpu().numpy()) < 1e-4, (cap, b)
+    finally:
+        lib.dh_tune_set(0, -1)
+
+
 def test_renderer_backward_arbitrary_gradient_vs_oracle(big_seq):
     """dh_sil_backward with a random upstream gradient vs the oracle's autograd on the same vertices."""
     from dynhor_b200.renderer import Renderer

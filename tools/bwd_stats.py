@@ -33,11 +33,20 @@ def main():
         mt = np.where(seq["target_masks"] > 0, 1, np.where(seq["target_masks"] >= 0, 0, -1)).astype(np.int8)
         counts, gpool, pos, neg, rend = emu_lib.loss_epilogue(abits, mt, S, True, np.float32(1e-6))
         out = np.zeros(16, np.int64)
+        span_len = np.zeros((2 * len(faces), 6), np.int32)
         emu_lib.lib().emu_backward_stats(emu_lib._p(np.ascontiguousarray(proj[0])), emu_lib._p(faces),
                                          emu_lib._p(np.ascontiguousarray(fidx[0])),
                                          emu_lib._p(np.ascontiguousarray(abits[0])),
                                          emu_lib._p(np.ascontiguousarray(neg[0])), len(verts), len(faces), S, 1,
-                                         emu_lib._p(out))
+                                         emu_lib._p(out), emu_lib._p(span_len))
+        sl = span_len[:out[1]]
+        # items are processed in face order: the given windings of a chunk first, then (per face) ... approximate by order
+        nb = len(sl) // 32
+        bl = sl[:nb * 32].reshape(nb, 32, 6)
+        A = bl.sum(2).max(1).sum()           # one loop over all six spans per lane
+        Bv = bl.max(1).sum()                 # six uniform loops
+        print("   loop iterations per frame: per-lane-sequential", int(A) + 6 * nb, " uniform-span", int(Bv),
+              " ideal", int(sl.sum() / 32))
         rows.append(out[:len(NAMES)])
         print(off, dict(zip(NAMES, out.tolist())))
     m = np.mean(rows, 0)
