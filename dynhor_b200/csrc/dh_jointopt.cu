@@ -497,6 +497,25 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_PREFETCH_OWNER
 #define DH_PREFETCH_OWNER 0
 #endif
+#ifndef DH_EVEN_LAST
+#define DH_EVEN_LAST 1
+#endif
+#ifndef DH_FIDX_NOALLOC
+#define DH_FIDX_NOALLOC 0
+#endif
+#ifndef DH_FAST_COEF
+#define DH_FAST_COEF 1
+#endif
+// one face-index read of the ownership test: random 4-byte reads of a 1 MB map, no reuse
+__device__ __forceinline__ int load_fidx(const int32_t* p) {
+#if DH_FIDX_NOALLOC
+    int v;
+    asm volatile("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 constexpr int kBwdThreads = DH_BWD_THREADS;   // 9 warps x 2 CTAs/SM is what ~109 registers and ~112 KB smem allow
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kTaskCap = 96;
@@ -509,12 +528,18 @@ constexpr int kChunkFaces = DH_CHUNK_FACES;   // faces per backward CTA at most 
 #endif
 constexpr int kPairCap = DH_PAIR_CAP;  // pixels one out-scan task handles before it re-queues its remainder
 
-struct BwdWarp {
+struct __align__(16) BwdWarp {
     float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot
     int fn[32];
     unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
-    uint32_t tasks[kTaskCap];            // slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 | resume d1 << 19
-    float tcross[kTaskCap];              // d1_cross of the task's crossing (computed once, in phase 1)
+    uint2 tq[kTaskCap];                  // .x: slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 | resume d1 << 19
+                                         // .y: d1_cross of the task's crossing (float bits; computed once, in phase 1)
+};
+// list path only: the six (edge, axis) spans of every face of the batch, set up at full lanes before the crossing
+// loop.  rng = d0_from | d0_to << 10 | (direction > 0) << 20 | empty << 21
+struct __align__(16) BwdSpans {
+    float slope[6][32];
+    uint32_t rng[6][32];
 };
 
 // 64-bit fixed-point accumulation in shared memory as two native 32-bit atomics (a 64-bit shared atomicAdd is a
@@ -673,7 +698,11 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 // amounts of work.
 // LISTS: the out scan walks the line's compressed pixel list (k_neg_maps) instead of bitmap words; task word
 //        slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 (9 bits) | (resume list index + 1) << 18.
-struct NegLists { const uint16_t* start[2]; const uint16_t* ent[2]; };
+struct NegLists {   // both axes behind one base pointer (indexing an array of pointers by axis would go to local memory)
+    const uint16_t* base;
+    __device__ __forceinline__ const uint16_t* start(int axis) const { return base + axis * kNLAxis; }
+    __device__ __forceinline__ const uint16_t* ent(int axis) const { return base + axis * kNLAxis + kNLStart; }
+};
 template <bool FUSED, bool LISTS>
 __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m,
                                              const NegLists& nl, float eps, float fpscale, float gcoef) {
@@ -694,14 +723,25 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
     if (0 < sp.direction) d1_in = f2i_sat(floorf(d1_cross));
     else                  d1_in = f2i_sat(ceilf(d1_cross));
     const int d1_out = d1_in + sp.direction;
-    if (kind != 0) {
-        float px[3], py[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) { px[k] = W.px[k][slot]; py[k] = W.py[k][slot]; }
-        span_setup(px, py, edge, axis, is, sp);
+    if (kind != 0) {  // in scan: the whole span, read by (dynamic) vertex index straight from shared memory
+        const int e2 = (edge + 2) % 3;
+        sp.p01 = axis ? W.px[edge][slot] : W.py[edge][slot];
+        sp.p11 = axis ? W.px[e1][slot] : W.py[e1][slot];
+        sp.p20 = axis ? W.py[e2][slot] : W.px[e2][slot];
+        sp.p21 = axis ? W.px[e2][slot] : W.py[e2][slot];
+        sp.d0_from = f2i_sat(fmaxf(ceilf(fminf(sp.p00, sp.p10)), 0.0f));
+        sp.d0_to = f2i_sat(fminf(fmaxf(sp.p00, sp.p10), (float)(is - 1)));
+        sp.slope = (sp.p11 - sp.p01) / (sp.p10 - sp.p00);
     }
     const int fn = W.fn[slot];
     EdgeCoef ec;
+#if DH_FAST_COEF
+    if (LISTS) {  // gradients carry a 1e-3 bar: the approximate divider (2 ulp) is enough for the coefficients
+        const float num = sp.p10 - sp.p00;
+        ec.ka = (sp.p10 != (float)d0) ? __fdividef(num, sp.p10 - (float)d0) : 0.0f;
+        ec.kb = (sp.p00 != (float)d0) ? __fdividef(num, (float)d0 - sp.p00) : 0.0f;
+    } else
+#endif
     edge_coefs(sp.p00, sp.p10, d0, ec);
     const float two_over_is = 2.0f / (float)is;
     float sa = 0.0f, sb = 0.0f;
@@ -712,9 +752,10 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             // upwards) of the line's sorted list.  Along an out scan d1 - d1_cross has the sign of the direction, so
             // the sign of dist = k (d1 - d1_cross) (2/is) -- and with it the sign of eps -- is fixed per task, and
             // a skipped term (k == 0) becomes 1 / inf.  -dL/dpixel = code * dunit; dunit multiplies the task's sums.
-            const int own = m.fidx[r_in * is + c_in];
-            const int ls = nl.start[axis][d0], le = nl.start[axis][d0 + 1];
-            const uint16_t* E = nl.ent[axis];
+            const int own = load_fidx(m.fidx + r_in * is + c_in);
+            const uint16_t* L = nl.start(axis);
+            const int ls = L[d0], le = L[d0 + 1];
+            const uint16_t* E = L + kNLStart;
             const bool up = sp.direction < 0;
             const int step = up ? 1 : -1;
             const int i_end = up ? le : ls - 1;
@@ -819,14 +860,15 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
            float* __restrict__ grad_verts, int nchunks, float gcoef, int only_overflow) {
     extern __shared__ __align__(16) uint32_t smw[];
     __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
-    __shared__ BwdWarp s_warp[kBwdWarps];
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
-    __shared__ float s_bsum[2 * kChunkFaces / 32][13];  // pose-gradient partial sums, one row per batch of 32 items
+    __shared__ float s_bsum[2 * kChunkFaces / 32 + kBwdWarps][13];  // pose-gradient partial sums, one row per batch
     __shared__ int s_wcount[kBwdWarps], s_woff[kBwdWarps + 1];
     __shared__ int s_next_batch;
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
-    uint32_t* s_alpha = smw;
+    BwdWarp* s_warp = reinterpret_cast<BwdWarp*>(smw);   // per-warp queues first (static smem is capped at 48 KB)
+    BwdSpans* s_spans = reinterpret_cast<BwdSpans*>(smw + kBwdWarps * (sizeof(BwdWarp) / sizeof(uint32_t)));
+    uint32_t* s_alpha = smw + kBwdWarps * ((sizeof(BwdWarp) + (LISTS ? sizeof(BwdSpans) : 0)) / sizeof(uint32_t));
     uint32_t* s_negT = s_alpha + is * wpr;                  // bitmap path
     uint32_t* s_negp = s_negT + is * wpr;
     uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha + is * wpr);  // list path: 2 x (starts, entries)
@@ -880,11 +922,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         uint4* sa4 = reinterpret_cast<uint4*>(s_alpha);
         for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
 #if DH_LISTS_GLOBAL
-#pragma unroll
-        for (int axis = 0; axis < 2; axis++) {   // the lists stay in global memory (L1-cached reads)
-            nl.start[axis] = g_lists + axis * kNLAxis;
-            nl.ent[axis] = g_lists + axis * kNLAxis + kNLStart;
-        }
+        nl.base = g_lists;   // the lists stay in global memory (L1-cached reads)
 #else
         const int n_ent = g_lists[is];
         const int n16 = (kNLStart + n_ent + 7) >> 3;
@@ -893,9 +931,8 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             const uint4* g4 = reinterpret_cast<const uint4*>(g_lists + axis * kNLAxis);
             uint4* s4 = reinterpret_cast<uint4*>(s_lists + axis * kNLAxis);
             for (int i = tid; i < n16; i += kBwdThreads) s4[i] = g4[i];
-            nl.start[axis] = s_lists + axis * kNLAxis;
-            nl.ent[axis] = s_lists + axis * kNLAxis + kNLStart;
         }
+        nl.base = s_lists;
 #endif
     } else {
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
@@ -907,7 +944,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
             s_rng[1][i] = s.row_rng[((size_t)b * 2 + 1) * is + i];
         }
-        nl.start[0] = nl.start[1] = nl.ent[0] = nl.ent[1] = nullptr;
+        nl.base = nullptr;
     }
     __syncthreads();
     if (tid == 0) {
@@ -918,9 +955,10 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     if (LISTS) {
         for (int i = tid; i < 2 * is; i += kBwdThreads) {  // first / last listed pixel of every row and column
             const int axis = i >= is, line = axis ? i - is : i;   // axis of the LIST: 0 = columns, 1 = rows
-            const int ls = nl.start[axis][line], le = nl.start[axis][line + 1];
-            const int lo = ls < le ? (int)(nl.ent[axis][ls] & 1023u) : is;
-            const int hi = ls < le ? (int)(nl.ent[axis][le - 1] & 1023u) : -1;
+            const uint16_t* L = nl.start(axis);
+            const int ls = L[line], le = L[line + 1];
+            const int lo = ls < le ? (int)(L[kNLStart + ls] & 1023u) : is;
+            const int hi = ls < le ? (int)(L[kNLStart + le - 1] & 1023u) : -1;
             s_rng[axis ? 0 : 2][line] = (int16_t)lo;
             s_rng[axis ? 1 : 3][line] = (int16_t)hi;
         }
@@ -978,22 +1016,36 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     }
     for (int i = 0; i < 6; i++) Km[i] = s.K[9 * b + i];
     BwdWarp& W = s_warp[warp];
+    BwdSpans& SP = s_spans[LISTS ? warp : 0];   // only the list path has (and touches) it
     // Batches of 32 items are handed to the warps dynamically (balance), yet the result does not depend on who
     // ran what: inside a batch every reduction has a fixed order, and each batch leaves its 13 pose-gradient sums
     // in its own row of s_bsum, which are added up in batch order at the end (bit-reproducible results).
+    // Batch schedule (a function of n_items only): rounds of kBwdWarps full batches, then the remainder split
+    // evenly into kBwdWarps smaller batches, so that the last round keeps every warp busy instead of leaving most
+    // of them waiting at the final barrier.
+#if DH_EVEN_LAST
+    const int full_batches = (n_items / (32 * kBwdWarps)) * kBwdWarps;
+#else
+    const int full_batches = n_items / 32;
+#endif
+    const int rem_items = n_items - 32 * full_batches;
+    const int last_size = DH_EVEN_LAST ? (rem_items + kBwdWarps - 1) / kBwdWarps : 32;
+    const int n_batches = full_batches + (rem_items ? (rem_items + last_size - 1) / last_size : 0);
     for (;;) {
         int batch = 0;
         if (lane == 0) batch = atomicAdd(&s_next_batch, 1);
         batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch * 32 >= n_items) break;
+        if (batch >= n_batches) break;
+        const int bstart = batch < full_batches ? 32 * batch : 32 * full_batches + (batch - full_batches) * last_size;
+        const int bsize = batch < full_batches ? 32 : min(last_size, n_items - bstart);
         float acc[13];
 #pragma unroll
         for (int i = 0; i < 13; i++) acc[i] = 0.0f;
-        const bool have = batch * 32 + lane < n_items;
+        const bool have = lane < bsize;
         float px[3], py[3];
         int ids[3] = {0, 0, 0};
         if (have) {
-            const uint32_t it = s_items[batch * 32 + lane];
+            const uint32_t it = s_items[bstart + lane];
             const int fn = f0 + (int)(it & 0x7FFFu) + ((it >> 15) ? s.F : 0);
             FaceSetup fs;
             load_face(P, s.faces, fn, s.F, fs, ids);
@@ -1013,31 +1065,38 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         int n_tasks = 0;
         int span_id = have ? 0 : 6, d0 = 0;
         Span sp;
+        sp.d0_to = -1;
         if (have) {
-            span_setup(px, py, 0, 0, is, sp);
-            d0 = sp.d0_from;
+            if (LISTS) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    Span t;
+                    span_setup(px, py, k >> 1, k & 1, is, t);
+                    SP.slope[k][lane] = t.slope;
+                    SP.rng[k][lane] = (uint32_t)t.d0_from | ((uint32_t)max(t.d0_to, 0) << 10) |
+                                      ((0 < t.direction) ? (1u << 20) : 0u) | ((t.d0_to < t.d0_from) ? (1u << 21) : 0u);
+                    if (k == 0) { sp = t; d0 = t.d0_from; }
+                }
+            } else {
+                span_setup(px, py, 0, 0, is, sp);
+                d0 = sp.d0_from;
+            }
         }
         while (__any_sync(0xffffffffu, span_id < 6)) {
             bool t_out = false, t_in = false;
             uint32_t tw = 0;
             float tcross = 0.0f;
             if (span_id < 6) {
-                if (d0 > sp.d0_to) {
-                    span_id++;
-                    if (span_id < 6) {
-                        span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
-                        d0 = sp.d0_from;
-                    }
-                } else {
+                if (d0 <= sp.d0_to) {
                     const int axis = span_id & 1;
                     float d1_cross;
                     int d1_in, d1_out;
                     if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) {
-                        int from, to;
-                        out_scan_range(sp.direction, d1_out, is, &from, &to);
-                        const int lo = (axis == 0) ? m.col_lo[d0] : m.row_lo[d0];
-                        const int hi = (axis == 0) ? m.col_hi[d0] : m.row_hi[d0];
-                        t_out = max(from, lo) <= min(to, hi);
+                        // an out scan can contribute iff the line has a wanted pixel at or beyond d1_out in the scan
+                        // direction: one compare against the line's last (direction +) or first (direction -) one
+                        const bool dpos = 0 < sp.direction;
+                        const int bound = s_rng[(axis ? 0 : 2) + (dpos ? 1 : 0)][d0];
+                        t_out = dpos ? (d1_out <= bound) : (bound <= d1_out);
 #if DH_PREFETCH_OWNER
                         if (t_out) {  // the ownership test of phase 2 reads this pixel of the face-index map
                             const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
@@ -1045,37 +1104,53 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                         }
 #endif
                         const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
-                        t_in = !alpha_at(m, r_out, c_out);
+                        t_in = !((s_alpha[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u);
                         tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
                              ((uint32_t)d0 << 9);
                         tcross = d1_cross;
                     }
                     d0++;
                 }
+                if (d0 > sp.d0_to) {  // next span of this lane's face (its set-up was done at full lanes above)
+                    span_id++;
+                    if (span_id < 6) {
+                        if (LISTS) {
+                            const int e0 = span_id >> 1, ax = span_id & 1;
+                            const uint32_t rg = SP.rng[span_id][lane];
+                            sp.slope = SP.slope[span_id][lane];
+                            sp.p00 = ax ? W.py[e0][lane] : W.px[e0][lane];
+                            sp.p01 = ax ? W.px[e0][lane] : W.py[e0][lane];
+                            sp.direction = (rg >> 20) & 1u ? 1 : -1;
+                            d0 = (int)(rg & 1023u);
+                            sp.d0_to = (rg >> 21) & 1u ? -1 : (int)((rg >> 10) & 1023u);
+                        } else {
+                            span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
+                            d0 = sp.d0_from;
+                        }
+                    }
+                }
             }
             const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
             if (t_out) {
                 const int q = n_tasks + __popc(mo & lt_mask);
-                W.tasks[q] = tw;
-                W.tcross[q] = tcross;
+                W.tq[q] = make_uint2(tw, __float_as_uint(tcross));
             }
             if (t_in) {
                 const int q = n_tasks + __popc(mo) + __popc(mi & lt_mask);
-                W.tasks[q] = tw | (1u << 8);
-                W.tcross[q] = tcross;
+                W.tq[q] = make_uint2(tw | (1u << 8), __float_as_uint(tcross));
             }
             n_tasks += __popc(mo) + __popc(mi);
             __syncwarp();
             while (n_tasks >= 32) {
                 n_tasks -= 32;
-                const float dc = W.tcross[n_tasks + lane];
-                const uint32_t cont = bwd_task<FUSED, LISTS>(W.tasks[n_tasks + lane], dc, W, m, nl, s.eps, fpscale, gcoef);
+                const uint2 tk = W.tq[n_tasks + lane];
+                const float dc = __uint_as_float(tk.y);
+                const uint32_t cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef);
                 __syncwarp();
                 const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
                 if (cont) {
                     const int q = n_tasks + __popc(mc & lt_mask);
-                    W.tasks[q] = cont;
-                    W.tcross[q] = dc;
+                    W.tq[q] = make_uint2(cont, __float_as_uint(dc));
                 }
                 n_tasks += __popc(mc);
                 __syncwarp();
@@ -1087,15 +1162,15 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             uint32_t cont = 0;
             float dc = 0.0f;
             if (lane < nt) {
-                dc = W.tcross[n_tasks + lane];
-                cont = bwd_task<FUSED, LISTS>(W.tasks[n_tasks + lane], dc, W, m, nl, s.eps, fpscale, gcoef);
+                const uint2 tk = W.tq[n_tasks + lane];
+                dc = __uint_as_float(tk.y);
+                cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef);
             }
             __syncwarp();
             const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
             if (cont) {
                 const int q = n_tasks + __popc(mc & lt_mask);
-                W.tasks[q] = cont;
-                W.tcross[q] = dc;
+                W.tq[q] = make_uint2(cont, __float_as_uint(dc));
             }
             n_tasks += __popc(mc);
             __syncwarp();
@@ -1146,7 +1221,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         if (tid < 16) {
             float t = 0.0f;
             if (tid < 13)
-                for (int k = 0; k * 32 < n_items; k++) t += s_bsum[k][tid];
+                for (int k = 0; k < n_batches; k++) t += s_bsum[k][tid];
             partials[((size_t)b * nchunks + chunk) * 16 + tid] = t;
         }
     }
@@ -1348,11 +1423,12 @@ int neg_list_cap() { return g_neg_list_cap < kNLCap ? (g_neg_list_cap < 0 ? 0 : 
 
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(2 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
+    return kBwdWarps * sizeof(BwdWarp) + (size_t)(2 * is * (is / 32) + s.S * ((s.S + 31) / 32)) * sizeof(uint32_t);
 }
 size_t bwd_lists_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(is * (is / 32)) * sizeof(uint32_t) + (DH_LISTS_GLOBAL ? 0 : (size_t)2 * kNLAxis * sizeof(uint16_t));
+    return kBwdWarps * (sizeof(BwdWarp) + sizeof(BwdSpans)) + (size_t)(is * (is / 32)) * sizeof(uint32_t) +
+           (DH_LISTS_GLOBAL ? 0 : (size_t)2 * kNLAxis * sizeof(uint16_t));
 }
 size_t neg_maps_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
