@@ -23,11 +23,21 @@ namespace {
 
 using namespace dh;
 
-constexpr int kSH = 16;            // strip height in raster rows
+#ifndef DH_STRIP_ROWS
+#define DH_STRIP_ROWS 16
+#endif
+constexpr int kSH = DH_STRIP_ROWS;  // strip height in raster rows (even: a strip holds whole 2x2 pooling cells)
 constexpr int kThreads = 256;      // CTA size of the backward / elementwise kernels
 #ifndef DH_RASTER_THREADS
 #define DH_RASTER_THREADS 384
 #endif
+#ifndef DH_RASTER_EVEN
+#define DH_RASTER_EVEN 1
+#endif
+#ifndef DH_DEFER_DEPTH
+#define DH_DEFER_DEPTH 0   // 1: deferred depth (see raster_hit): ~77k -> ~200 exact depth evaluations per frame and 12 %
+#endif                     // fewer instructions, bit-exact, but not faster on B200 (1.09 vs 1.08 ms): off by default
+constexpr int kRasterWarps = DH_RASTER_THREADS / 32;
 constexpr int kRasterThreads = DH_RASTER_THREADS;  // 12 warps x 2 CTAs/SM: the 64 KB z-buffer strip caps CTAs/SM at 2
 constexpr int kOwnedSmemWords = 1024;
 constexpr int kMaxIS = 512;        // largest raster resolution (bitmaps + z-buffer strip must fit shared memory)
@@ -214,16 +224,53 @@ __device__ __forceinline__ void load_face(const float4* __restrict__ P, const in
     }
 }
 
-// Depth of one queued hit and the z-buffer update.  ent = slot | x << 5 | local_row << 15.
-// setup rows: inv[9], z[3], zcull (nearest vertex depth * (1 - 1e-5), or -inf when the bound does not apply).
+// Exact key of face g at pixel (xi, yi), recomputed from global memory: used when a hit meets a deferred z-buffer
+// entry (below).  Rare, kept out of line.
+__device__ __noinline__ unsigned long long exact_key_of(const float4* __restrict__ P, const int32_t* __restrict__ faces,
+                                                        int g, int F, int is, int xi, int yi, float near, float far) {
+    FaceSetup fg;
+    int ids[3];
+    load_face(P, faces, g, F, fg, ids);
+    face_inverse(fg, is);
+    float zg;
+    if (!pixel_depth(fg, xi, yi, near, far, &zg)) return DH_ZKEY_EMPTY;
+    return zkey(zg, g);
+}
+
+// One queued hit and the z-buffer update.  ent = slot | x << 5 | local_row << 15.
+// setup rows: inv[9], z[3], zlo, zhi.  zlo = nearest vertex depth * (1 - 1e-5) (or -inf when that bound does not
+// apply), zhi = farthest vertex depth * (1 + 1e-5) when the face may be DEFERRED, else 0.
+//
+// The face-index map only needs the depth ORDER.  The depth of a face at a pixel (a clamped, normalised harmonic
+// blend of its vertex depths) lies in [zlo, zhi], so:
+//   * a hit whose zlo is above the depth field of the cell loses without any arithmetic (the pre-test);
+//   * the first hit on an empty pixel is stored "deferred": depth field = zhi, bit 31 of the face word set, no
+//     division at all.  For a closed mesh rasterised near side first that is almost every covered pixel: the far
+//     side then fails the pre-test against zhi;
+//   * only a hit that can neither lose nor defer (overlapping depth intervals: silhouette folds, shared edges)
+//     computes its exact depth, resolves a deferred occupant exactly as well, and installs the smaller exact key.
+// Every losing face is strictly farther than the entry that beat it and the depth field only ever decreases, so
+// the final face number is the exact arg-min (lowest face number on exact ties) whatever the order of the hits.
+constexpr uint32_t kDeferBit = 0x80000000u;
 __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32], const int* fns,
-                                           unsigned long long* zbuf, int is, int row0, float near, float far) {
+                                           unsigned long long* zbuf, int is, int row0, float near, float far,
+                                           const float4* __restrict__ P, const int32_t* __restrict__ faces, int F) {
     const int slot = ent & 31, xi = (ent >> 5) & 1023, yl = ent >> 15;
     unsigned long long* cell = zbuf + yl * is + xi;
-    const unsigned long long cur = *cell;
-    // the face cannot be nearer than its nearest vertex (zp is a clamped, normalised harmonic blend of the three
-    // vertex depths, >= zmin * (1 - 1e-6)): skip the divisions if the pixel already holds something nearer
-    if (__uint_as_float((uint32_t)(cur >> 32)) < setup[12][slot]) return;
+    unsigned long long cur = *cell;
+    const float zlo = setup[12][slot];
+    if (__uint_as_float((uint32_t)(cur >> 32)) < zlo) return;   // an empty cell (NaN bits) never compares below
+    const int fn = fns[slot];
+#if DH_DEFER_DEPTH
+    const float zhi = setup[13][slot];
+    if (cur == DH_ZKEY_EMPTY && zhi > 0.0f) {
+        const unsigned long long want = ((unsigned long long)__float_as_uint(zhi) << 32) | ((uint32_t)fn | kDeferBit);
+        const unsigned long long old = atomicCAS(cell, DH_ZKEY_EMPTY, want);
+        if (old == DH_ZKEY_EMPTY) return;
+        cur = old;
+        if (__uint_as_float((uint32_t)(cur >> 32)) < zlo) return;
+    }
+#endif
     FaceSetup f;
 #pragma unroll
     for (int k = 0; k < 9; k++) f.inv[k] = setup[k][slot];
@@ -231,21 +278,40 @@ __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32
     for (int k = 0; k < 3; k++) f.z[k] = setup[9 + k][slot];
     float zp;
     if (!pixel_depth(f, xi, row0 + yl, near, far, &zp)) return;
-    const unsigned long long key = zkey(zp, fns[slot]);
+    const unsigned long long key = zkey(zp, fn);
+#if DH_DEFER_DEPTH
+    for (;;) {
+        unsigned long long best = key;
+        if (cur != DH_ZKEY_EMPTY && ((uint32_t)cur & kDeferBit)) {
+            const unsigned long long kg = exact_key_of(P, faces, (int)((uint32_t)cur & ~kDeferBit), F, is, xi,
+                                                       row0 + yl, near, far);
+            if (kg < best) best = kg;
+        } else if (cur <= key) {
+            return;
+        }
+        const unsigned long long old = atomicCAS(cell, cur, best);
+        if (old == cur) return;
+        cur = old;
+    }
+#else
     if (key < cur) atomicMin(cell, key);
+#endif
 }
 
 // FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
 // else : epilogue writes the pooled, flipped silhouette `rend` (the renderer's return value).
+#ifndef DH_RASTER_MIN_CTAS
+#define DH_RASTER_MIN_CTAS 2
+#endif
 template <bool FUSED>
-__global__ void __launch_bounds__(kRasterThreads)
+__global__ void __launch_bounds__(kRasterThreads, DH_RASTER_MIN_CTAS)
 k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float* __restrict__ rend,
          int32_t* __restrict__ loss_counts) {
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
     __shared__ uint32_t abits[kSH][kMaxIS / 32];
     __shared__ int red[3][kRasterThreads / 32];
     __shared__ float s_ndc[kMaxIS];                    // NDC coordinate of every pixel centre
-    __shared__ float s_setup[kRasterThreads / 32][13][32];   // per warp: inv[9], z[3], zcull of the batch's faces
+    __shared__ float s_setup[kRasterThreads / 32][14][32];   // per warp: inv[9], z[3], zlo, zhi of the batch's faces
     __shared__ float s_geo[kRasterThreads / 32][6][32];      // per warp: NDC x[3], y[3]
     __shared__ uint32_t s_box[kRasterThreads / 32][32];      // x_lo | x_hi << 10 | local first row << 20
     __shared__ int s_start[kRasterThreads / 32][32];         // first row-item of every face of the batch
@@ -275,6 +341,22 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // the target-mask cells this thread scores in the epilogue, fetched now so that their latency hides behind the
+    // rasterisation (same cell order as epilogue 2)
+    constexpr int kMaskPre = 6;
+    unsigned long long m_pre = 0ull;   // one byte per epilogue iteration
+    if (FUSED) {
+        const int S_ = s.S, wprp_ = (S_ + 31) >> 5, rows_ = s.aa ? kSH / 2 : kSH;
+#pragma unroll
+        for (int k = 0; k < kMaskPre; k++) {
+            const int seg = warp + k * kRasterWarps;
+            if (seg < rows_ * wprp_) {
+                const int ly = seg / wprp_, x = ((seg - ly * wprp_) << 5) + lane;
+                const int yo = s.aa ? ((is - 1 - (row0 + 2 * ly)) >> 1) : (is - 1 - (row0 + ly));
+                m_pre |= (unsigned long long)(uint8_t)mask_tri[((size_t)b * S_ + yo) * S_ + x] << (8 * k);
+            }
+        }
+    }
     // Two passes (given windings, then reversed windings), warp-synchronous batches of 32 bin entries handed out
     // dynamically.  Per batch: (1) lane = face: set-up; (2) lane = (face, row): analytic x-span of the row, then
     // the exact edge tests pixel by pixel, survivors compacted into a per-warp queue; (3) whenever 32 hits are
@@ -285,14 +367,27 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     for (int pass_i = 0; pass_i < 2; pass_i++) {
         const int pass = pass_i ^ DH_PASS_ORDER;
         const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
+        // batch schedule: rounds of one 32-face batch per warp, then the remainder split evenly over the warps (a
+        // strip holds only a few hundred faces per pass: whole batches would leave most warps idle in the last
+        // round).  The z-buffer minimum does not depend on who rasterises what.
+#if DH_RASTER_EVEN
+        const int full = (count / (32 * kRasterWarps)) * kRasterWarps;
+        const int rem = count - 32 * full;
+        const int last = (rem + kRasterWarps - 1) / kRasterWarps;
+#else
+        const int full = count / 32, rem = count - 32 * full, last = 32;
+#endif
+        const int nbatch = full + (rem ? (rem + last - 1) / last : 0);
         for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_next[pass], 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= count) break;
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&s_next[pass], 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= nbatch) break;
+            const int base = k < full ? 32 * k : 32 * full + (k - full) * last;
+            const int bsize = k < full ? 32 : min(last, count - base);
             const int e = base + lane;
             int nrows = 0;
-            if (e < count) {
+            if (lane < bsize) {
                 const int fn = pass ? bin[2 * s.F - 1 - e] : bin[e];
                 FaceSetup fs;
                 int ids[3];
@@ -310,7 +405,18 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                         s_geo[warp][3 + k][lane] = fs.y[k];
                     }
                     const float zmin = fminf(fs.z[0], fminf(fs.z[1], fs.z[2]));
-                    s_setup[warp][12][lane] = (zmin > 0.0f) ? zmin * (1.0f - 1e-5f) : -3.0e38f;
+                    const float zmax = fmaxf(fs.z[0], fmaxf(fs.z[1], fs.z[2]));
+                    const float zlo = (zmin > 0.0f) ? zmin * (1.0f - 1e-5f) : -3.0e38f;
+                    const float zhi = zmax * (1.0f + 1e-5f);
+                    // deferrable: depth bounds valid and inside (near, far), barycentric set-up well conditioned (the
+                    // exact path leaves a pixel unrecorded when its weights degenerate to NaN)
+                    bool defer = zmin > 0.0f && s.near_ < zlo && zhi < s.far_;
+#pragma unroll
+                    for (int k = 0; k < 3; k++)   // NaN fails every comparison
+                        defer = defer && fabsf(fs.inv[3 * k]) <= 1.0e3f && fabsf(fs.inv[3 * k + 1]) <= 1.0e3f &&
+                                fabsf(fs.inv[3 * k + 2]) <= 1.0e6f;
+                    s_setup[warp][12][lane] = zlo;
+                    s_setup[warp][13][lane] = defer ? zhi : 0.0f;
                     s_box[warp][lane] = (uint32_t)fs.x_lo | ((uint32_t)fs.x_hi << 10) | ((uint32_t)(r_lo - row0) << 20);
                     s_fn[warp][lane] = fn;
                 }
@@ -364,12 +470,14 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                     if (qn >= 32) {
                         qn -= 32;
                         raster_hit(s_queue[warp][qn + lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_,
-                                   s.far_);
+                                   s.far_, P, s.faces, s.F);
                         __syncwarp();
                     }
                 }
             }
-            if (lane < qn) raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_);
+            if (lane < qn)
+                raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_, P, s.faces,
+                           s.F);
             __syncwarp();
         }
         // no barrier between the passes: a warp that runs ahead into the reversed windings only makes the depth
@@ -381,23 +489,24 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int wpr = is >> 5;
     int32_t* fidx = s.fidx + (size_t)b * is * is + (size_t)row0 * is;
     uint32_t* abits_g = s.alpha_bits + ((size_t)b * is + row0) * wpr;
-    for (int r = 0; r < kSH; r++) {
-        for (int c = tid; c < is; c += kRasterThreads) {
-            const int i = r * is + c;
-            const unsigned long long key = zbuf[i];
-            const bool cov = key != DH_ZKEY_EMPTY;
-            const int fn = cov ? (int32_t)(uint32_t)(key & 0xFFFFFFFFull) : -1;
-            fidx[i] = fn;
-            // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the
-            // same face along a row set the bit once
-            const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
-            if (cov && ((tid & 31) == 0 || fn_left != fn))
-                atomicOr(owned_smem ? &s_owned[fn >> 5] : &g_owned[fn >> 5], 1u << (fn & 31));
-            const uint32_t word = __ballot_sync(0xffffffffu, cov);
-            if ((tid & 31) == 0) {
-                abits[r][c >> 5] = word;
-                abits_g[r * wpr + (c >> 5)] = word;
-            }
+    const int wpr_sh = 31 - __clz(wpr);
+    const bool wpr_pow2 = (wpr & (wpr - 1)) == 0;
+    for (int seg = warp; seg < kSH * wpr; seg += kRasterWarps) {   // one warp = 32 consecutive pixels of a row
+        const int r = wpr_pow2 ? (seg >> wpr_sh) : seg / wpr, cw = seg - r * wpr;
+        const int i = r * is + (cw << 5) + lane;
+        const unsigned long long key = zbuf[i];
+        const bool cov = key != DH_ZKEY_EMPTY;
+        const int fn = cov ? (int32_t)((uint32_t)key & ~kDeferBit) : -1;
+        fidx[i] = fn;
+        // face-owns-a-pixel bitmap (lets the backward skip faces that are completely hidden); runs of the
+        // same face along a row set the bit once
+        const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
+        if (cov && (lane == 0 || fn_left != fn))
+            atomicOr(owned_smem ? &s_owned[fn >> 5] : &g_owned[fn >> 5], 1u << (fn & 31));
+        const uint32_t word = __ballot_sync(0xffffffffu, cov);
+        if (lane == 0) {
+            abits[r][cw] = word;
+            abits_g[r * wpr + cw] = word;
         }
     }
     __syncthreads();
@@ -411,8 +520,11 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const int cell_rows = s.aa ? kSH / 2 : kSH;
     const int wprp = (S + 31) >> 5;
     int sse = 0, inter = 0, uni = 0;
-    for (int ci = tid; ci < cell_rows * S; ci += kRasterThreads) {
-        const int ly = ci / S, x = ci - ly * S;
+    const int wprp_sh = 31 - __clz(wprp);
+    const bool wprp_pow2 = (wprp & (wprp - 1)) == 0;
+    int mi = 0;
+    for (int seg = warp; seg < cell_rows * wprp; seg += kRasterWarps, mi++) {   // one warp = 32 consecutive cells
+        const int ly = wprp_pow2 ? (seg >> wprp_sh) : seg / wprp, x = ((seg - ly * wprp) << 5) + lane;
         int pop, yo;
         if (s.aa) {
             const int r = 2 * ly;
@@ -426,7 +538,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         }
         const size_t o = ((size_t)b * S + yo) * S + x;
         if (FUSED) {
-            const int m = mask_tri[o];
+            const int m = (mi < kMaskPre) ? (int)(int8_t)(uint8_t)(m_pre >> (8 * mi)) : (int)mask_tri[o];
             const int keep = m >= 0, ref = m > 0;
             const int k = keep ? pop - 4 * ref : 0;  // 4 * (image - ref)
             sse += k * k;
@@ -435,7 +547,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             s.gpool[o] = gcoef * ((float)k * 0.5f);
             const uint32_t pw = __ballot_sync(0xffffffffu, k > 0);
             const uint32_t nw = __ballot_sync(0xffffffffu, k < 0);
-            if ((tid & 31) == 0) {
+            if (lane == 0) {
                 s.pos_pool[((size_t)b * S + yo) * wprp + (x >> 5)] = pw;
                 s.neg_pool[((size_t)b * S + yo) * wprp + (x >> 5)] = nw;
             }
@@ -701,7 +813,6 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 struct NegLists {   // both axes behind one base pointer (indexing an array of pointers by axis would go to local memory)
     const uint16_t* base;
     __device__ __forceinline__ const uint16_t* start(int axis) const { return base + axis * kNLAxis; }
-    __device__ __forceinline__ const uint16_t* ent(int axis) const { return base + axis * kNLAxis + kNLStart; }
 };
 template <bool FUSED, bool LISTS>
 __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m,
@@ -871,7 +982,9 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     uint32_t* s_alpha = smw + kBwdWarps * ((sizeof(BwdWarp) + (LISTS ? sizeof(BwdSpans) : 0)) / sizeof(uint32_t));
     uint32_t* s_negT = s_alpha + is * wpr;                  // bitmap path
     uint32_t* s_negp = s_negT + is * wpr;
+#if !DH_LISTS_GLOBAL
     uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha + is * wpr);  // list path: 2 x (starts, entries)
+#endif
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;

@@ -3,6 +3,7 @@
 // serial loops that mirror the kernels' glue (strip binning, shared-memory z-buffer, bitmap staging).  The CPU
 // test-suite (-m "not gpu") compares it with the oracle so that logic errors are caught without a GPU.
 // The product never loads this library; the GPU tests exercise the real kernels through the C ABI.
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -118,6 +119,51 @@ void emu_raster(const float* proj, const int32_t* faces, int B, int V, int F, in
             }
         }
     }
+}
+
+// Hit statistics of the rasteriser with deferred depth, faces taken in the kernel's pass order (given windings,
+// then reversed), sequentially (tools/raster_stats.py).  out[8]: bin entries pass 0 / pass 1, hits, pre-test
+// rejects, deferred installs, exact evaluations, deferred resolutions, not deferrable faces.
+void emu_raster_stats(const float* proj, const int32_t* faces, int V, int F, int is, float near, float far,
+                      int order, long long* out) {
+    std::vector<float> depth((size_t)is * is, 0.f);
+    std::vector<int> state((size_t)is * is, 0);  // 0 empty, 1 deferred, 2 exact
+    long long ent[2] = {0, 0}, hits = 0, rej = 0, defer = 0, exact = 0, resolve = 0, nodefer = 0;
+    for (int pi = 0; pi < 2; pi++) {
+        const int pass = pi ^ order;
+        for (int f = 0; f < F; f++) {
+            const int fn = f + pass * F;
+            FaceSetup fs;
+            int ids[3];
+            load_face(proj, faces, fn, F, fs, ids);
+            if (!face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) continue;
+            ent[pass]++;
+            face_inverse(fs, is);
+            const float zmin = fminf(fs.z[0], fminf(fs.z[1], fs.z[2])), zmax = fmaxf(fs.z[0], fmaxf(fs.z[1], fs.z[2]));
+            const float zlo = zmin > 0.f ? zmin * (1.0f - 1e-5f) : -3.0e38f, zhi = zmax * (1.0f + 1e-5f);
+            bool df = zmin > 0.f && near < zlo && zhi < far;
+            for (int k = 0; k < 3; k++)
+                df = df && fabsf(fs.inv[3 * k]) <= 1e3f && fabsf(fs.inv[3 * k + 1]) <= 1e3f && fabsf(fs.inv[3 * k + 2]) <= 1e6f;
+            if (!df) nodefer++;
+            for (int yi = fs.y_lo; yi <= fs.y_hi; yi++) {
+                const float yp = pix_to_ndc(yi, is);
+                for (int xi = fs.x_lo; xi <= fs.x_hi; xi++) {
+                    if (!pixel_inside(fs, pix_to_ndc(xi, is), yp)) continue;
+                    hits++;
+                    const size_t c = (size_t)yi * is + xi;
+                    if (state[c] != 0 && depth[c] < zlo) { rej++; continue; }
+                    if (state[c] == 0 && df) { state[c] = 1; depth[c] = zhi; defer++; continue; }
+                    float zp;
+                    exact++;
+                    if (!pixel_depth(fs, xi, yi, near, far, &zp)) continue;
+                    if (state[c] == 1) { resolve++; state[c] = 2; depth[c] = fminf(depth[c], zp); }
+                    else if (state[c] == 0 || zp < depth[c]) { state[c] = 2; depth[c] = zp; }
+                }
+            }
+        }
+    }
+    long long o[8] = {ent[0], ent[1], hits, rej, defer, exact, resolve, nodefer};
+    memcpy(out, o, sizeof(o));
 }
 
 // k_raster<true> epilogue 2 for whole frames: integer loss sums, dL/drend and its sign bitmaps
