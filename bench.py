@@ -411,7 +411,27 @@ def run_dino(args):
         "planted_match_rank0": ok, "gpu_launches": 3 * args.steps}))
 
 
+def _quiet_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, tqdm) to stderr; the JSON line is written
+    to the real stdout at the end, so that stdout carries exactly one line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    import builtins
+    _print = builtins.print
+
+    def emit(*a, **k):
+        if k.get("file") is None:
+            k["file"] = out
+            k["flush"] = True
+        _print(*a, **k)
+    return emit
+
+
 def main():
+    global print
+    print = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)     # configs/custom_shoes.yaml:14 joint_num_iterations

@@ -34,6 +34,9 @@ constexpr int kThreads = 256;      // CTA size of the backward / elementwise ker
 #ifndef DH_RASTER_EVEN
 #define DH_RASTER_EVEN 1
 #endif
+#ifndef DH_TILE_Z
+#define DH_TILE_Z 1
+#endif
 #ifndef DH_DEFER_DEPTH
 #define DH_DEFER_DEPTH 0   // 1: deferred depth (see raster_hit): ~77k -> ~200 exact depth evaluations per frame and 12 %
 #endif                     // fewer instructions, bit-exact, but not faster on B200 (1.09 vs 1.08 ms): off by default
@@ -224,6 +227,7 @@ __device__ __forceinline__ void load_face(const float4* __restrict__ P, const in
     }
 }
 
+#if DH_DEFER_DEPTH
 // Exact key of face g at pixel (xi, yi), recomputed from global memory: used when a hit meets a deferred z-buffer
 // entry (below).  Rare, kept out of line.
 __device__ __noinline__ unsigned long long exact_key_of(const float4* __restrict__ P, const int32_t* __restrict__ faces,
@@ -236,6 +240,7 @@ __device__ __noinline__ unsigned long long exact_key_of(const float4* __restrict
     if (!pixel_depth(fg, xi, yi, near, far, &zg)) return DH_ZKEY_EMPTY;
     return zkey(zg, g);
 }
+#endif
 
 // One queued hit and the z-buffer update.  ent = slot | x << 5 | local_row << 15.
 // setup rows: inv[9], z[3], zlo, zhi.  zlo = nearest vertex depth * (1 - 1e-5) (or -inf when that bound does not
@@ -318,6 +323,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     __shared__ int s_fn[kRasterThreads / 32][32];
     __shared__ uint32_t s_queue[kRasterThreads / 32][64];    // pending (lane slot, x, local row) hits
     __shared__ int s_next[2];
+    __shared__ uint32_t s_tilez[kMaxIS / 16];
     const int is = raster_size(s);
     const int nstrips = is / kSH;
     const int strip = blockIdx.x, b = blockIdx.y;
@@ -367,6 +373,26 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     for (int pass_i = 0; pass_i < 2; pass_i++) {
         const int pass = pass_i ^ DH_PASS_ORDER;
         const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
+#if DH_TILE_Z
+        if (pass_i == 1) {
+            // Between the passes: farthest recorded depth of every 16-column tile of the strip (an empty pixel
+            // makes it +inf).  A second-pass face whose nearest vertex lies behind that bound in every tile its
+            // bounding box touches cannot win a pixel -- for a closed mesh that is the whole far side, which then
+            // costs a vertex fetch and a bounding box instead of spans, edge tests and per-pixel depth pre-tests.
+            __syncthreads();
+            for (int t = warp; t < (is >> 4); t += kRasterWarps) {
+                uint32_t m = 0u;
+#pragma unroll
+                for (int j = 0; j < (kSH * 16) / 32; j++) {
+                    const int q = j * 32 + lane;   // pixel q of the tile: row q / 16, column q % 16
+                    m = max(m, (uint32_t)(zbuf[(q >> 4) * is + (t << 4) + (q & 15)] >> 32));
+                }
+                m = __reduce_max_sync(0xffffffffu, m);
+                if (lane == 0) s_tilez[t] = m;
+            }
+            __syncthreads();
+        }
+#endif
         // batch schedule: rounds of one 32-face batch per warp, then the remainder split evenly over the warps (a
         // strip holds only a few hundred faces per pass: whole batches would leave most warps idle in the last
         // round).  The z-buffer minimum does not depend on who rasterises what.
@@ -392,7 +418,19 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                 FaceSetup fs;
                 int ids[3];
                 load_face(P, s.faces, fn, s.F, fs, ids);
-                if (face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi)) {
+                bool live = face_bbox(fs.x, fs.y, is, &fs.x_lo, &fs.x_hi, &fs.y_lo, &fs.y_hi);
+#if DH_TILE_Z
+                if (live && pass_i == 1) {
+                    const float zn = fminf(fs.z[0], fminf(fs.z[1], fs.z[2]));
+                    if (zn > 0.0f) {   // same bound as the per-pixel pre-test; positive floats order like their bits
+                        const uint32_t zb = __float_as_uint(zn * (1.0f - 1e-5f));
+                        bool hidden = true;
+                        for (int t = fs.x_lo >> 4; t <= (fs.x_hi >> 4); t++) hidden = hidden && s_tilez[t] < zb;
+                        live = !hidden;
+                    }
+                }
+#endif
+                if (live) {
                     face_inverse(fs, is);
                     const int r_lo = max(fs.y_lo, row0), r_hi = min(fs.y_hi, row0 + kSH - 1);
                     nrows = max(r_hi - r_lo + 1, 0);
@@ -711,7 +749,10 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
     __shared__ int s_wsum[kNegThreads / 32];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
+    // grid (B, 2): block y = 1 builds the row side (row ranges, row lists), y = 0 the column side (transposed bitmap,
+    // column lists); a (B, 1) grid does both.
     const int b = blockIdx.x, tid = threadIdx.x;
+    const int axis_lo = gridDim.y == 2 ? (int)blockIdx.y : 0, axis_hi = gridDim.y == 2 ? (int)blockIdx.y : 1;
     const int warp = tid >> 5, lane = tid & 31;
     uint32_t* words = nm_words;
     uint32_t* wordsT = nm_words + is * wpr;
@@ -722,6 +763,7 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
         words[i] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, r, w);
     }
     __syncthreads();
+    if (axis_lo == 0)
     for (int blk = warp; blk < wpr * wpr; blk += kNegThreads / 32) {
         const int rb = blk / wpr, cb = blk - rb * wpr;
         const uint32_t word = words[(32 * rb + lane) * wpr + cb];
@@ -735,8 +777,9 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
     }
     __syncthreads();
     uint32_t* gT = s.negT + (size_t)b * is * wpr;
-    for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[i];
-    for (int axis = 0; axis < 2; axis++) {
+    if (axis_lo == 0)
+        for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[i];
+    for (int axis = axis_lo; axis <= axis_hi; axis++) {
         // axis 0: lines are columns (words of wordsT), axis 1: lines are rows
         const uint32_t* W = axis ? words : wordsT;
         int cnt = 0, lo = is, hi = -1;
@@ -1605,7 +1648,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
         if (mode != 2) {
             rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
             if (rc) return rc;
-            k_neg_maps<<<B, kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
+            k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
             DH_LAUNCH_OK("k_neg_maps");
             const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
             rc = set_smem(k_backward<true, true>, sl);
@@ -1726,7 +1769,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     t.gpool = const_cast<float*>(grad_rend);
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(t));
     if (rc) return rc;
-    k_neg_maps<<<t.B, kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0, 0);
+    k_neg_maps<<<dim3(t.B, 2), kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0, 0);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sb = bwd_smem_bytes(t);
     rc = set_smem(k_backward<false, false>, sb);
