@@ -332,7 +332,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"custom_shoes-shaped joint pose optimisation, {Bl} frames per GPU "
-                                   f"({B_total} total) 480x640, 5k-vertex mesh (V={V}, F={F}), 256x256 ROI rendered "
+                                   f"({B_total} total) {H}x{W}, {MESH} mesh (V={V}, F={F}), 256x256 ROI rendered "
                                    f"512x512 + 2x2 pool, {C} correspondences per frame, lw_sil 1 / lw_smooth 10"
                                    + (f" / lw_corr {LW_CORR}" if C > 0 else "") + ", lr 1e-4 (BASELINE configs[1])",
                        "frames_per_gpu": Bl, "frames_total": B_total, "correspondences_per_frame": C,
@@ -341,7 +341,7 @@ def run_ours(args):
                        "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": True},
             "roofline": roofline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": (8 + (1 if C > 0 else 0)) * args.steps,
+            "gpu_launches": (9 + (1 if C > 0 else 0)) * args.steps,
             "loss_first_last": [hist["loss"][0], hist["loss"][-1]],
             "iou_first_last": [hist["iou_object"][0], hist["iou_object"][-1]],
         }
@@ -441,9 +441,15 @@ def main():
     ap.add_argument("--corr", type=int, default=10000,
                     help="correspondences per frame (builder-defined reprojection term; 0 = the reference's two terms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mesh", default=MESH, choices=["uv50x100", "uv100x200"],
+                    help="uv100x200 = the 20k-vertex mesh of BASELINE configs[2]")
+    ap.add_argument("--camera", default=f"{H}x{W}", help="full-frame camera HxW (configs[2]: 1080x1920)")
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
+    global MESH, H, W
+    MESH = args.mesh
+    H, W = (int(v) for v in args.camera.split("x"))
     if args.workload == "dino":
         run_dino(args)
     elif args.impl == "reference":
