@@ -430,7 +430,7 @@ def _quiet_stdout():
 
 
 def main():
-    global print
+    global print, MESH, H, W
     print = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,7 +447,6 @@ def main():
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
-    global MESH, H, W
     MESH = args.mesh
     H, W = (int(v) for v in args.camera.split("x"))
     if args.workload == "dino":
