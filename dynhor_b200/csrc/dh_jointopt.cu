@@ -924,8 +924,11 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             const float ea = (ec.ka == 0.0f) ? inf : ((0.0f < ka2 * dirf) ? eps : -eps);
             const float eb = (ec.kb == 0.0f) ? inf : ((0.0f < kb2 * dirf) ? eps : -eps);
             if (own == fn && 0.0f < dunit && (ec.ka != 0.0f || ec.kb != 0.0f)) {
+                uint32_t e = (i != i_stop) ? E[i] : 0u;
                 while (i != i_stop) {
-                    const uint32_t e = E[i];
+                    // the next entry is fetched one iteration ahead (L1 latency behind the two reciprocals); one
+                    // entry past either end of a line is still inside the frame's list block
+                    const uint32_t e_next = E[i + step];
                     const int d1 = (int)(e & 1023u);
                     if (lim < d1 * step) { i = i_end; break; }  // past d1_out against the walking direction
                     const float x = (float)d1 - d1_cross;
@@ -936,6 +939,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
                     sa = fmaf(cf, ra, sa);
                     sb = fmaf(cf, rb, sb);
                     i += step;
+                    e = e_next;
                 }
                 if (i != i_end) cont = (t & 0x3FFFFu) | ((uint32_t)(i + 1) << 18);  // rest of the line: a later round
                 sa *= dunit;
@@ -1575,7 +1579,8 @@ size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-ow
 
 // pixels per frame the list path takes (dh_tune_set knob 0 lowers it: the tests force the bitmap path with it)
 int g_neg_list_cap = kNLCap;
-int neg_list_cap() { return g_neg_list_cap < kNLCap ? (g_neg_list_cap < 0 ? 0 : g_neg_list_cap) : kNLCap; }
+// (8 entries short of the block: the out scan's look-ahead read may touch the entry after the last one)
+int neg_list_cap() { return g_neg_list_cap < kNLCap - 8 ? (g_neg_list_cap < 0 ? 0 : g_neg_list_cap) : kNLCap - 8; }
 
 size_t bwd_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
