@@ -745,7 +745,8 @@ __device__ __forceinline__ int block_exclusive_scan_512(int v, int* s_wsum, int*
 
 __global__ void __launch_bounds__(kNegThreads)
 k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
-    extern __shared__ uint32_t nm_words[];  // [is][wpr] row-major, then [is][wpr] column-major
+    extern __shared__ uint32_t nm_words[];  // [is][wpr + 1] row-major, then [is][wpr + 1] column-major (rows padded
+                                            // by one word: a thread per line and the block transposes stay conflict-free)
     __shared__ int s_wsum[kNegThreads / 32];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
@@ -755,37 +756,38 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
     const int axis_lo = gridDim.y == 2 ? (int)blockIdx.y : 0, axis_hi = gridDim.y == 2 ? (int)blockIdx.y : 1;
     const int warp = tid >> 5, lane = tid & 31;
     uint32_t* words = nm_words;
-    uint32_t* wordsT = nm_words + is * wpr;
+    const int wps = wpr + 1;
+    uint32_t* wordsT = nm_words + is * wps;
     const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
     const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
     for (int i = tid; i < is * wpr; i += kNegThreads) {
         const int r = i / wpr, w = i - r * wpr;
-        words[i] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, r, w);
+        words[r * wps + w] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, r, w);
     }
     __syncthreads();
     if (axis_lo == 0)
     for (int blk = warp; blk < wpr * wpr; blk += kNegThreads / 32) {
         const int rb = blk / wpr, cb = blk - rb * wpr;
-        const uint32_t word = words[(32 * rb + lane) * wpr + cb];
+        const uint32_t word = words[(32 * rb + lane) * wps + cb];
         uint32_t mine = 0;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
             const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
             if (lane == j) mine = colw;
         }
-        wordsT[(32 * cb + lane) * wpr + rb] = mine;
+        wordsT[(32 * cb + lane) * wps + rb] = mine;
     }
     __syncthreads();
     uint32_t* gT = s.negT + (size_t)b * is * wpr;
     if (axis_lo == 0)
-        for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[i];
+        for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[(i / wpr) * wps + (i % wpr)];
     for (int axis = axis_lo; axis <= axis_hi; axis++) {
         // axis 0: lines are columns (words of wordsT), axis 1: lines are rows
         const uint32_t* W = axis ? words : wordsT;
         int cnt = 0, lo = is, hi = -1;
         if (tid < is) {
             for (int w = 0; w < wpr; w++) {
-                const uint32_t bits = W[tid * wpr + w];
+                const uint32_t bits = W[tid * wps + w];
                 if (bits) {
                     if (lo == is) lo = (w << 5) + ctz32(bits);
                     hi = (w << 5) + 31 - __clz((int)bits);
@@ -807,7 +809,7 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
         if (over || tid >= is) continue;
         uint16_t* E = L + kNLStart + start;
         for (int w = 0; w < wpr; w++) {
-            uint32_t bits = W[tid * wpr + w];
+            uint32_t bits = W[tid * wps + w];
             while (bits) {
                 const int d1 = (w << 5) + ctz32(bits);
                 bits &= bits - 1;
@@ -1593,7 +1595,7 @@ size_t bwd_lists_smem_bytes(const dh_sil& s) {
 }
 size_t neg_maps_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(2 * is * (is / 32)) * sizeof(uint32_t);
+    return (size_t)(2 * is * (is / 32 + 1)) * sizeof(uint32_t);
 }
 
 template <typename KernelT>
