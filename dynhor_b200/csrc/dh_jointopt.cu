@@ -335,6 +335,8 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const bool owned_smem = owned_words <= kOwnedSmemWords;
     uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
     uint32_t* g_owned = s.owned + (size_t)b * owned_words;
+    // both passes' entry counts, requested before the z-buffer clear so that their latency is hidden
+    const int2 bin_counts = *reinterpret_cast<const int2*>(s.bin_count + (b * nstrips + strip) * 2);
     for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
     if (owned_smem)
         for (int i = tid; i < owned_words; i += kRasterThreads) s_owned[i] = 0u;
@@ -350,7 +352,9 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     // the target-mask cells this thread scores in the epilogue, fetched now so that their latency hides behind the
     // rasterisation (same cell order as epilogue 2)
     constexpr int kMaskPre = 6;
-    unsigned long long m_pre = 0ull;   // one byte per epilogue iteration
+    int m_pre[kMaskPre];   // one register per epilogue iteration: nothing consumes the loads before the epilogue
+#pragma unroll
+    for (int k = 0; k < kMaskPre; k++) m_pre[k] = 0;
     if (FUSED) {
         const int S_ = s.S, wprp_ = (S_ + 31) >> 5, rows_ = s.aa ? kSH / 2 : kSH;
 #pragma unroll
@@ -359,7 +363,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             if (seg < rows_ * wprp_) {
                 const int ly = seg / wprp_, x = ((seg - ly * wprp_) << 5) + lane;
                 const int yo = s.aa ? ((is - 1 - (row0 + 2 * ly)) >> 1) : (is - 1 - (row0 + ly));
-                m_pre |= (unsigned long long)(uint8_t)mask_tri[((size_t)b * S_ + yo) * S_ + x] << (8 * k);
+                m_pre[k] = mask_tri[((size_t)b * S_ + yo) * S_ + x];
             }
         }
     }
@@ -372,7 +376,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
 #endif
     for (int pass_i = 0; pass_i < 2; pass_i++) {
         const int pass = pass_i ^ DH_PASS_ORDER;
-        const int count = s.bin_count[(b * nstrips + strip) * 2 + pass];
+        const int count = pass ? bin_counts.y : bin_counts.x;
 #if DH_TILE_Z
         if (pass_i == 1) {
             // Between the passes: farthest recorded depth of every 16-column tile of the strip (an empty pixel
@@ -560,8 +564,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     int sse = 0, inter = 0, uni = 0;
     const int wprp_sh = 31 - __clz(wprp);
     const bool wprp_pow2 = (wprp & (wprp - 1)) == 0;
-    int mi = 0;
-    for (int seg = warp; seg < cell_rows * wprp; seg += kRasterWarps, mi++) {   // one warp = 32 consecutive cells
+    auto score_cells = [&](int seg, int m) {   // one warp = 32 consecutive cells of a row; m: the lane's mask cell
         const int ly = wprp_pow2 ? (seg >> wprp_sh) : seg / wprp, x = ((seg - ly * wprp) << 5) + lane;
         int pop, yo;
         if (s.aa) {
@@ -576,7 +579,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         }
         const size_t o = ((size_t)b * S + yo) * S + x;
         if (FUSED) {
-            const int m = (mi < kMaskPre) ? (int)(int8_t)(uint8_t)(m_pre >> (8 * mi)) : (int)mask_tri[o];
+            if (m == 2) m = mask_tri[o];   // not prefetched
             const int keep = m >= 0, ref = m > 0;
             const int k = keep ? pop - 4 * ref : 0;  // 4 * (image - ref)
             sse += k * k;
@@ -592,7 +595,11 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         } else {
             rend[o] = (float)pop * 0.25f;
         }
-    }
+    };
+#pragma unroll
+    for (int k = 0; k < kMaskPre; k++)
+        if (warp + k * kRasterWarps < cell_rows * wprp) score_cells(warp + k * kRasterWarps, m_pre[k]);
+    for (int seg = warp + kMaskPre * kRasterWarps; seg < cell_rows * wprp; seg += kRasterWarps) score_cells(seg, 2);
     if (FUSED) {
         for (int o = 16; o > 0; o >>= 1) {
             sse += __shfl_xor_sync(0xffffffffu, sse, o);
