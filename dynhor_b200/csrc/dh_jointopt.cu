@@ -34,6 +34,9 @@ constexpr int kThreads = 256;      // CTA size of the backward / elementwise ker
 #ifndef DH_RASTER_EVEN
 #define DH_RASTER_EVEN 1
 #endif
+#ifndef DH_RASTER_SPLIT
+#define DH_RASTER_SPLIT 1   // batches per warp the last (partial) round is cut into
+#endif
 #ifndef DH_TILE_Z
 #define DH_TILE_Z 1
 #endif
@@ -403,7 +406,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
 #if DH_RASTER_EVEN
         const int full = (count / (32 * kRasterWarps)) * kRasterWarps;
         const int rem = count - 32 * full;
-        const int last = (rem + kRasterWarps - 1) / kRasterWarps;
+        const int last = (rem + DH_RASTER_SPLIT * kRasterWarps - 1) / (DH_RASTER_SPLIT * kRasterWarps);
 #else
         const int full = count / 32, rem = count - 32 * full, last = 32;
 #endif
