@@ -141,3 +141,39 @@ def test_emu_raster_triangle_soup_vs_bruteforce_oracle(seed):
     assert np.array_equal(maps["face_index"], fidx)
     assert np.array_equal(unpack_alpha(abits), maps["alpha"] > 0.5)
     assert (fidx >= 0).mean() > 0.2
+
+
+def test_emu_real_shoe_mesh_vs_oracle():
+    """The reference's own object prior (tests/golden/shoe_mesh.npz <- assets/shoes, normalised like run.py:110-112):
+    a non-convex real mesh through the kernel arithmetic -- face ownership / coverage bit-exact against the oracle's
+    brute-force rasteriser, losses and pose gradients against the oracle pipeline."""
+    import os
+    from helpers import GOLDEN
+    from dynhor_b200 import synth
+    from oracle import jointopt_oracle as jo
+    m = np.load(os.path.join(GOLDEN, "shoe_mesh.npz"))
+    verts, faces = m["verts"].astype(np.float32), m["faces"].astype(np.int64)
+    assert verts.shape == (2502, 3) and faces.shape == (5000, 3)
+    S = 64
+
+    def render_fn(vc, fc, K, size):
+        B = len(vc)
+        r = nr_oracle.Renderer(image_size=size, K=torch.from_numpy(K), R=torch.eye(3)[None], t=torch.zeros(1, 3),
+                               orig_size=1, anti_aliasing=False)
+        return r(torch.from_numpy(vc), torch.from_numpy(fc)[None].repeat(B, 1, 1), mode="silhouettes").numpy()
+
+    seq = synth.make_sequence(2, mesh=(verts, faces), seed=5, size=S, render_fn=render_fn, period=5)
+    mt = np.where(seq["target_masks"] > 0, 1, np.where(seq["target_masks"] >= 0, 0, -1)).astype(np.int8)
+    out = E.full_grads(verts, faces.astype(np.int32), seq["K_roi"], mt, seq["rot6d_init"], seq["T_init"], S, 1.0, 10.0)
+    B = 2
+    faces2 = np.concatenate([faces, faces[:, ::-1]], 0)
+    maps = nr_oracle.rasterize_forward_np(out["proj"][:, :, :3][np.arange(B)[:, None, None], faces2[None]], 2 * S)
+    assert np.array_equal(out["fidx"], maps["face_index"])
+    assert np.array_equal(unpack_alpha(out["abits"]), maps["alpha"] > 0.5)
+    orc = jo.JointOptOracle(seq["rot6d_init"], seq["T_init"], verts, faces, seq["K_roi"], seq["target_masks"], lr=1e-4,
+                            image_size=S)
+    ref, grads = orc.loss_and_grads({"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0})
+    assert abs(out["loss_sil_obj"] - ref["loss_sil_obj"]) <= 1e-4 * ref["loss_sil_obj"]
+    assert abs(out["iou_object"] - ref["iou_object"]) <= 1e-6
+    assert rel_err(out["grad_rot6d"], grads["rot6d"]) < 1e-3
+    assert rel_err(out["grad_trans"], grads["trans"]) < 1e-3

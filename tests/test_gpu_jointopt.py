@@ -241,10 +241,29 @@ def big_seq():
 def test_reference_size_frames_vs_oracle(big_seq):
     """BASELINE configs[0]/[1] frame shape against the CPU oracle computed here: rasteriser maps bit-exact on the
     kernel's own projected vertices, end-to-end silhouettes bit-exact, losses 1e-4, gradients 1e-3."""
+    _check_frames_vs_oracle(big_seq)
+
+
+@pytest.fixture(scope="module")
+def shoe_seq():
+    """The reference's own object prior (assets/shoes, configs/custom_shoes.yaml): 2502 vertices / 5000 faces,
+    non-convex (the shoe opening), normalised like run.py:110-112 (tests/golden/make_shoe_mesh.py)."""
+    from dynhor_b200 import synth
+    m = np.load(os.path.join(GOLDEN, "shoe_mesh.npz"))
+    mesh = (m["verts"].astype(np.float32), m["faces"].astype(np.int64))
+    return synth.make_sequence(3, mesh=mesh, seed=11, render_fn=_oracle_render_fn, period=7)
+
+
+def test_real_shoe_mesh_frames_vs_oracle(shoe_seq):
+    """Same bars on the real shoe mesh: self-occlusion and concavities exercise the depth pre-test, the tile-z
+    culling between the winding passes and the ownership tests of the backward on a non-convex object."""
+    _check_frames_vs_oracle(shoe_seq)
+
+
+def _check_frames_vs_oracle(seq):
     from dynhor_b200.jointopt import FusedJointOpt
     from oracle import jointopt_oracle as jo
     from oracle import nr_oracle
-    seq = big_seq
     lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
     model = _model_from_seq(seq)
     fused = FusedJointOpt(model, lw, 1e-4, 4)
