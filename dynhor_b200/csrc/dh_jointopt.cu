@@ -654,9 +654,6 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_BWD_MIN_CTAS
 #define DH_BWD_MIN_CTAS 2
 #endif
-#ifndef DH_PREFETCH_OWNER
-#define DH_PREFETCH_OWNER 0
-#endif
 #ifndef DH_EVEN_LAST
 #define DH_EVEN_LAST 1
 #endif
@@ -1269,12 +1266,6 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                         const bool dpos = 0 < sp.direction;
                         const int bound = s_rng[(axis ? 0 : 2) + (dpos ? 1 : 0)][d0];
                         t_out = dpos ? (d1_out <= bound) : (bound <= d1_out);
-#if DH_PREFETCH_OWNER
-                        if (t_out) {  // the ownership test of phase 2 reads this pixel of the face-index map
-                            const int r_in = (axis == 0) ? d1_in : d0, c_in = (axis == 0) ? d0 : d1_in;
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(m.fidx + r_in * is + c_in));
-                        }
-#endif
                         const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
                         t_in = !((s_alpha[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u);
                         tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
