@@ -220,8 +220,17 @@ def run_ours(args):
     Bl = args.frames_per_gpu
     B_total = Bl * world
     shard = FrameShard(rank, world, B_total)
-    seq = synth.make_sequence(Bl, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=B_total,
-                              frame_offset=shard.start)
+    period, offset = B_total, shard.start
+    if args.emulate_shard and world == 1:
+        # diagnostic: the frames rank r of a w-GPU run would own, timed stand-alone on one GPU (no halo)
+        r, w = (int(v) for v in args.emulate_shard.split("/"))
+        period, offset = Bl * w, Bl * r
+    # weak scaling: the object's motion repeats every `frames_per_gpu` frames, so every rank's range holds one
+    # full period of it (same amount of work per GPU at every N; --traj-period total: one period over the whole
+    # sequence, where the ranks' frame ranges differ in content and the slowest one sets the pace)
+    traj = Bl if args.traj_period == "per-gpu" else period
+    seq = synth.make_sequence(Bl, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=period,
+                              frame_offset=offset, traj_period=traj)
     V, F = len(seq["verts"]), len(seq["faces"])
     C = args.corr
     lw = loss_weights(C)
@@ -291,7 +300,8 @@ def run_ours(args):
         m_local = torch.from_numpy(seq["target_masks"]).cuda()
         ms_all = [torch.empty_like(m_local) for _ in range(world)]
         dist.all_gather(ms_all, m_local)
-        full = synth.make_sequence(B_total, H, W, mesh=MESH, seed=0, render_fn=None, period=B_total)
+        full = synth.make_sequence(B_total, H, W, mesh=MESH, seed=0, render_fn=None, period=B_total,
+                                   traj_period=traj)
         full["target_masks"] = torch.cat(ms_all).cpu().numpy()
         if C > 0:  # only this rank's frames are read by joint_optimize; the others are placeholders
             full["correspondences"] = np.zeros((B_total, C, 6), np.float32)
@@ -337,6 +347,7 @@ def run_ours(args):
                                    + (f" / lw_corr {LW_CORR}" if C > 0 else "") + ", lr 1e-4 (BASELINE configs[1])",
                        "frames_per_gpu": Bl, "frames_total": B_total, "correspondences_per_frame": C,
                        "parallelism": f"frame-shard x{world}",
+                       "trajectory_period_frames": traj,
                        "halo": fused.halo_mode,
                        "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": True},
@@ -444,6 +455,9 @@ def main():
     ap.add_argument("--mesh", default=MESH, choices=["uv50x100", "uv100x200"],
                     help="uv100x200 = the 20k-vertex mesh of BASELINE configs[2]")
     ap.add_argument("--camera", default=f"{H}x{W}", help="full-frame camera HxW (configs[2]: 1080x1920)")
+    ap.add_argument("--traj-period", default="per-gpu", choices=["per-gpu", "total"],
+                    help="frames after which the synthetic motion repeats: frames-per-gpu (default) or the whole sequence")
+    ap.add_argument("--emulate-shard", default="", help="r/w: time the frames of rank r of a w-GPU run on one GPU")
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()

@@ -211,12 +211,14 @@ def add_disc_occluder(masks01, seed=0, radius=40.0):
 
 
 def make_sequence(B, H=480, W=640, mesh="uv50x100", seed=0, render_fn=None, size=REND_SIZE, occluder=True,
-                  period=None, frame_offset=0):
+                  period=None, frame_offset=0, traj_period=None):
     """Build one synthetic joint-optimisation problem.
 
     render_fn(verts_cam [B,V,3] f32, faces [F,3] i64, K_roi [B,3,3] f32, size) -> [B,size,size] silhouettes
     in [0,1] rendered WITHOUT anti-aliasing; required unless masks are not needed.
-    `period`/`frame_offset` let a rank build frames [frame_offset, frame_offset+B) of a longer sequence.
+    `period`/`frame_offset` let a rank build frames [frame_offset, frame_offset+B) of a longer sequence of
+    `period` frames; `traj_period` (default: the sequence length) is the number of frames after which the
+    ground-truth motion repeats.
     Returns a dict with the arguments of joint_optimize plus the ground truth."""
     if isinstance(mesh, str):
         if mesh == "uv50x100":
@@ -232,7 +234,7 @@ def make_sequence(B, H=480, W=640, mesh="uv50x100", seed=0, render_fn=None, size
     else:
         verts, faces = mesh
     n = B + frame_offset if period is None else period
-    R_all, T_all = gt_trajectory(n, period=n)
+    R_all, T_all = gt_trajectory(n, period=traj_period if traj_period else n)
     Rn_all, Tn_all = perturb_poses(R_all, T_all, seed)
     sl = slice(frame_offset, frame_offset + B)
     R_gt, T_gt, R0, T0 = R_all[sl], T_all[sl], Rn_all[sl], Tn_all[sl]
