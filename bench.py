@@ -422,6 +422,64 @@ def run_dino(args):
         "planted_match_rank0": ok, "gpu_launches": 3 * args.steps}))
 
 
+def run_preprocess(args):
+    """Secondary workload: run.py:26-72 process_input for a whole sequence -- tight boxes,
+    ROIAlign crops of object mask / hand mask / image, tri-state target masks.  One JSON line; `value` = frames/s with
+    the inputs resident in HBM, `e2e` = from host arrays (H2D of masks + images, D2H of every output)."""
+    from dynhor_b200.preprocess import process_input, process_input_batched
+    from oracle import roi_oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import roi_scenes
+    B = args.frames_per_gpu
+    torch.cuda.set_device(0)
+    base = roi_scenes(12, H, W, 0)
+    images = [base[0][i % 12] for i in range(B)]
+    objs = [base[1][i % 12] for i in range(B)]
+    hands = [base[2][i % 12] for i in range(B)]
+    im_d = torch.from_numpy(np.stack(images)).cuda()
+    ob_d = torch.from_numpy(np.stack([o == 255 for o in objs])).cuda().to(torch.uint8)   # bit masks resident in HBM
+    hb_d = torch.from_numpy(np.stack([h == 255 for h in hands])).cuda().to(torch.uint8)
+    for _ in range(max(args.warmup, 3)):
+        process_input_batched(im_d, ob_d, hb_d, masks_are_bits=True)
+    steps = max(1, min(args.steps, 50))
+    times = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = process_input_batched(im_d, ob_d, hb_d, masks_are_bits=True)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
+    t0 = time.perf_counter()
+    out = process_input(images, objs, hands)
+    e2e_s = time.perf_counter() - t0
+    # bytes: every input byte once (masks as float64 arrays like run.py's load_data + uint8 image), every output once
+    in_bytes = B * H * W * (1 + 1 + 3)          # device-resident: uint8 bit masks + uint8 image
+    h2d_bytes = in_bytes                           # the host wrapper compares the float64 masks into pinned uint8
+    out_bytes = B * (256 * 256 * (1 + 4 + 1 + 12) + 32)
+    hbm, kind = measured_peaks()
+    nf = min(B, 16)
+    t0 = time.perf_counter()
+    ref = roi_oracle.process_input(images[:nf], objs[:nf], hands[:nf])
+    cpu_s = (time.perf_counter() - t0) / nf
+    ok = all(np.array_equal(out[i]["target_crop_mask"], ref[i]["target_crop_mask"]) for i in range(nf))
+    print(json.dumps({
+        "metric": "ROI preprocessing frames / second (boxes + ROIAlign crops + target masks)", "value": B / (ms / 1e3),
+        "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"run.py process_input: {B} frames {H}x{W}, object + hand masks + RGB image -> 256x256 "
+                               "crop mask, crop image and tri-state target mask", "l2": "inputs (1.5 MB/frame, 461 MB) exceed L2"},
+        "roofline": {"bound": "hbm", "achieved": (in_bytes + out_bytes) / (ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": (in_bytes + out_bytes) / (ms / 1e3) / 1e9 / hbm, "peak_source": f"{kind} hbm_gbs",
+                     "traffic": None, "algorithmic_bytes_per_launch": in_bytes + out_bytes},
+        "e2e": {"value": B / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_bytes},
+        "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
+                         "sample": f"{nf} frames, run.py:26-72 restated line by line over torchvision's CPU roi_align "
+                                   "(what detectron2's ROIAlign executes)"},
+        "matches_oracle": bool(ok), "gpu_launches": 3 * steps}))
+
+
 def _quiet_stdout():
     """Route everything libraries print on fd 1 (NCCL's version banner, tqdm) to stderr; the JSON line is written
     to the real stdout at the end, so that stdout carries exactly one line."""
@@ -458,13 +516,15 @@ def main():
     ap.add_argument("--traj-period", default="per-gpu", choices=["per-gpu", "total"],
                     help="frames after which the synthetic motion repeats: frames-per-gpu (default) or the whole sequence")
     ap.add_argument("--emulate-shard", default="", help="r/w: time the frames of rank r of a w-GPU run on one GPU")
-    ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino"])
+    ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino", "preprocess"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     MESH = args.mesh
     H, W = (int(v) for v in args.camera.split("x"))
     if args.workload == "dino":
         run_dino(args)
+    elif args.workload == "preprocess":
+        run_preprocess(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

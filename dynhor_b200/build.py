@@ -18,6 +18,7 @@ SOURCES = {
     "dh_jointopt.cu": ["--fmad=false"],
     "dh_dino.cu": [],
     "dh_corr.cu": [],
+    "dh_roi.cu": ["--fmad=false"],
 }
 
 

@@ -229,6 +229,25 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
 int dh_dino_prescale(const float* feats, const float* mask, int32_t n, int32_t P, int32_t D, void* out_bf16,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ROI preprocessing: the target masks the joint optimisation consumes.
+ * Replaces the per-frame CPU loop ObjTracker/run.py:26-72 (process_input) and its helpers utils/bbox.py:8-36
+ * (crop_and_resize = detectron2 ROIAlign((S,S), 1.0, 0, aligned=True)), utils/bbox.py:73-117 (square box, box
+ * modes) and utils/maskutils.py:8-30 (add_occlusions), for all B frames in three launches.
+ *   obj_bits, hand_bits  [B,H,W] u8, 1 where the SAM mask == 255 (hand_bits may be NULL: no occluder)
+ *   images_hwc           [B,H,W,3] u8 (NULL with crop_image NULL: masks only)
+ *   bounds               [B,4] i32 scratch -> min_row, max_row, min_col, max_col (max_row < 0: empty object mask;
+ *                        the reference raises there, the caller must check)
+ *   bbox, square_bbox    [B,4] f32 xywh  (run.py:41-43)
+ *   crop_mask            [B,S,S] u8      (run.py:47)        target [B,S,S] f32 in {1, 0, -1} (run.py:66-68)
+ *   target_tri           [B,S,S] i8 or NULL (the same values, the fused iteration's mask format)
+ *   crop_image           [B,3,S,S] f32 or NULL, white outside the object mask (run.py:49-51)
+ * ------------------------------------------------------------------------------------------------ */
+int dh_roi_process(const uint8_t* obj_bits, const uint8_t* hand_bits, const uint8_t* images_hwc, int32_t B,
+                   int32_t H, int32_t W, int32_t S, float pad, float expansion, int32_t* bounds, float* bbox,
+                   float* square_bbox, uint8_t* crop_mask, float* target, int8_t* target_tri, float* crop_image,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

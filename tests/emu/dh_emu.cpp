@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../dynhor_b200/csrc/dh_core.h"
+#include "../../dynhor_b200/csrc/dh_roi_core.h"
 
 using namespace dh;
 
@@ -361,6 +362,47 @@ void emu_backward_stats(const float* proj, const int32_t* faces, const int32_t* 
     long long o[16] = {front, items, span_iters, crossings, t_out, t_out_owner, words, words_nz, pairs, t_in, in_px,
                        in_pairs, max_pairs_task, n_neg, 0, 0};
     memcpy(out, o, sizeof(o));
+}
+
+// dh_roi.cu on the host: tight bounds, boxes, ROIAlign crops of the object / occluder bit masks and of the image
+// status[b] = 1 if the object mask of frame b is empty (the reference's np.min raises there)
+void emu_roi_process(const uint8_t* obj_bits, const uint8_t* hand_bits, const uint8_t* images_hwc, int B, int H, int W,
+                     int S, float pad, float expansion, float* bbox, float* square_bbox, uint8_t* crop_mask,
+                     float* target, float* crop_image, int32_t* status) {
+    for (int b = 0; b < B; b++) {
+        const uint8_t* ob = obj_bits + (size_t)b * H * W;
+        const uint8_t* hb = hand_bits ? hand_bits + (size_t)b * H * W : nullptr;
+        int r0 = H, r1 = -1, c0 = W, c1 = -1;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+                if (ob[(size_t)y * W + x]) {
+                    r0 = std::min(r0, y); r1 = std::max(r1, y); c0 = std::min(c0, x); c1 = std::max(c1, x);
+                }
+        status[b] = r1 < 0;
+        if (r1 < 0) continue;
+        float xyxy[4];
+        dh::roi_boxes(r0, r1, c0, c1, H, W, pad, expansion, bbox + 4 * b, square_bbox + 4 * b, xyxy);
+        const dh::RoiGeom g = dh::roi_geom(xyxy, S);
+        for (int ph = 0; ph < S; ph++)
+            for (int pw = 0; pw < S; pw++) {
+                const float vo = dh::roi_align_cell(g, ph, pw, H, W, [&](int y, int x) { return (float)ob[(size_t)y * W + x]; });
+                const bool obit = vo >= 0.5f;
+                bool hbit = false;
+                if (hb) hbit = dh::roi_align_cell(g, ph, pw, H, W, [&](int y, int x) { return (float)hb[(size_t)y * W + x]; }) >= 0.5f;
+                const size_t o = ((size_t)b * S + ph) * S + pw;
+                crop_mask[o] = obit;
+                target[o] = dh::target_value(obit, hbit);
+                if (images_hwc && crop_image) {
+                    const uint8_t* im = images_hwc + (size_t)b * H * W * 3;
+                    float v[3] = {1.0f, 1.0f, 1.0f};
+                    if (obit)
+                        dh::roi_align_cell3(g, ph, pw, H, W, [&](int y, int x, float* px) {
+                            for (int c = 0; c < 3; c++) px[c] = (float)((double)im[((size_t)y * W + x) * 3 + c] / 255.0);
+                        }, v);
+                    for (int c = 0; c < 3; c++) crop_image[(((size_t)b * 3 + c) * S + ph) * S + pw] = v[c];
+                }
+            }
+    }
 }
 
 // k_pose_prep: st [B,16]

@@ -197,3 +197,21 @@ def full_grads(verts, faces, K_roi, mask_tri, rot6d, trans, S, lw_sil, lw_smooth
         "fidx": fidx, "abits": abits, "rend": rend, "proj": proj, "cam": cam, "gpool": gpool, "grad_faces": gf,
     }
     return out
+
+
+def roi_process(obj_bits, hand_bits, images, S, pad=5.0, expansion=0.3):
+    """dh_roi.cu on the host (dh_roi_core.h): boxes, crop mask, tri-state target, image crop."""
+    ob = np.ascontiguousarray(obj_bits, np.uint8)
+    hb = np.ascontiguousarray(hand_bits, np.uint8) if hand_bits is not None else None
+    im = np.ascontiguousarray(images, np.uint8) if images is not None else None
+    B, H, W = ob.shape
+    bbox = np.zeros((B, 4), np.float32)
+    sq = np.zeros((B, 4), np.float32)
+    cm = np.zeros((B, S, S), np.uint8)
+    tg = np.zeros((B, S, S), np.float32)
+    ci = np.zeros((B, 3, S, S), np.float32) if im is not None else None
+    st = np.zeros(B, np.int32)
+    lib().emu_roi_process(_p(ob), _p(hb), _p(im), B, H, W, S, ctypes.c_float(pad), ctypes.c_float(expansion), _p(bbox),
+                          _p(sq), _p(cm), _p(tg), _p(ci), _p(st))
+    return {"bbox": bbox, "square_bbox": sq, "crop_mask": cm.astype(bool), "target_crop_mask": tg, "crop_image": ci,
+            "status": st}

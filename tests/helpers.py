@@ -47,3 +47,29 @@ def object_parameters_from_golden(g):
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def roi_scenes(n, H=480, W=640, seed=0, border=False):
+    """Synthetic SAM-style inputs of run.py:load_data: per frame an RGB image (uint8 HWC), an object mask and a hand
+    mask (float64 arrays, 255 = set).  Rotated ellipses with a disc occluder; `border` pushes objects against the
+    image edges (box clamping, samples outside the image)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    images, objs, hands = [], [], []
+    for i in range(n):
+        if border and i % 2 == 0:
+            cy, cx = rng.choice([5.0, H - 6.0]), rng.choice([4.0, W - 5.0])
+        else:
+            cy, cx = rng.uniform(0.2 * H, 0.8 * H), rng.uniform(0.2 * W, 0.8 * W)
+        a, b = rng.uniform(0.02 * H, 0.3 * H), rng.uniform(0.02 * W, 0.3 * W)
+        th = rng.uniform(0, np.pi)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+        v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        obj = (u / b) ** 2 + (v / a) ** 2 < 1
+        obj[int(np.clip(cy, 0, H - 1)), int(np.clip(cx, 0, W - 1))] = True   # never empty
+        hy, hx = cy + rng.uniform(-a, a), cx + rng.uniform(-b, b)
+        hand = (yy - hy) ** 2 + (xx - hx) ** 2 < rng.uniform(0.04 * H, 0.17 * H) ** 2
+        images.append(rng.integers(0, 256, (H, W, 3)).astype(np.uint8))
+        objs.append(obj.astype(np.float64) * 255)
+        hands.append(hand.astype(np.float64) * 255)
+    return images, objs, hands

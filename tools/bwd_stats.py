@@ -11,7 +11,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import emu_lib  # noqa: E402
-from bench import H, W, MESH, oracle_render_fn  # noqa: E402
+from bench import H, W, oracle_render_fn  # noqa: E402
+import bench as _bench  # noqa: E402
+MESH = os.environ.get("DH_STATS_MESH", _bench.MESH)
 from dynhor_b200 import synth  # noqa: E402
 
 NAMES = ["front", "items", "span_iters", "crossings", "t_out", "t_out_owner", "words", "words_nz", "pairs", "t_in",
