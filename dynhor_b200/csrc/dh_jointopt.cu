@@ -340,10 +340,14 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     uint32_t* g_owned = s.owned + (size_t)b * owned_words;
     // both passes' entry counts, requested before the z-buffer clear so that their latency is hidden
     const int2 bin_counts = *reinterpret_cast<const int2*>(s.bin_count + (b * nstrips + strip) * 2);
-    for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
+    // a strip no face reaches (above / below the object: about a fifth of them) skips the z-buffer altogether
+    const bool empty_strip = (bin_counts.x | bin_counts.y) == 0;
+    if (!empty_strip) {
+        for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
+        for (int i = tid; i < is; i += kRasterThreads) s_ndc[i] = pix_to_ndc(i, is);
+    }
     if (owned_smem)
         for (int i = tid; i < owned_words; i += kRasterThreads) s_owned[i] = 0u;
-    for (int i = tid; i < is; i += kRasterThreads) s_ndc[i] = pix_to_ndc(i, is);
     if (tid < 2) s_next[tid] = 0;
     if (FUSED && strip == 0 && tid == 0) s.gmax[b] = 2.0f * fabsf(gcoef) * (s.aa ? 0.25f : 1.0f);
     __syncthreads();
@@ -377,7 +381,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
 #ifndef DH_PASS_ORDER
 #define DH_PASS_ORDER 0
 #endif
-    for (int pass_i = 0; pass_i < 2; pass_i++) {
+    for (int pass_i = 0; pass_i < 2 && !empty_strip; pass_i++) {
         const int pass = pass_i ^ DH_PASS_ORDER;
         const int count = pass ? bin_counts.y : bin_counts.x;
 #if DH_TILE_Z
@@ -536,7 +540,15 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     uint32_t* abits_g = s.alpha_bits + ((size_t)b * is + row0) * wpr;
     const int wpr_sh = 31 - __clz(wpr);
     const bool wpr_pow2 = (wpr & (wpr - 1)) == 0;
-    for (int seg = warp; seg < kSH * wpr; seg += kRasterWarps) {   // one warp = 32 consecutive pixels of a row
+    if (empty_strip) {
+        int4* f4 = reinterpret_cast<int4*>(fidx);   // (row0 * is) * 4 bytes: 16-byte aligned, is % 32 == 0
+        for (int i = tid; i < kSH * is / 4; i += kRasterThreads) f4[i] = make_int4(-1, -1, -1, -1);
+        for (int i = tid; i < kSH * wpr; i += kRasterThreads) {
+            (&abits[0][0])[(i / wpr) * (kMaxIS / 32) + (i % wpr)] = 0u;
+            abits_g[i] = 0u;
+        }
+    }
+    for (int seg = warp; seg < kSH * wpr && !empty_strip; seg += kRasterWarps) {   // one warp = 32 consecutive pixels
         const int r = wpr_pow2 ? (seg >> wpr_sh) : seg / wpr, cw = seg - r * wpr;
         const int i = r * is + (cw << 5) + lane;
         const unsigned long long key = zbuf[i];
