@@ -1,0 +1,50 @@
+"""GPU: the data path of run.py on either side of the joint optimisation, end to end on the device --
+full-frame SAM-style masks -> process_input (run.py:26-72) -> K_roi (pose_initializtion.py:271-277,327) ->
+joint_optimize (run.py:155-164).  The full-frame masks are silhouettes of the object under the ground-truth poses,
+so the optimisation must pull the perturbed poses back towards them."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_masks_to_target_masks_to_joint_optimisation():
+    from dynhor_b200 import synth
+    from dynhor_b200.camera import get_K_crop_resize
+    from dynhor_b200.jointopt import joint_optimize
+    from dynhor_b200.preprocess import process_input_batched
+    from dynhor_b200.renderer import Renderer
+    B, H, W, S = 6, 512, 512, 256
+    verts, faces = synth.icosphere_mesh(3, seed=2)
+    R_gt, T_gt = synth.gt_trajectory(B, period=40)
+    R0, T0 = synth.perturb_poses(R_gt, T_gt, seed=3)
+    K_full = synth.full_frame_K(H, W)
+    # full-frame object masks: the object under the ground-truth pose, rendered with the frame's own intrinsics
+    K_unit = K_full.copy()
+    K_unit[:2] /= H
+    vc = torch.from_numpy((verts.astype(np.float64)[None] @ R_gt + T_gt[:, None, :]).astype(np.float32)).cuda()
+    frame = Renderer(image_size=H, K=torch.from_numpy(K_unit)[None].cuda(), R=torch.eye(3)[None].cuda(),
+                     t=torch.zeros(1, 3).cuda(), orig_size=1, anti_aliasing=False)
+    with torch.no_grad():
+        sil = frame(vc, torch.from_numpy(faces).cuda()[None].repeat(B, 1, 1), mode="silhouettes")
+    obj_masks = (sil > 0.5).to(torch.uint8) * 255                      # SAM convention (run.py:30)
+    hand_masks = torch.zeros_like(obj_masks)
+    hand_masks[:, 40:130, 180:330] = 255                                # a "hand" across the top edge of the object
+    pre = process_input_batched(None, obj_masks, hand_masks)
+    target = pre["target_crop_mask"]
+    assert set(torch.unique(target).tolist()) <= {-1.0, 0.0, 1.0} and (target == 1).any() and (target == -1).any()
+    # pose_initializtion.py:271-277, 327: crop intrinsics from the square box, rows 0-1 over REND_SIZE
+    sq = pre["square_bbox"].cpu()
+    boxes = torch.stack([sq[:, 0], sq[:, 1], sq[:, 0] + sq[:, 2], sq[:, 1] + sq[:, 2]], 1)
+    K_roi = get_K_crop_resize(torch.from_numpy(K_full)[None].repeat(B, 1, 1), boxes, [S])
+    K_roi[:, :2] = K_roi[:, :2] / S
+    params = [{"rotations": torch.from_numpy(R0[b:b + 1].astype(np.float32)),
+               "translations": torch.from_numpy(T0[b:b + 1].astype(np.float32)).reshape(1, 1, 3),
+               "K_roi": K_roi[b:b + 1].unsqueeze(0), "target_masks": target[b:b + 1]} for b in range(B)]
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    model, evo = joint_optimize(params, objvertices=verts, objfaces=np.stack([faces] * B), loss_weights=lw,
+                                num_iterations=150, lr=1e-3)
+    iou = np.asarray(evo["iou_object"])
+    assert iou[0] > 0.6 and iou[-1] > iou[0] + 0.03 and iou[-1] > 0.93, (iou[0], iou[-1])
+    assert evo["loss_sil_obj"][-1] < 0.5 * evo["loss_sil_obj"][0]
