@@ -762,39 +762,61 @@ __device__ __forceinline__ int block_exclusive_scan_512(int v, int* s_wsum, int*
     return base + incl - v;
 }
 
+// 32x32 bit-matrix transpose across a warp: lane k holds row k (bit i = column i) and gets column k back
+// (bit i = row i).  Five butterfly stages of one shuffle each (recursive swap of the off-diagonal quadrants).
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1) {
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        if ((lane & j) == 0) x ^= (((x >> j) ^ y) & m) << j;
+        else                 x ^= ((y >> j) ^ x) & m;
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
 __global__ void __launch_bounds__(kNegThreads)
 k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
-    extern __shared__ uint32_t nm_words[];  // [is][wpr + 1] row-major, then [is][wpr + 1] column-major (rows padded
-                                            // by one word: a thread per line and the block transposes stay conflict-free)
+    extern __shared__ uint32_t nm_words[];  // [is][wpr + 1] row-major; the column-side CTA transposes it in place
+                                            // (rows padded by one word: a thread per line and the block transposes
+                                            // stay conflict-free); then the frame's coverage bitmap [is][wpr]
     __shared__ int s_wsum[kNegThreads / 32];
     const int is = raster_size(s), S = s.S;
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     // grid (B, 2): block y = 1 builds the row side (row ranges, row lists), y = 0 the column side (transposed bitmap,
-    // column lists); a (B, 1) grid does both.
+    // column lists)
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int axis_lo = gridDim.y == 2 ? (int)blockIdx.y : 0, axis_hi = gridDim.y == 2 ? (int)blockIdx.y : 1;
+    const int axis_lo = blockIdx.y, axis_hi = blockIdx.y;
     const int warp = tid >> 5, lane = tid & 31;
     uint32_t* words = nm_words;
     const int wps = wpr + 1;
-    uint32_t* wordsT = nm_words + is * wps;
+    uint32_t* wordsT = nm_words;            // after the in-place transpose
+    uint32_t* s_alpha = nm_words + is * wps;  // the lists' pixel codes read it (long lines would otherwise wait on
+                                              // two global loads per listed pixel)
     const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
     const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
+    for (int i = tid; i < is * wpr; i += kNegThreads) s_alpha[i] = ga[i];
+    __syncthreads();
     for (int i = tid; i < is * wpr; i += kNegThreads) {
         const int r = i / wpr, w = i - r * wpr;
-        words[r * wps + w] = neg_row_word(ga, gn, is, s.aa, wpr, wprp, r, w);
+        words[r * wps + w] = neg_row_word(s_alpha, gn, is, s.aa, wpr, wprp, r, w);
     }
     __syncthreads();
-    if (axis_lo == 0)
-    for (int blk = warp; blk < wpr * wpr; blk += kNegThreads / 32) {
-        const int rb = blk / wpr, cb = blk - rb * wpr;
-        const uint32_t word = words[(32 * rb + lane) * wps + cb];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const uint32_t colw = __ballot_sync(0xffffffffu, (word >> j) & 1u);
-            if (lane == j) mine = colw;
+    if (axis_lo == 0) {
+        // in-place transpose: the 32x32 bit blocks (rb, cb) and (cb, rb), rb <= cb, are transposed through ballots
+        // and swapped; every warp owns whole block pairs
+        const int npairs = wpr * (wpr + 1) / 2;
+        for (int pr = warp; pr < npairs; pr += kNegThreads / 32) {
+            int rb = 0, rem = pr;
+            while (rem >= wpr - rb) { rem -= wpr - rb; rb++; }
+            const int cb = rb + rem;
+            const uint32_t wa = words[(32 * rb + lane) * wps + cb], wb = words[(32 * cb + lane) * wps + rb];
+            const uint32_t ta = transpose32(wa, lane), tb = transpose32(wb, lane);
+            __syncwarp();
+            words[(32 * cb + lane) * wps + rb] = ta;
+            words[(32 * rb + lane) * wps + cb] = tb;
         }
-        wordsT[(32 * cb + lane) * wps + rb] = mine;
     }
     __syncthreads();
     uint32_t* gT = s.negT + (size_t)b * is * wpr;
@@ -836,7 +858,7 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
                 int pop = 0;
                 if (s.aa) {
                     const int sh = c & 30;
-                    const uint32_t w0 = __ldg(&ga[(r & ~1) * wpr + (c >> 5)]), w1 = __ldg(&ga[(r | 1) * wpr + (c >> 5)]);
+                    const uint32_t w0 = s_alpha[(r & ~1) * wpr + (c >> 5)], w1 = s_alpha[(r | 1) * wpr + (c >> 5)];
                     pop = __popc((w0 >> sh) & 3u) + __popc((w1 >> sh) & 3u);
                 }
                 *E++ = (uint16_t)((uint32_t)d1 | ((uint32_t)(4 - pop) << 10));
@@ -1608,7 +1630,7 @@ size_t bwd_lists_smem_bytes(const dh_sil& s) {
 }
 size_t neg_maps_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return (size_t)(2 * is * (is / 32 + 1)) * sizeof(uint32_t);
+    return (size_t)(is * (is / 32 + 1) + is * (is / 32)) * sizeof(uint32_t);
 }
 
 template <typename KernelT>
