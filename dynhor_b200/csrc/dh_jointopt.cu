@@ -174,8 +174,11 @@ k_setup_bin(const float4* __restrict__ proj, const int32_t* __restrict__ faces, 
     const int tid = threadIdx.x;
     if (tid < 2 * kMaxStrips) (&s_cnt[0][0])[tid] = 0;
     __syncthreads();
-    // up to 2 windings x 2 strips are kept in registers; anything beyond goes straight to the global counters
-    int e_fn[4], e_strip[4], e_slot[4], ne = 0;
+    // per winding the first two strips of the face are kept in registers (statically indexed: slot 2 w + j);
+    // anything beyond goes straight to the global counters
+    int e_fn[4], e_strip[4], e_slot[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) e_fn[k] = -1;
     if (f < F) {
         const float4* P = proj + (size_t)b * V;
         const float4 a0 = P[faces[3 * f + 0]], a1 = P[faces[3 * f + 1]], a2 = P[faces[3 * f + 2]];
@@ -188,16 +191,18 @@ k_setup_bin(const float4* __restrict__ proj, const int32_t* __restrict__ faces, 
             int xl, xh, yl, yh;
             if (!face_bbox(x, y, is, &xl, &xh, &yl, &yh)) continue;
             const int fn = f + w * F;
-            for (int st = yl / kSH; st <= yh / kSH; st++) {
-                if (ne < 4) {
-                    e_fn[ne] = fn; e_strip[ne] = st;
-                    e_slot[ne] = atomicAdd(&s_cnt[st][w], 1);
-                    ne++;
-                } else {
-                    const int slot = atomicAdd(&bin_count[(b * nstrips + st) * 2 + w], 1);
-                    int32_t* bin = bins + ((size_t)b * nstrips + st) * (size_t)(2 * F);
-                    bin[w ? 2 * F - 1 - slot : slot] = fn;
+            const int st0 = yl / kSH, st1 = yh / kSH;
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (st0 + j <= st1) {
+                    e_fn[2 * w + j] = fn;
+                    e_strip[2 * w + j] = st0 + j;
+                    e_slot[2 * w + j] = atomicAdd(&s_cnt[st0 + j][w], 1);
                 }
+            for (int st = st0 + 2; st <= st1; st++) {
+                const int slot = atomicAdd(&bin_count[(b * nstrips + st) * 2 + w], 1);
+                int32_t* bin = bins + ((size_t)b * nstrips + st) * (size_t)(2 * F);
+                bin[w ? 2 * F - 1 - slot : slot] = fn;
             }
         }
     }
@@ -208,8 +213,10 @@ k_setup_bin(const float4* __restrict__ proj, const int32_t* __restrict__ faces, 
         s_base[st][w] = c ? atomicAdd(&bin_count[(b * nstrips + st) * 2 + w], c) : 0;
     }
     __syncthreads();
-    for (int k = 0; k < ne; k++) {
-        const int w = e_fn[k] >= F;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (e_fn[k] < 0) continue;
+        const int w = k >> 1;
         const int slot = s_base[e_strip[k]][w] + e_slot[k];
         int32_t* bin = bins + ((size_t)b * nstrips + e_strip[k]) * (size_t)(2 * F);
         bin[w ? 2 * F - 1 - slot : slot] = e_fn[k];
