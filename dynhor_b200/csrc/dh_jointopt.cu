@@ -974,11 +974,13 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             const float ea = (ec.ka == 0.0f) ? inf : ((0.0f < ka2 * dirf) ? eps : -eps);
             const float eb = (ec.kb == 0.0f) ? inf : ((0.0f < kb2 * dirf) ? eps : -eps);
             if (own == fn && 0.0f < dunit && (ec.ka != 0.0f || ec.kb != 0.0f)) {
-                uint32_t e = (i != i_stop) ? E[i] : 0u;
+                const uint16_t* pe = E + i;   // running pointer: one 64-bit add per pixel instead of re-indexing
+                uint32_t e = (i != i_stop) ? *pe : 0u;
                 while (i != i_stop) {
                     // the next entry is fetched one iteration ahead (L1 latency behind the two reciprocals); one
                     // entry past either end of a line is still inside the frame's list block
-                    const uint32_t e_next = E[i + step];
+                    pe += step;
+                    const uint32_t e_next = *pe;
                     const int d1 = (int)(e & 1023u);
                     if (lim < d1 * step) { i = i_end; break; }  // past d1_out against the walking direction
                     const float x = (float)d1 - d1_cross;
