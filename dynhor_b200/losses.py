@@ -1,12 +1,15 @@
-"""Host-side mirror of ObjTracker/utils/losses.py with the CUDA renderer underneath.
+"""Loss terms of the composable (autograd) path, with the CUDA silhouette renderer underneath.
 
-Same class, method names, arguments, return structure and error behaviour:
-    batch_mask_iou(ref, pred)                          losses.py:7-24   (ValueError outside [0,1])
-    Losses(ref_mask_object, keep_mask_object, camintr_rois_object)      losses.py:26-40
-    Losses.compute_sil_loss(verts, faces) -> ({"loss_sil_obj": Tensor[1]}, {"iou_object": float})   :66-78
-    Losses.compute_smooth_loss(verts)     -> {"loss_smooth_obj": Tensor[]}                          :80-84
-    Losses.compute_offscreen_loss(verts)                                                            :42-64
-This is the composable (autograd) path; jointopt.joint_optimize uses the fused kernels instead.
+Interface mirror of ObjTracker/utils/losses.py -- same public names, argument meaning, return structure and error
+behaviour, so that code written against the reference keeps working:
+
+    batch_mask_iou(ref, pred, eps)        losses.py:7-24   per-frame IoU; ValueError when a mask leaves [0, 1]
+    Losses(ref_mask_object, keep_mask_object, camintr_rois_object)             losses.py:26-40
+      .compute_offscreen_loss(verts)      losses.py:42-64  summed distance of projected vertices outside the view
+      .compute_sil_loss(verts, faces)     losses.py:66-78  ({"loss_sil_obj": Tensor[1]}, {"iou_object": float})
+      .compute_smooth_loss(verts)         losses.py:80-84  {"loss_smooth_obj": Tensor[]}
+
+`jointopt.joint_optimize` does not come through here: it runs the fused kernels (csrc/dh_jointopt.cu).
 """
 import torch
 
@@ -14,50 +17,55 @@ from .constants import REND_SIZE
 from .renderer import Renderer, projection
 
 
+def _require_unit_range(mask):
+    lo, hi = mask.min(), mask.max()
+    if hi > 1 or lo < 0:
+        raise ValueError("Ref mask should have values in [0, 1], " f"not [{lo, hi}]")
+
+
 def batch_mask_iou(ref, pred, eps=0.000001):
-    ref = ref.float()
-    pred = pred.float()
-    if ref.max() > 1 or ref.min() < 0:
-        raise ValueError("Ref mask should have values in [0, 1], " f"not [{ref.min(), ref.max()}]")
-    if pred.max() > 1 or pred.min() < 0:
-        raise ValueError("Ref mask should have values in [0, 1], " f"not [{pred.min(), pred.max()}]")
-    inter = ref * pred
-    union = ref + pred - inter
-    ious = inter.sum(1).sum(1).float() / (union.sum(1).sum(1).float() + eps)
-    return ious
+    """Intersection over union of every frame's pair of soft masks, [B,H,W] x [B,H,W] -> [B]."""
+    ref, pred = ref.float(), pred.float()
+    _require_unit_range(ref)
+    _require_unit_range(pred)
+    both = ref * pred
+    either = ref + pred - both
+    per_frame = lambda t: t.sum(1).sum(1).float()   # rows first, then columns: the reference's summation order
+    return per_frame(both) / (per_frame(either) + eps)
 
 
 class Losses():
+    """Holds the target masks and the silhouette renderer of one sequence."""
+
     def __init__(self, ref_mask_object, keep_mask_object, camintr_rois_object, image_size=None):
-        self.ref_mask_object = ref_mask_object
-        self.keep_mask_object = keep_mask_object
+        self.ref_mask_object, self.keep_mask_object = ref_mask_object, keep_mask_object
         self.camintr_rois_object = camintr_rois_object
-        dev = camintr_rois_object.device
-        size = int(ref_mask_object.shape[-1]) if image_size is None else image_size
-        self.sil_renderer = Renderer(image_size=size if size else REND_SIZE, K=camintr_rois_object,
-                                     R=torch.eye(3, device=dev).unsqueeze(0), t=torch.zeros(1, 3, device=dev),
+        device = camintr_rois_object.device
+        side = int(ref_mask_object.shape[-1]) if image_size is None else image_size
+        self.sil_renderer = Renderer(image_size=side or REND_SIZE, K=camintr_rois_object,
+                                     R=torch.eye(3, device=device)[None], t=torch.zeros(1, 3, device=device),
                                      orig_size=1)
 
     def compute_offscreen_loss(self, verts):
-        proj = projection(verts, self.sil_renderer.K, self.sil_renderer.R, self.sil_renderer.t,
-                          self.sil_renderer.dist_coeffs, orig_size=1)
-        coord_xy, coord_z = proj[:, :, :2], proj[:, :, 2:]
-        zeros = torch.zeros_like(coord_z)
-        lower_right = torch.max(coord_xy - 1, zeros).sum()
-        upper_left = torch.max(-1 - coord_xy, zeros).sum()
-        behind = torch.max(-coord_z, zeros).sum()
-        too_far = torch.max(coord_z - self.sil_renderer.far, zeros).sum()
-        return lower_right + upper_left + behind + too_far
+        """How far the projected vertices stick out of the view volume ([-1, 1]^2 x (0, far)), summed."""
+        r = self.sil_renderer
+        uvz = projection(verts, r.K, r.R, r.t, r.dist_coeffs, orig_size=1)
+        uv, z = uvz[..., :2], uvz[..., 2:]
+        zero = torch.zeros_like(z)
+        excess = [torch.max(uv - 1, zero), torch.max(-1 - uv, zero),       # beyond +1, below -1
+                  torch.max(-z, zero), torch.max(z - r.far, zero)]         # behind the camera, beyond far
+        return excess[0].sum() + excess[1].sum() + excess[2].sum() + excess[3].sum()
 
     def compute_sil_loss(self, verts, faces):
-        loss_sil = torch.zeros(1, device=verts.device, dtype=torch.float32)
-        rend = self.sil_renderer(verts, faces, mode="silhouettes")
-        image = self.keep_mask_object * rend
-        l_m = torch.sum((image - self.ref_mask_object) ** 2) / self.keep_mask_object.sum()
-        loss_sil = loss_sil + l_m
-        ious = batch_mask_iou(image, self.ref_mask_object)
-        return {"loss_sil_obj": loss_sil / len(verts)}, {"iou_object": ious.mean().item()}
+        """Masked L2 between the rendered silhouettes and the target, per kept pixel and per frame, plus the IoU."""
+        silhouettes = self.sil_renderer(verts, faces, mode="silhouettes")
+        kept = self.keep_mask_object * silhouettes
+        residual = torch.sum((kept - self.ref_mask_object) ** 2) / self.keep_mask_object.sum()
+        loss = torch.zeros(1, device=verts.device, dtype=torch.float32) + residual
+        iou = batch_mask_iou(kept, self.ref_mask_object).mean().item()
+        return {"loss_sil_obj": loss / len(verts)}, {"iou_object": iou}
 
     def compute_smooth_loss(self, verts):
-        smooth_loss_obj = ((verts[1:] - verts[:-1]) ** 2).mean()
-        return {"loss_smooth_obj": smooth_loss_obj}
+        """Mean squared vertex displacement between consecutive frames."""
+        step = verts[1:] - verts[:-1]
+        return {"loss_smooth_obj": (step ** 2).mean()}
