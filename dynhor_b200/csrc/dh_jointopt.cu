@@ -317,6 +317,18 @@ __device__ __forceinline__ void raster_hit(uint32_t ent, const float (*setup)[32
 #endif
 }
 
+// Per-warp working set of the rasteriser and the pixel-centre table.  They live in the dynamic shared-memory block
+// behind the z-buffer strip and are reached through one pointer per warp: accesses to separately declared static
+// __shared__ arrays each re-derive the shared-window address (S2UR / UMOV / UIADD3 / ULEA) inside the hot loops.
+struct __align__(16) RasterWarp {
+    float setup[14][32];   // inv[9], z[3], zlo, zhi of the batch's faces
+    float geo[6][32];      // NDC x[3], y[3]
+    uint32_t box[32];      // x_lo | x_hi << 10 | local first row << 20
+    int start[32];         // first row-item of every face of the batch
+    int fn[32];
+    uint32_t queue[64];    // pending (lane slot, x, local row) hits
+};
+
 // FUSED: epilogue computes the masked-L2 / IoU integer sums and dL/drend (+ sign bitmaps) for this strip.
 // else : epilogue writes the pooled, flipped silhouette `rend` (the renderer's return value).
 #ifndef DH_RASTER_MIN_CTAS
@@ -329,13 +341,6 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
     __shared__ uint32_t abits[kSH][kMaxIS / 32];
     __shared__ int red[3][kRasterThreads / 32];
-    __shared__ float s_ndc[kMaxIS];                    // NDC coordinate of every pixel centre
-    __shared__ float s_setup[kRasterThreads / 32][14][32];   // per warp: inv[9], z[3], zlo, zhi of the batch's faces
-    __shared__ float s_geo[kRasterThreads / 32][6][32];      // per warp: NDC x[3], y[3]
-    __shared__ uint32_t s_box[kRasterThreads / 32][32];      // x_lo | x_hi << 10 | local first row << 20
-    __shared__ int s_start[kRasterThreads / 32][32];         // first row-item of every face of the batch
-    __shared__ int s_fn[kRasterThreads / 32][32];
-    __shared__ uint32_t s_queue[kRasterThreads / 32][64];    // pending (lane slot, x, local row) hits
     __shared__ int s_next[2];
     __shared__ uint32_t s_tilez[kMaxIS / 16];
     const int is = raster_size(s);
@@ -348,6 +353,9 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     // meshes the bits go straight to global memory so that the CTA still fits twice per SM
     const bool owned_smem = owned_words <= kOwnedSmemWords;
     uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
+    RasterWarp* s_rw = reinterpret_cast<RasterWarp*>(s_owned + ((owned_smem ? owned_words : 0) + 3) / 4 * 4);
+    float* s_ndc = reinterpret_cast<float*>(s_rw + kRasterWarps);   // NDC coordinate of every pixel centre [is]
+    RasterWarp& RW = s_rw[threadIdx.x >> 5];
     uint32_t* g_owned = s.owned + (size_t)b * owned_words;
     // both passes' entry counts, requested before the z-buffer clear so that their latency is hidden
     const int2 bin_counts = *reinterpret_cast<const int2*>(s.bin_count + (b * nstrips + strip) * 2);
@@ -457,12 +465,12 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                     const int r_lo = max(fs.y_lo, row0), r_hi = min(fs.y_hi, row0 + kSH - 1);
                     nrows = max(r_hi - r_lo + 1, 0);
 #pragma unroll
-                    for (int k = 0; k < 9; k++) s_setup[warp][k][lane] = fs.inv[k];
+                    for (int k = 0; k < 9; k++) RW.setup[k][lane] = fs.inv[k];
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
-                        s_setup[warp][9 + k][lane] = fs.z[k];
-                        s_geo[warp][k][lane] = fs.x[k];
-                        s_geo[warp][3 + k][lane] = fs.y[k];
+                        RW.setup[9 + k][lane] = fs.z[k];
+                        RW.geo[k][lane] = fs.x[k];
+                        RW.geo[3 + k][lane] = fs.y[k];
                     }
                     const float zmin = fminf(fs.z[0], fminf(fs.z[1], fs.z[2]));
                     const float zmax = fmaxf(fs.z[0], fmaxf(fs.z[1], fs.z[2]));
@@ -475,10 +483,10 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                     for (int k = 0; k < 3; k++)   // NaN fails every comparison
                         defer = defer && fabsf(fs.inv[3 * k]) <= 1.0e3f && fabsf(fs.inv[3 * k + 1]) <= 1.0e3f &&
                                 fabsf(fs.inv[3 * k + 2]) <= 1.0e6f;
-                    s_setup[warp][12][lane] = zlo;
-                    s_setup[warp][13][lane] = defer ? zhi : 0.0f;
-                    s_box[warp][lane] = (uint32_t)fs.x_lo | ((uint32_t)fs.x_hi << 10) | ((uint32_t)(r_lo - row0) << 20);
-                    s_fn[warp][lane] = fn;
+                    RW.setup[12][lane] = zlo;
+                    RW.setup[13][lane] = defer ? zhi : 0.0f;
+                    RW.box[lane] = (uint32_t)fs.x_lo | ((uint32_t)fs.x_hi << 10) | ((uint32_t)(r_lo - row0) << 20);
+                    RW.fn[lane] = fn;
                 }
             }
             int incl = nrows;
@@ -487,7 +495,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            s_start[warp][lane] = incl - nrows;
+            RW.start[lane] = incl - nrows;
             const int total_rows = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
             int qn = 0;
@@ -502,15 +510,15 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
 #pragma unroll
                     for (int k = 0; k < 5; k++) {
                         const int mid = (lo + hi + 1) >> 1;
-                        if (s_start[warp][mid] <= it) lo = mid; else hi = mid - 1;
+                        if (RW.start[mid] <= it) lo = mid; else hi = mid - 1;
                     }
                     slot = lo;
-                    const uint32_t box = s_box[warp][slot];
-                    rl = (int)(box >> 20) + (it - s_start[warp][slot]);
+                    const uint32_t box = RW.box[slot];
+                    rl = (int)(box >> 20) + (it - RW.start[slot]);
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
-                        fs.x[k] = s_geo[warp][k][slot];
-                        fs.y[k] = s_geo[warp][3 + k][slot];
+                        fs.x[k] = RW.geo[k][slot];
+                        fs.y[k] = RW.geo[3 + k][slot];
                     }
                     yp = s_ndc[row0 + rl];
                     row_span(fs, yp, is, (int)(box & 1023u), (int)((box >> 10) & 1023u), &xi, &xb);
@@ -524,19 +532,19 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
                         xi++;
                     }
                     const uint32_t hits = __ballot_sync(0xffffffffu, hit);
-                    if (hit) s_queue[warp][qn + __popc(hits & lt_mask)] = ent;
+                    if (hit) RW.queue[qn + __popc(hits & lt_mask)] = ent;
                     qn += __popc(hits);
                     __syncwarp();
                     if (qn >= 32) {
                         qn -= 32;
-                        raster_hit(s_queue[warp][qn + lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_,
+                        raster_hit(RW.queue[qn + lane], RW.setup, RW.fn, zbuf, is, row0, s.near_,
                                    s.far_, P, s.faces, s.F);
                         __syncwarp();
                     }
                 }
             }
             if (lane < qn)
-                raster_hit(s_queue[warp][lane], s_setup[warp], s_fn[warp], zbuf, is, row0, s.near_, s.far_, P, s.faces,
+                raster_hit(RW.queue[lane], RW.setup, RW.fn, zbuf, is, row0, s.near_, s.far_, P, s.faces,
                            s.F);
             __syncwarp();
         }
@@ -1621,10 +1629,11 @@ int check_sil(const dh_sil* s) {
     return DH_OK;
 }
 
-size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-owns-a-pixel bitmap
+size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-owns-a-pixel bitmap + per-warp sets
     const int words = (2 * s.F + 31) / 32;
     return (size_t)kSH * raster_size(s) * sizeof(unsigned long long) +
-           (size_t)(words <= kOwnedSmemWords ? words : 0) * sizeof(uint32_t);
+           (size_t)(((words <= kOwnedSmemWords ? words : 0) + 3) / 4 * 4) * sizeof(uint32_t) +
+           (size_t)kRasterWarps * sizeof(RasterWarp) + (size_t)raster_size(s) * sizeof(float);
 }
 
 // pixels per frame the list path takes (dh_tune_set knob 0 lowers it: the tests force the bitmap path with it)
