@@ -130,23 +130,6 @@ def loss_weights(C):
     return dict(LW, lw_corr_obj=LW_CORR) if C > 0 else dict(LW)
 
 
-def build_model(seq):
-    from dynhor_b200 import synth
-    from dynhor_b200.jointopt import Joint_Optimizer
-    params = synth.to_object_parameters(seq)
-    B = len(params)
-    corr = torch.from_numpy(seq["correspondences"]) if "correspondences" in seq else None
-    return Joint_Optimizer(
-        correspondences=corr,
-        translations_object=torch.cat([p["translations"] for p in params]),
-        rotations_object=torch.cat([p["rotations"] for p in params]),
-        verts_object_og=torch.from_numpy(seq["verts"]),
-        faces_object=torch.from_numpy(seq["faces"]),
-        camintr_rois_object=torch.cat([p["K_roi"][:, 0] for p in params]),
-        target_masks_object=torch.cat([p["target_masks"] for p in params]),
-        int_scale_init=1, optimize_object_scale=False)
-
-
 # ---------------------------------------------------------------------------------------------- CPU arm
 def cpu_baseline(frames=None, iters=1, C=0):
     """The CPU oracle (kind "port": the reference cannot run on CPU) on a bounded sample of
@@ -178,6 +161,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     frames = max(2, min(cores // 2, 32))
     cb_rows = []
+    if args.corr is None:
+        args.corr = 10000
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(frames=2, iters=1, C=args.corr)
     t_total = 0.0
@@ -205,11 +190,55 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def make_range(start, stop, B_total, C, with_masks=True):
+    """Frames [start, stop) of the B_total-frame synthetic sequence (one period of the motion over the WHOLE
+    sequence): every frame's data depends on (seed, global frame number) only, so any rank -- or rank 0 alone, for
+    the sharded-equals-single check -- builds the same frames."""
+    from dynhor_b200 import synth
+    seq = synth.make_sequence(stop - start, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn if with_masks else None,
+                              period=B_total, frame_offset=start, traj_period=B_total)
+    if C > 0:
+        seq["correspondences"] = synth.make_correspondences(seq, C, seed=0, frame_offset=start, device="cuda")
+    return seq
+
+
+def model_from(seq):
+    from dynhor_b200.jointopt import Joint_Optimizer
+    corr = seq.get("correspondences")
+    if corr is not None and not torch.is_tensor(corr):
+        corr = torch.from_numpy(corr)
+    return Joint_Optimizer(
+        correspondences=corr,
+        translations_object=torch.from_numpy(seq["T_init"]),
+        rotations_object=torch.from_numpy(seq["R_init"]),
+        verts_object_og=torch.from_numpy(seq["verts"]),
+        faces_object=torch.from_numpy(seq["faces"]),
+        camintr_rois_object=torch.from_numpy(seq["K_roi"]),
+        target_masks_object=torch.from_numpy(seq["target_masks"]),
+        int_scale_init=1, optimize_object_scale=False)
+
+
+def host_parameters(seq, start, B_total, C):
+    """The per-frame dict list joint_optimize takes (pose_initializtion.py:460-471) for the whole sequence, with
+    pinned host tensors for the frames of `seq` (global numbers start ...) and references to one of them elsewhere
+    (frames another rank owns are never read by this rank)."""
+    from dynhor_b200 import synth
+    if C > 0 and torch.is_tensor(seq["correspondences"]):
+        seq = dict(seq, correspondences=seq["correspondences"].cpu().numpy())
+    local = synth.to_object_parameters(seq)
+    keys = ("rotations", "translations", "K_roi", "target_masks") + (("correspondences",) if C > 0 else ())
+    for p in local:
+        for k in keys:
+            p[k] = p[k].pin_memory()
+    full = [local[0]] * start + local + [local[-1]] * (B_total - start - len(local))
+    nbytes = lambda fr: sum(p[k].numel() * p[k].element_size() for p in fr for k in keys)  # noqa: E731
+    return full, nbytes
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from dynhor_b200 import synth
     from dynhor_b200.jointopt import FusedJointOpt, joint_optimize
-    from dynhor_b200.sharding import FrameShard
+    from dynhor_b200.sharding import FrameShard, allgather_equal, balanced_bounds, frame_costs_from_blocks
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,25 +246,16 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    Bl = args.frames_per_gpu
-    B_total = Bl * world
-    shard = FrameShard(rank, world, B_total)
-    period, offset = B_total, shard.start
-    if args.emulate_shard and world == 1:
-        # diagnostic: the frames rank r of a w-GPU run would own, timed stand-alone on one GPU (no halo)
-        r, w = (int(v) for v in args.emulate_shard.split("/"))
-        period, offset = Bl * w, Bl * r
-    # weak scaling: the object's motion repeats every `frames_per_gpu` frames, so every rank's range holds one
-    # full period of it (same amount of work per GPU at every N; --traj-period total: one period over the whole
-    # sequence, where the ranks' frame ranges differ in content and the slowest one sets the pace)
-    traj = Bl if args.traj_period == "per-gpu" else period
-    seq = synth.make_sequence(Bl, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=period,
-                              frame_offset=offset, traj_period=traj)
-    V, F = len(seq["verts"]), len(seq["faces"])
-    C = args.corr
+    scaling = args.scaling if args.scaling != "auto" else ("strong" if world > 1 else "single")
+    if scaling == "strong":          # BASELINE configs[4]: fixed total, 50k correspondences per frame pair
+        B_total = args.frames_total or 4096
+        C = 50000 if args.corr is None else args.corr
+        workload = "scaling sweep (BASELINE configs[4])"
+    else:                            # BASELINE configs[1] on one GPU; weak: the same number of frames per GPU
+        B_total = args.frames_per_gpu * world
+        C = 10000 if args.corr is None else args.corr
+        workload = "custom_shoes-shaped joint pose optimisation (BASELINE configs[1])"
     lw = loss_weights(C)
-    if C > 0:
-        seq["correspondences"] = synth.make_correspondences(seq, C, seed=shard.start)
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,8 +263,37 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- frame ranges: by count on one GPU; by measured cost across GPUs (one probe pass over the equal-count
+    #      ranges: the ranks' frames differ in content and every rank steps at the pace of the slowest range)
+    shard = FrameShard(rank, world, B_total)
+    if args.emulate_shard and world == 1:
+        # diagnostic: the frames rank r of a w-GPU run would own (by count), timed stand-alone on one GPU
+        r, w = (int(v) for v in args.emulate_shard.split("/"))
+        B_total = args.frames_total or args.frames_per_gpu * w
+        es = FrameShard(r, w, B_total)
+        seq = make_range(es.start, es.stop, B_total, C)
+        shard = FrameShard(0, 1, es.B)
+    else:
+        seq = None
+    probe_ms = None
+    if world > 1 and args.balance == "probe":
+        seq0 = make_range(shard.start, shard.stop, B_total, 0)
+        nblocks = max(1, min(16, (B_total // world) // 32))
+        with FusedJointOpt(model_from(seq0), dict(LW), LR, 0, shard=shard, keep_sum=1.0, exchange=False) as pr:
+            ms_blocks = torch.from_numpy(pr.probe(nblocks)).cuda()
+        ms_all = allgather_equal(ms_blocks, shard).cpu().numpy()
+        cost = np.concatenate([frame_costs_from_blocks(ms_all[r, :nblocks], shard.bounds[r], shard.bounds[r + 1])
+                               for r in range(world)])
+        probe_ms = [float(ms_all[r, :nblocks].sum()) for r in range(world)]
+        shard = shard.with_bounds(balanced_bounds(cost, world))
+        del seq0, pr
+    if seq is None:
+        seq = make_range(shard.start, shard.stop, B_total, C)
+    Bl = shard.B
+    V, F = len(seq["verts"]), len(seq["faces"])
+
     # ---- device-resident throughput: K fused iterations, inputs already in HBM
-    model = build_model(seq)
+    model = model_from(seq)
     fused = FusedJointOpt(model, lw, LR, args.steps + args.warmup + 64, shard=shard, halo=args.halo)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -259,7 +308,8 @@ def run_ours(args):
     fused.run(args.steps, use_graph=True)
     ev1.record()
     barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    ms_rank = ev0.elapsed_time(ev1)
+    ms = torch.tensor([ms_rank], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
@@ -268,7 +318,10 @@ def run_ours(args):
     hist = fused.history()
 
     # ---- per-kernel times (CUDA events on the launch stream) -> roofline of the dominant kernel
+    # (the eager profile runs whole iterations: in a sharded run every rank does it, in lockstep like the timed loop)
     prof = fused.profile(5)
+    fused.check_status()
+    halo_used = fused.halo_mode
     fused.release()
     ab = algorithmic_bytes_per_frame(V, S, C)
     top = max(("project", "raster", "backward", "pose_update", "corr"), key=lambda k: prof[k])
@@ -288,42 +341,77 @@ def run_ours(args):
                 "kernel_ms_all": prof,
                 "kernel_gbs_all": {k: ab[k] * Bl / (prof[k] / 1000.0) / 1e9
                                    for k in ("project", "raster", "backward", "pose_update", "corr") if prof[k] > 0},
-                "whole_step": {"algorithmic_bytes": ab["total"] * Bl,
-                               "achieved": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9,
-                               "frac": ab["total"] * Bl / (ms / args.steps / 1000.0) / 1e9 / peak}}
+                "whole_step": {"algorithmic_bytes": ab["total"] * B_total,
+                               "achieved": ab["total"] * B_total / (ms / args.steps / 1000.0) / 1e9,
+                               "frac": ab["total"] * B_total / (ms / args.steps / 1000.0) / 1e9 / peak / world},
+                "alu": alu_roofline(top, Bl, prof[top])}
 
-    # ---- end to end through the public call with HOST buffers (H2D of inputs, D2H of results inside the timing)
-    full = seq if world == 1 else None
+    # ---- sharded == single GPU, bit for bit: 3 iterations from the initial poses on all ranks, then the whole
+    #      sequence alone on rank 0 (which also gives the one-GPU time of this very configuration)
+    extra = {}
+    if world > 1 and not args.no_shard_check:
+        from dynhor_b200.sharding import allgather_frames
+        n_chk = 3
+        m2 = model_from(seq)
+        with FusedJointOpt(m2, lw, LR, n_chk, shard=shard, halo=args.halo) as f2:
+            f2.run(n_chk)
+            f2.check_status()
+        pose = torch.cat([m2.rotations_object.detach().reshape(Bl, 6), m2.translations_object.detach().reshape(Bl, 3)], 1)
+        pose = allgather_frames(pose, shard)
+        del m2, f2, model, fused
+        torch.cuda.empty_cache()
+        if rank == 0:
+            full = make_range(0, B_total, B_total, C)
+            m1 = model_from(full)
+            with FusedJointOpt(m1, lw, LR, n_chk + args.warmup + args.steps + 8) as f1:
+                f1.run(n_chk)
+                pose1 = torch.cat([m1.rotations_object.detach().reshape(B_total, 6),
+                                   m1.translations_object.detach().reshape(B_total, 3)], 1)
+                extra["shard_equals_single"] = bool(torch.equal(pose, pose1))
+                extra["shard_check"] = {"iterations": n_chk, "frames": B_total,
+                                        "max_abs_diff": float((pose - pose1).abs().max())}
+                n1 = max(3, min(args.steps, 10))
+                f1.run(3)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                f1.run(n1)
+                e1.record()
+                torch.cuda.synchronize()
+                ms1 = e0.elapsed_time(e1) / n1
+                extra["single_gpu_same_config"] = {"value": B_total / (ms1 / 1000.0), "unit": UNIT, "ms_per_step": ms1,
+                                                   "steps": n1, "note": "the whole sequence on rank 0 alone"}
+            del m1, f1, full
+            torch.cuda.empty_cache()
+        barrier()
+    elif world == 1:
+        del model, fused
+
+    # ---- end to end through the public call with HOST buffers (H2D of inputs, D2H of results inside the timing).
+    #      Every rank passes the whole-sequence list like run.py would; it holds real (pinned) tensors for the frames it
+    #      can end up owning (its equal-count range, its cost-balanced range and a margin).
     if world > 1:
-        # every rank holds the full-sequence host inputs, like run.py would; masks of other ranks are rebuilt
-        # from the all-gathered local masks
-        m_local = torch.from_numpy(seq["target_masks"]).cuda()
-        ms_all = [torch.empty_like(m_local) for _ in range(world)]
-        dist.all_gather(ms_all, m_local)
-        full = synth.make_sequence(B_total, H, W, mesh=MESH, seed=0, render_fn=None, period=B_total,
-                                   traj_period=traj)
-        full["target_masks"] = torch.cat(ms_all).cpu().numpy()
-        if C > 0:  # only this rank's frames are read by joint_optimize; the others are placeholders
-            full["correspondences"] = np.zeros((B_total, C, 6), np.float32)
-            full["correspondences"][shard.start:shard.stop] = seq["correspondences"]
-    params = synth.to_object_parameters(full)
-    keys = ("rotations", "translations", "K_roi", "target_masks") + (("correspondences",) if C > 0 else ())
-    for p in params:
-        for k in keys:
-            p[k] = p[k].pin_memory()
-    faces_b = np.stack([full["faces"]] * B_total)
+        eq = FrameShard(rank, world, B_total)
+        lo, hi = max(0, min(eq.start, shard.start) - 32), min(B_total, max(eq.stop, shard.stop) + 32)
+        hseq = seq if (lo, hi) == (shard.start, shard.stop) else make_range(lo, hi, B_total, C)
+    else:
+        lo, hseq = 0, seq
+    params, nbytes = host_parameters(hseq, lo, B_total, C)
+    del hseq
+    faces_b = np.stack([seq["faces"]] * B_total)     # run.py:158
     e2e_iters = args.steps
-    h2d = sum(p[k].numel() * p[k].element_size() for p in params[shard.start:shard.stop] for k in keys)
-    h2d += full["verts"].nbytes + faces_b.nbytes
-    joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=lw, num_iterations=2, lr=LR)
+    kw = dict(objvertices=seq["verts"], objfaces=faces_b, loss_weights=lw, lr=LR, board=None, halo=args.halo,
+              balance=args.balance)
+    joint_optimize(params, num_iterations=2, **kw)
     barrier()
     t0 = time.perf_counter()
-    model2, evo = joint_optimize(params, objvertices=full["verts"], objfaces=faces_b, loss_weights=lw,
-                                 num_iterations=e2e_iters, lr=LR, board=None)
+    model2, evo = joint_optimize(params, num_iterations=e2e_iters, **kw)
     rot_h = model2.rotations_object.detach().cpu()
     tr_h = model2.translations_object.detach().cpu()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    own = model2.frame_shard
+    h2d = nbytes(params[own.start:own.stop]) + seq["verts"].nbytes + seq["faces"].astype(np.int32).nbytes
     d2h = rot_h.numel() * 4 + tr_h.numel() * 4 + 4 * 8 * e2e_iters
     dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -333,29 +421,45 @@ def run_ours(args):
            "d2h_bytes_per_step": d2h / e2e_iters, "iterations": e2e_iters, "seconds": dt,
            "final_loss": evo["loss"][-1]}
 
+    secondary = {}
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb, _ = cpu_baseline(C=C)
+    if rank == 0 and world == 1:
+        if not args.no_secondary and not args.emulate_shard:
+            del model2
+            torch.cuda.empty_cache()
+            try:
+                secondary["dino"] = dino_numbers(max(3, min(args.steps, 20)))[0]
+            except Exception as exc:  # the headline line must not die with a secondary workload
+                secondary["dino"] = {"error": repr(exc)}
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_baseline(C=C)
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if scaling == "strong" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"custom_shoes-shaped joint pose optimisation, {Bl} frames per GPU "
-                                   f"({B_total} total) {H}x{W}, {MESH} mesh (V={V}, F={F}), 256x256 ROI rendered "
-                                   f"512x512 + 2x2 pool, {C} correspondences per frame, lw_sil 1 / lw_smooth 10"
-                                   + (f" / lw_corr {LW_CORR}" if C > 0 else "") + ", lr 1e-4 (BASELINE configs[1])",
-                       "frames_per_gpu": Bl, "frames_total": B_total, "correspondences_per_frame": C,
+            "config": {"workload": f"{workload}: {B_total} frames {H}x{W}"
+                                   + (f", frame-sharded over {world} GPUs" if world > 1 else "")
+                                   + f", {MESH} mesh (V={V}, F={F}), 256x256 ROI rendered 512x512 + 2x2 pool, {C} "
+                                   f"correspondences per frame, lw_sil 1 / lw_smooth 10"
+                                   + (f" / lw_corr {LW_CORR}" if C > 0 else "") + ", lr 1e-4",
+                       "frames_total": B_total, "frames_this_rank": Bl, "correspondences_per_frame": C,
                        "parallelism": f"frame-shard x{world}",
-                       "trajectory_period_frames": traj,
-                       "halo": fused.halo_mode,
-                       "l2": "per-step working set (face-index maps 1 MB/frame + bins) exceeds the 126 MB L2; "
+                       "partition": {"by": args.balance if world > 1 else "single", "bounds": shard.bounds,
+                                     "probe_ms_per_equal_range": probe_ms},
+                       "trajectory_period_frames": B_total,
+                       "halo": halo_used,
+                       "l2": "per-step working set (face-index maps + bins, > 1 MB/frame) exceeds the 126 MB L2; "
                              "no explicit flush", "cuda_graph": True},
             "roofline": roofline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": (9 + (1 if C > 0 else 0)) * args.steps,
             "loss_first_last": [hist["loss"][0], hist["loss"][-1]],
             "iou_first_last": [hist["iou_object"][0], hist["iou_object"][-1]],
         }
+        out.update(extra)
+        if secondary:
+            out["secondary"] = secondary
         if cb is not None:
             out["cpu_baseline"] = cb
         print(json.dumps(out))
@@ -363,21 +467,41 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_dino(args):
-    """Secondary workload (BASELINE configs[3]): DINO ViT-S/14 patch-feature matching, 1k templates x 300 frames,
-    bf16 similarity GEMM (K = 1369*384) + fused top-10.  One JSON line; `value` = template-frame pairs / second."""
-    from dynhor_b200 import synth
+def alu_roofline(kernel, frames, kernel_ms):
+    """Instruction roofline beside the HBM one: thread-instructions per frame of the kernel from the committed ncu
+    capture of this round (profiles/alu.json, written by tools/ncu_summary.py) against the SM's issue rate."""
+    path = os.path.join(ROOT, "profiles", "alu.json")
+    try:
+        a = json.load(open(path))[kernel]
+    except Exception:
+        return None
+    sm_mhz = 1965.0
+    try:
+        sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        pass
+    peak = 148 * 4 * 32 * sm_mhz * 1e6            # thread-instructions / s: 148 SMs x 4 schedulers x 32 lanes
+    ach = a["thread_inst_per_frame"] * frames / (kernel_ms / 1000.0)
+    return {"thread_inst_per_frame": a["thread_inst_per_frame"], "achieved_inst_per_s": ach, "peak": peak,
+            "frac": ach / peak, "issue_pct": a.get("issue_pct"), "lanes": a.get("lanes"),
+            "source": a.get("source")}
+
+
+def dino_numbers(steps, warmup=3):
+    """BASELINE configs[3]: DINO ViT-S/14 patch-feature matching, 1k templates x 300 frames, bf16 similarity GEMM
+    (K = 1369*384) with the top-10 selection fused into it.  Returns the numbers of one JSON object."""
+    import ctypes
+    from dynhor_b200 import _lib, synth
     from dynhor_b200.dino_match import build_bank, dino_cos_topk
     N, Fm, P, D, k = 1000, 300, 1369, 384, 10
-    torch.cuda.set_device(0)
     d = synth.make_dino_features(N, Fm, P, D, seed=0, device="cuda")
     tb = build_bank(d["templ"])
     fb = build_bank(d["frames"], d["masks"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         dino_cos_topk(fb, tb, k)
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()                      # 256 MB write: evicts the banks from the 126 MB L2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -395,19 +519,11 @@ def run_dino(args):
     except Exception:
         pass
     ok = bool(torch.equal(i[:, 0].cpu(), d["match"]))
-    import ctypes
-    from dynhor_b200 import _lib
     plan = (ctypes.c_int32 * 8)()
     _lib.load().dh_dino_plan_info(N, Fm, P * D, plan)
-    # CPU baseline: the reference expression verbatim on a bounded sample of frames
-    from oracle import dino_oracle
-    nf = 2
-    t0 = time.perf_counter()
-    dino_oracle.dino_cos_topk(d["frames"][:nf].cpu(), d["masks"][:nf].cpu(), d["templ"].cpu(), k)
-    cpu_s = (time.perf_counter() - t0) / nf
-    print(json.dumps({
+    return {
         "metric": "DINO template-frame pairs scored / second (bf16 GEMM + fused top-k)", "value": N * Fm / (ms / 1e3),
-        "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "unit": "pairs/s", "n_gpus": 1, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "DINO ViT-S/14 patch-feature pose initialisation: 1000 templates x 300 frames, "
                                "P=1369, D=384, top-10 (BASELINE configs[3])", "l2": "256 MB flush between steps"},
@@ -415,11 +531,24 @@ def run_dino(args):
                      "frac": bytes_ / (ms / 1e3) / 1e9 / hbm, "peak_source": f"{kind} hbm_gbs",
                      "tensor": {"achieved_tflops": flops / (ms / 1e3) / 1e12, "peak_tflops": tf_peak,
                                 "frac": flops / (ms / 1e3) / 1e12 / tf_peak}},
-        "cpu_baseline": {"value": N / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
-                         "sample": f"{nf} frames x 1000 templates, pose_initializtion.py:295-296 verbatim + topk"},
         "plan": dict(zip(["m_tiles", "n_pairs", "k_slices", "kblocks", "kb_per_slice", "cluster", "ctas_sized_for",
                           "ldc"], list(plan))),
-        "planted_match_rank0": ok, "gpu_launches": 3 * args.steps}))
+        "planted_match_rank0": ok, "gpu_launches": 3 * steps}, d
+
+
+def run_dino(args):
+    """Secondary workload as its own line (`--workload dino`); `value` = template-frame pairs / second."""
+    torch.cuda.set_device(0)
+    out, d = dino_numbers(args.steps, args.warmup)
+    # CPU baseline: the reference expression verbatim on a bounded sample of frames
+    from oracle import dino_oracle
+    nf, N, k = 2, 1000, 10
+    t0 = time.perf_counter()
+    dino_oracle.dino_cos_topk(d["frames"][:nf].cpu(), d["masks"][:nf].cpu(), d["templ"].cpu(), k)
+    cpu_s = (time.perf_counter() - t0) / nf
+    out["cpu_baseline"] = {"value": N / cpu_s, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
+                           "sample": f"{nf} frames x 1000 templates, pose_initializtion.py:295-296 verbatim + topk"}
+    print(json.dumps(out))
 
 
 def run_preprocess(args):
@@ -507,14 +636,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=300)
-    ap.add_argument("--corr", type=int, default=10000,
-                    help="correspondences per frame (builder-defined reprojection term; 0 = the reference's two terms)")
+    ap.add_argument("--corr", type=int, default=None,
+                    help="correspondences per frame (builder-defined reprojection term; 0 = the reference's two terms; "
+                         "default 10000, 50000 in the strong-scaling sweep)")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="auto: one GPU = BASELINE configs[1] (300 frames); several GPUs = strong scaling on configs[4] "
+                         "(4096 frames, 50k correspondences, fixed total).  weak: --frames-per-gpu frames on every GPU")
+    ap.add_argument("--frames-total", type=int, default=0, help="strong scaling: frames of the whole sequence (4096)")
+    ap.add_argument("--balance", default="probe", choices=["probe", "count"],
+                    help="frame ranges of equal measured cost (one probe pass) or of equal frame count")
+    ap.add_argument("--no-shard-check", action="store_true",
+                    help="skip the sharded == single-GPU comparison (and the one-GPU time of the same configuration)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the DINO numbers in the one-GPU line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mesh", default=MESH, choices=["uv50x100", "uv100x200"],
                     help="uv100x200 = the 20k-vertex mesh of BASELINE configs[2]")
     ap.add_argument("--camera", default=f"{H}x{W}", help="full-frame camera HxW (configs[2]: 1080x1920)")
-    ap.add_argument("--traj-period", default="per-gpu", choices=["per-gpu", "total"],
-                    help="frames after which the synthetic motion repeats: frames-per-gpu (default) or the whole sequence")
     ap.add_argument("--emulate-shard", default="", help="r/w: time the frames of rank r of a w-GPU run on one GPU")
     ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino", "preprocess"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])

@@ -48,6 +48,9 @@ class DhJointOpt(ctypes.Structure):
         ("step", c_p), ("hist", c_p), ("max_iters", c_i),
         ("halo_prev", c_p), ("halo_next", c_p),
         ("mailbox", c_p), ("peer_prev", c_p), ("peer_next", c_p),
+        ("tick_base", c_i), ("halo_timeout_ms", c_i), ("status", c_p),
+        ("rank", c_i), ("world", c_i), ("scale_mode", c_i),
+        ("peers", c_p * 16), ("scale_part", c_p),
         ("B_total", c_i),
         ("keep_sum", c_d), ("lw_sil", c_d), ("lw_smooth", c_d), ("lr", c_d),
         ("optimize_scale", c_i),
@@ -81,6 +84,8 @@ SIGNATURES = {
     "dh_jointopt_grads": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_p, c_p, c_p]),
     "dh_jointopt_profile": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
     "dh_jointopt_release": (c_i, [ctypes.POINTER(DhJointOpt)]),
+    "dh_jointopt_probe": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
+    "dh_scale_apply": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_i, c_p]),
     "dh_dev_alloc": (c_i, [ctypes.POINTER(c_p), c_l]),
     "dh_dev_free": (c_i, [c_p]),
     "dh_memcpy_d2d": (c_i, [c_p, c_p, c_l, c_p]),
@@ -94,6 +99,11 @@ SIGNATURES = {
     "dh_dino_prescale": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "dh_roi_process": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
+
+MAILBOX_WORDS = 512      # DH_MAILBOX_WORDS
+MAX_RANKS = 16           # DH_MAX_RANKS
+SCALE_LOCAL, SCALE_P2P, SCALE_DEFERRED = 0, 1, 2
+STATUS_HALO_TIMEOUT = 1
 
 _LIB = None
 

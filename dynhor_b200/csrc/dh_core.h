@@ -662,6 +662,30 @@ DH_HD void corr_record(const float* rec, const float* R, const float* T, float s
     acc[12] += w * rho;
 }
 
+// ---------------------------------------------------------------------------------------------- exact sums
+// 128-bit fixed point, value = hi + lo * 2^-64 (hi: signed integer part, floor; lo: fraction).  Adding such numbers
+// is exact and associative, so a sum of doubles accumulated this way does not depend on the order or grouping of
+// the terms: the gradient of the shared object scale (jointopt.py:42-46) comes out bit-identical whether the frames
+// sit on one GPU or are sharded over several.  Doubles of magnitude < 2^62 convert exactly down to 2^-64.
+struct Fx128 { long long hi; unsigned long long lo; };
+DH_HD Fx128 fx_from_double(double x) {
+    Fx128 r;
+    r.hi = 0; r.lo = 0ull;
+    if (!(fabs(x) < 4.0e18)) return r;   // NaN / inf / absurd magnitudes contribute nothing
+    const double fl = floor(x);
+    const double fr = x - fl;            // [0,1]; rounds up to 1 only for a negative x below 2^-54 in magnitude
+    r.hi = (long long)fl + ((fr >= 1.0) ? 1 : 0);
+    r.lo = (fr >= 1.0) ? 0ull : (unsigned long long)(fr * 18446744073709551616.0);   // exact scaling by 2^64
+    return r;
+}
+DH_HD Fx128 fx_add(Fx128 a, Fx128 b) {
+    Fx128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + ((r.lo < a.lo) ? 1 : 0);
+    return r;
+}
+DH_HD double fx_to_double(Fx128 a) { return (double)a.hi + (double)a.lo * 5.421010862427522e-20; }  // 2^-64
+
 // ---------------------------------------------------------------------------------------------- Adam
 // torch.optim.Adam, single-tensor path, defaults betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad
 // (jointopt.py:135-141).  bc1 = 1 - beta1^t, bc2s = sqrt(1 - beta2^t): python doubles, as torch computes them.

@@ -18,6 +18,7 @@
 // Compiled with --fmad=false: see dh_core.h for the fp32 contract.
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "dh_common.h"
@@ -1446,30 +1447,54 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ pose kernels
-// ---- peer-to-peer halo mailboxes (layout: include/dynhor_b200.h)
-__device__ __forceinline__ float* mb_slot(float* mb, int side, int parity) { return mb + (side * 2 + parity) * 16; }
-__device__ __forceinline__ volatile int* mb_flag(float* mb, int side, int parity) {
-    return reinterpret_cast<volatile int*>(mb + 64) + side * 2 + parity;
+// ---- peer-to-peer mailboxes (layout: include/dynhor_b200.h)
+__device__ __forceinline__ float* mb_slot(float* mb, int side, int tick) { return mb + (side * 4 + (tick & 3)) * 16; }
+__device__ __forceinline__ volatile int* mb_flag(float* mb, int side, int tick) {
+    return reinterpret_cast<volatile int*>(mb + 128) + side * 4 + (tick & 3);
 }
-// wait until the neighbour has published the pose valid for iteration `it`, then copy it out (9 floats)
-__device__ void mb_wait_read(float* mb, int side, int it, float* out9) {
-    volatile int* flag = mb_flag(mb, side, it & 1);
-    const long long t0 = clock64();
-    while (*flag < it) {
-        if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s: a lost neighbour aborts instead of hanging the GPU
-        __nanosleep(64);
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag has reached `tick` (wrap-safe).  Wall-clock bounded: after timeout_ms (default 60 s) -- or at once
+// when an earlier wait of this run already failed -- DH_STATUS_HALO_TIMEOUT goes into *status and the caller carries
+// on with whatever the slot holds, so that the kernel (and the graph) always terminates; the host raises after
+// the run.  A neighbour that is merely slow (lazy peer mapping, graph instantiation, a debugger) is waited for.
+__device__ bool mb_wait(volatile int* flag, int tick, int timeout_ms, int32_t* status) {
+    if (status != nullptr && *reinterpret_cast<volatile int32_t*>(status) != 0) return false;
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long limit = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 60000) * 1000000ull;
+    while (*flag - tick < 0) {
+        if (globaltimer_ns() - t0 > limit) {
+            if (status != nullptr) atomicExch(status, DH_STATUS_HALO_TIMEOUT);
+            return false;
+        }
+        __nanosleep(128);
     }
     __threadfence_system();
-    const volatile float* src = mb_slot(mb, side, it & 1);
+    return true;
+}
+// wait until the neighbour has published the pose valid for `tick`, then copy it out (9 floats)
+__device__ void mb_wait_read(const dh_jointopt& p, int side, int tick, float* out9) {
+    mb_wait(mb_flag(p.mailbox, side, tick), tick, p.halo_timeout_ms, p.status);
+    const volatile float* src = mb_slot(p.mailbox, side, tick);
     for (int i = 0; i < 9; i++) out9[i] = src[i];
 }
-// publish this rank's boundary pose for iteration `it` into a neighbour's mailbox
-__device__ void mb_publish(float* peer, int side, int it, const float* rot6d, const float* trans) {
-    volatile float* dst = mb_slot(peer, side, it & 1);
+// publish this rank's boundary pose for `tick` into a neighbour's mailbox
+__device__ void mb_publish(float* peer, int side, int tick, const float* rot6d, const float* trans) {
+    volatile float* dst = mb_slot(peer, side, tick);
     for (int i = 0; i < 6; i++) dst[i] = rot6d[i];
     for (int i = 0; i < 3; i++) dst[6 + i] = trans[i];
     __threadfence_system();
-    *mb_flag(peer, side, it & 1) = it;
+    *mb_flag(peer, side, tick) = tick;
+}
+// scale slots: one exact partial gradient per (tick & 3, rank)
+__device__ __forceinline__ volatile unsigned long long* mb_scale_slot(float* mb, int tick, int rank) {
+    return reinterpret_cast<volatile unsigned long long*>(mb + 136 + ((tick & 3) * DH_MAX_RANKS + rank) * 4);
+}
+__device__ __forceinline__ volatile int* mb_scale_flag(float* mb, int tick, int rank) {
+    return reinterpret_cast<volatile int*>(mb + 392) + (tick & 3) * DH_MAX_RANKS + rank;
 }
 
 __global__ void k_pose_prep(const dh_jointopt p) {
@@ -1484,14 +1509,14 @@ __global__ void k_pose_prep(const dh_jointopt p) {
     const float* hn = p.halo_next;
     float hbuf[2][9];
     if (p.mailbox != nullptr) {  // P2P mode: the neighbours' poses arrive in the mailbox
-        const int it = *p.step;
+        const int tick = p.tick_base + *p.step;
         hp = hn = nullptr;
         if (p.peer_prev != nullptr) {
-            if (b == 0) mb_wait_read(p.mailbox, 0, it, hbuf[0]);
+            if (b == 0) mb_wait_read(p, 0, tick, hbuf[0]);
             hp = hbuf[0];
         }
         if (p.peer_next != nullptr) {
-            if (b == B - 1) mb_wait_read(p.mailbox, 1, it, hbuf[1]);
+            if (b == B - 1) mb_wait_read(p, 1, tick, hbuf[1]);
             hn = hbuf[1];
         }
     }
@@ -1572,46 +1597,117 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
                     step_tr, bc2s);
     // P2P halo: the updated boundary poses go straight into the neighbours' mailboxes, valid for iteration t
     if (p.mailbox != nullptr) {
-        if (b == 0 && p.peer_prev != nullptr) mb_publish(p.peer_prev, 1, t, p.rot6d + 6 * b, p.trans + 3 * b);
-        if (b == p.sil.B - 1 && p.peer_next != nullptr) mb_publish(p.peer_next, 0, t, p.rot6d + 6 * b, p.trans + 3 * b);
+        const int tick = p.tick_base + t;
+        if (b == 0 && p.peer_prev != nullptr) mb_publish(p.peer_prev, 1, tick, p.rot6d + 6 * b, p.trans + 3 * b);
+        if (b == p.sil.B - 1 && p.peer_next != nullptr)
+            mb_publish(p.peer_next, 0, tick, p.rot6d + 6 * b, p.trans + 3 * b);
     }
 }
 
-// One CTA.  mode 0: history row + scale update + step++.  mode 1: history row only (grad_scale written).
-// mode 2: history row only.
+// One CTA.  mode 0: history row + scale update + step++.  mode 1: row max_iters only (grad_scale written).
+// mode 2: row max_iters only (forward-only evaluation).
+// The scale gradient (one number for the whole sequence, jointopt.py:42-46) is summed exactly (Fx128): first over
+// this rank's frames, then -- DH_SCALE_P2P -- over the ranks, every rank storing its partial into all mailboxes and
+// adding the `world` partials up in rank order, so that all ranks apply the same bits and a sharded run equals the
+// single-GPU run.
 __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int mode, float* __restrict__ grad_scale) {
-    __shared__ double red[kThreads / 32][5];
-    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < p.sil.B; b += kThreads)
-        for (int i = 0; i < 5; i++) a[i] += p.frame_terms[(size_t)b * 8 + i];
-    for (int i = 0; i < 5; i++)
-        for (int o = 16; o > 0; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-    if ((threadIdx.x & 31) == 0)
-        for (int i = 0; i < 5; i++) red[threadIdx.x >> 5][i] = a[i];
+    __shared__ double red[kThreads / 32][4];
+    __shared__ Fx128 redg[kThreads / 32];
+    __shared__ Fx128 s_parts[DH_MAX_RANKS];
+    double a[4] = {0.0, 0.0, 0.0, 0.0};   // 16*SSE, iou, pair_sse, corr loss
+    Fx128 g;
+    g.hi = 0; g.lo = 0ull;
+    for (int b = threadIdx.x; b < p.sil.B; b += kThreads) {
+        const double* ft = p.frame_terms + (size_t)b * 8;
+        a[0] += ft[0]; a[1] += ft[1]; a[2] += ft[2]; a[3] += ft[4];
+        g = fx_add(g, fx_from_double(ft[3]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < 4; i++) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        Fx128 t;
+        t.hi = __shfl_xor_sync(0xffffffffu, g.hi, o);
+        t.lo = __shfl_xor_sync(0xffffffffu, g.lo, o);
+        g = fx_add(g, t);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int i = 0; i < 4; i++) red[threadIdx.x >> 5][i] = a[i];
+        redg[threadIdx.x >> 5] = g;
+    }
     __syncthreads();
+    const int step = *p.step;
     if (threadIdx.x == 0) {
-        double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int w = 0; w < kThreads / 32; w++)
-            for (int i = 0; i < 5; i++) t[i] += red[w][i];
-        const int step = *p.step;
-        if (step < p.max_iters) {
-            double* h = p.hist + (size_t)step * 4;
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        Fx128 tg;
+        tg.hi = 0; tg.lo = 0ull;
+        for (int w = 0; w < kThreads / 32; w++) {
+            for (int i = 0; i < 4; i++) t[i] += red[w][i];
+            tg = fx_add(tg, redg[w]);
+        }
+        const int row = (mode == 0) ? step : p.max_iters;
+        if (mode != 0 || step < p.max_iters) {
+            double* h = p.hist + (size_t)row * 4;
             const double N = (double)(p.B_total - 1) * (double)p.sil.V * 3.0;
             h[0] = (p.B_total > 1) ? t[2] / N : 0.0;
             h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
             h[2] = t[1] / (double)p.B_total;
-            h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0) ? t[4] / p.corr.w_sum : 0.0;
+            h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0) ? t[3] / p.corr.w_sum : 0.0;
         }
-        if (mode == 1 && grad_scale != nullptr) grad_scale[0] = (float)t[3];
-        if (mode == 0) {
-            if (p.optimize_scale) {
+        redg[0] = tg;   // this rank's exact partial
+        if (mode == 1 && grad_scale != nullptr) grad_scale[0] = (float)fx_to_double(tg);
+    }
+    if (mode != 0) return;
+    __syncthreads();
+    if (p.optimize_scale) {
+        const Fx128 mine = redg[0];
+        if (p.scale_mode == DH_SCALE_P2P) {
+            const int tick = p.tick_base + step + 1;
+            const int r = threadIdx.x;
+            if (r < p.world) {
+                volatile unsigned long long* dst = mb_scale_slot(p.peers[r], tick, p.rank);
+                dst[0] = (unsigned long long)mine.hi;
+                dst[1] = mine.lo;
+                __threadfence_system();
+                *mb_scale_flag(p.peers[r], tick, p.rank) = tick;
+                mb_wait(mb_scale_flag(p.mailbox, tick, r), tick, p.halo_timeout_ms, p.status);
+                const volatile unsigned long long* src = mb_scale_slot(p.mailbox, tick, r);
+                s_parts[r].hi = (long long)src[0];
+                s_parts[r].lo = src[1];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            if (p.scale_mode == DH_SCALE_DEFERRED) {
+                p.scale_part[0] = (unsigned long long)mine.hi;
+                p.scale_part[1] = mine.lo;
+            } else {
+                Fx128 tot = mine;
+                if (p.scale_mode == DH_SCALE_P2P) {
+                    tot.hi = 0; tot.lo = 0ull;
+                    for (int r = 0; r < p.world; r++) tot = fx_add(tot, s_parts[r]);
+                }
                 float step_sz, bc2s;
                 adam_bias(step + 1, p.lr, &step_sz, &bc2s);
-                adam_update(p.scale, &p.adam_mv_scale[0], &p.adam_mv_scale[1], (float)t[3], step_sz, bc2s);
+                adam_update(p.scale, &p.adam_mv_scale[0], &p.adam_mv_scale[1], (float)fx_to_double(tot), step_sz, bc2s);
             }
-            *p.step = step + 1;
         }
     }
+    if (threadIdx.x == 0) *p.step = step + 1;
+}
+
+// DH_SCALE_DEFERRED: the partials of all ranks (gathered by the host side) -> Adam step of the scale.
+__global__ void k_scale_apply(const dh_jointopt p, const unsigned long long* __restrict__ parts, int world) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fx128 tot;
+    tot.hi = 0; tot.lo = 0ull;
+    for (int r = 0; r < world; r++) {
+        Fx128 t;
+        t.hi = (long long)parts[2 * r];
+        t.lo = parts[2 * r + 1];
+        tot = fx_add(tot, t);
+    }
+    float step_sz, bc2s;
+    adam_bias(*p.step, p.lr, &step_sz, &bc2s);   // *step was already advanced by the iteration's k_finalize
+    adam_update(p.scale, &p.adam_mv_scale[0], &p.adam_mv_scale[1], (float)fx_to_double(tot), step_sz, bc2s);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1675,10 +1771,52 @@ int launch_forward_common(const dh_sil& s, cudaStream_t st) {
 struct IterEvents { cudaEvent_t ev[9]; };
 #define DH_REC(i) do { if (evs) cudaEventRecord(evs->ev[i], st); } while (0)
 
+// The silhouette term's kernels of one iteration for the plan's frames: projection, binning, raster (+ fused loss
+// epilogue) and, unless forward_only, the per-frame map kernel and the two backward kernels.
+int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st, IterEvents* evs = nullptr) {
+    const dh_sil& s = p.sil;
+    const int is = raster_size(s), nstrips = is / kSH, B = s.B;
+    dim3 gv((s.V + kThreads - 1) / kThreads, B);
+    k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
+                                              reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
+                                              p.loss_counts, s.owned, (2 * s.F + 31) / 32);
+    DH_LAUNCH_OK("k_project");
+    DH_REC(2);
+    int rc = launch_forward_common(s, st);
+    if (rc) return rc;
+    DH_REC(3);
+    const size_t zb = raster_smem_bytes(s);
+    rc = set_smem(k_raster<true>, zb);
+    if (rc) return rc;
+    // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
+    const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
+    k_raster<true><<<dim3(nstrips, B), kRasterThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
+    DH_LAUNCH_OK("k_raster");
+    DH_REC(4);
+    if (forward_only) return DH_OK;
+    rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
+    if (rc) return rc;
+    k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
+    DH_LAUNCH_OK("k_neg_maps");
+    const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
+    rc = set_smem(k_backward<true, true>, sl);
+    if (rc) return rc;
+    rc = set_smem(k_backward<true, false>, sb);
+    if (rc) return rc;
+    k_backward<true, true><<<dim3(p.nchunks, B), kBwdThreads, sl, st>>>(
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0);
+    DH_LAUNCH_OK("k_backward<lists>");
+    // frames with more contributing pixels than the lists hold (only these CTAs do any work)
+    k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1);
+    DH_LAUNCH_OK("k_backward<bitmaps>");
+    return DH_OK;
+}
+
 int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
                      cudaStream_t st, IterEvents* evs = nullptr) {
     const dh_sil& s = p.sil;
-    const int is = raster_size(s), nstrips = is / kSH, B = s.B;
+    const int B = s.B;
     const bool with_sil = p.lw_sil > 0.0;
     DH_REC(0);
     k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
@@ -1692,41 +1830,8 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
     }
     DH_REC(8);
     if (with_sil) {
-        dim3 gv((s.V + kThreads - 1) / kThreads, B);
-        k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
-                                                  reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
-                                                  p.loss_counts, s.owned, (2 * s.F + 31) / 32);
-        DH_LAUNCH_OK("k_project");
-        DH_REC(2);
-        int rc = launch_forward_common(s, st);
+        const int rc = launch_sil_kernels(p, mode == 2, st, evs);
         if (rc) return rc;
-        DH_REC(3);
-        const size_t zb = raster_smem_bytes(s);
-        rc = set_smem(k_raster<true>, zb);
-        if (rc) return rc;
-        // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
-        const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
-        k_raster<true><<<dim3(nstrips, B), kRasterThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
-        DH_LAUNCH_OK("k_raster");
-        DH_REC(4);
-        if (mode != 2) {
-            rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
-            if (rc) return rc;
-            k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
-            DH_LAUNCH_OK("k_neg_maps");
-            const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
-            rc = set_smem(k_backward<true, true>, sl);
-            if (rc) return rc;
-            rc = set_smem(k_backward<true, false>, sb);
-            if (rc) return rc;
-            k_backward<true, true><<<dim3(p.nchunks, B), kBwdThreads, sl, st>>>(
-                s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0);
-            DH_LAUNCH_OK("k_backward<lists>");
-            // frames with more contributing pixels than the lists hold (only these CTAs do any work)
-            k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
-                s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1);
-            DH_LAUNCH_OK("k_backward<bitmaps>");
-        }
     } else {
         DH_REC(2); DH_REC(3); DH_REC(4);
     }
@@ -1738,6 +1843,38 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
     DH_LAUNCH_OK("k_finalize");
     DH_REC(7);
     return DH_OK;
+}
+
+// The plan restricted to frames [b0, b0 + nb) of its range: every per-frame array moved forward by b0 frames (the
+// probe's blocks).  Only what launch_sil_kernels touches is meaningful in the result.
+dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
+    dh_jointopt q = p;
+    dh_sil& s = q.sil;
+    const size_t o = (size_t)b0;
+    const int is = raster_size(p.sil), nstrips = is / kSH, wpr = is >> 5, S = p.sil.S, wprp = (S + 31) >> 5;
+    const int V = p.sil.V, F = p.sil.F;
+    s.B = nb;
+    s.K += o * 9;
+    s.proj += o * V * 4;
+    s.bin_count += o * nstrips * 2;
+    s.bins += o * nstrips * 2 * F;
+    s.fidx += o * is * is;
+    s.alpha_bits += o * is * wpr;
+    s.pos_pool += o * S * wprp;
+    s.neg_pool += o * S * wprp;
+    s.gpool += o * S * S;
+    s.gmax += o;
+    s.owned += o * ((2 * F + 31) / 32);
+    s.negT += o * is * wpr;
+    s.row_rng += o * 2 * is;
+    s.neg_lists += o * 2 * kNLAxis;
+    q.mask_tri += o * S * S;
+    q.rot6d += o * 6;
+    q.trans += o * 3;
+    q.Rmat += o * 9;
+    q.loss_counts += o * 4;
+    q.partials += o * p.nchunks * 16;
+    return q;
 }
 
 int check_plan(const dh_jointopt* p) {
@@ -1754,6 +1891,16 @@ int check_plan(const dh_jointopt* p) {
     DH_REQUIRE(p->nchunks >= 1 && (p->sil.F + p->nchunks - 1) / p->nchunks <= kChunkFaces,
                "nchunks must be >= ceil(F / 1024)");
     DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
+    DH_REQUIRE(p->max_iters >= 0, "max_iters < 0");
+    DH_REQUIRE(p->scale_mode == DH_SCALE_LOCAL || p->scale_mode == DH_SCALE_P2P || p->scale_mode == DH_SCALE_DEFERRED,
+               "bad scale_mode");
+    if (p->optimize_scale && p->scale_mode == DH_SCALE_P2P) {
+        DH_REQUIRE(p->mailbox != nullptr && p->world >= 1 && p->world <= DH_MAX_RANKS && p->rank >= 0 &&
+                       p->rank < p->world, "scale_mode P2P needs a mailbox and 1 <= world <= DH_MAX_RANKS");
+        for (int r = 0; r < p->world; r++) DH_REQUIRE(p->peers[r] != nullptr, "scale_mode P2P: peers[%d] is NULL", r);
+    }
+    if (p->optimize_scale && p->scale_mode == DH_SCALE_DEFERRED)
+        DH_REQUIRE(p->scale_part != nullptr, "scale_mode DEFERRED needs scale_part");
     DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
     if (p->corr.records != nullptr && p->corr.lw_corr > 0.0) {
         DH_REQUIRE(p->corr.partials != nullptr && p->corr.C > 0 && p->corr.nslots > 0, "corr: bad plan");
@@ -1762,10 +1909,20 @@ int check_plan(const dh_jointopt* p) {
     return DH_OK;
 }
 
+// Cached graph executables, keyed by the whole plan (every pointer and scalar a captured launch bakes in), the
+// device it was captured on and the tuning knobs read at capture time.  Guarded by a mutex (one host thread per GPU
+// is the convention, but several GPUs may be driven from one process); bounded: the oldest entry goes first.
 struct GraphEntry {
     dh_jointopt plan;
+    int device;
+    int list_cap;
     cudaGraphExec_t exec;
 };
+constexpr size_t kGraphCacheMax = 32;
+std::mutex& graph_mutex() {
+    static std::mutex m;
+    return m;
+}
 std::vector<GraphEntry>& graph_cache() {
     static std::vector<GraphEntry> c;
     return c;
@@ -1848,7 +2005,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
 int dh_tune_set(int32_t knob, int32_t value) {
     DH_REQUIRE(knob == 0, "dh_tune_set: unknown knob");
     g_neg_list_cap = value < 0 ? kNLCap : value;  // < 0 restores the default
-    return DH_OK;
+    return DH_OK;   // cached graphs carry the value they were captured with in their key: no stale reuse
 }
 
 int dh_rot6d_to_matrix(const float* rot6d, float* R, int32_t B, void* stream) {
@@ -1930,8 +2087,12 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         return DH_OK;
     }
     cudaGraphExec_t exec = nullptr;
+    int device = 0;
+    DH_CUDA(cudaGetDevice(&device));
+    const int list_cap = neg_list_cap();
+    std::lock_guard<std::mutex> lock(graph_mutex());
     for (auto& e : graph_cache())
-        if (memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0) exec = e.exec;
+        if (e.device == device && e.list_cap == list_cap && memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0) exec = e.exec;
     if (exec == nullptr) {
         // warm the function attributes outside capture
         rc = set_smem(k_raster<true>, raster_smem_bytes(p->sil));
@@ -1957,10 +2118,17 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         cudaGraphDestroy(graph);
         cudaStreamDestroy(cs);
         if (ce != cudaSuccess) return fail(DH_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+        auto& c = graph_cache();
+        if (c.size() >= kGraphCacheMax) {
+            cudaGraphExecDestroy(c.front().exec);
+            c.erase(c.begin());
+        }
         GraphEntry e;
         memcpy(&e.plan, p, sizeof(dh_jointopt));
+        e.device = device;
+        e.list_cap = list_cap;
         e.exec = exec;
-        graph_cache().push_back(e);
+        c.push_back(e);
     }
     for (int it = 0; it < n_iters; it++) DH_CUDA(cudaGraphLaunch(exec, st));
     return DH_OK;
@@ -2004,7 +2172,57 @@ int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_hos
     return rc;
 }
 
+int dh_jointopt_probe(const dh_jointopt* p, int32_t nblocks, float* ms_out_host, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(nblocks >= 1 && nblocks <= p->sil.B && nblocks <= 256 && ms_out_host != nullptr, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    dh_jointopt q = *p;
+    q.mailbox = nullptr;   // the probe never waits on a neighbour: halo_prev / halo_next as given (may be NULL)
+    q.peer_prev = q.peer_next = nullptr;
+    const int B = q.sil.B;
+    const bool with_sil = q.lw_sil > 0.0;
+    const bool with_corr = q.corr.records != nullptr && q.corr.lw_corr > 0.0;
+    std::vector<cudaEvent_t> ev(nblocks + 3);
+    for (auto& e : ev) DH_CUDA(cudaEventCreate(&e));
+    k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(q);
+    DH_LAUNCH_OK("k_pose_prep");
+    // one untimed pass over everything (first-touch, function attributes), then block by block
+    if (with_sil) rc = launch_sil_kernels(q, false, st);
+    for (int pass = 0; pass < 2 && !rc && with_corr; pass++) {
+        if (pass == 1) cudaEventRecord(ev[nblocks + 1], st);
+        rc = launch_corr(q.corr.records, B, q.corr.C, q.Rmat, q.trans, q.scale, q.sil.K, q.sil.S, q.corr.delta,
+                         q.corr.partials, q.corr.nslots, st);
+        if (pass == 1) cudaEventRecord(ev[nblocks + 2], st);
+    }
+    for (int k = 0; k < nblocks && !rc; k++) {
+        const int b0 = (int)((long long)B * k / nblocks), b1 = (int)((long long)B * (k + 1) / nblocks);
+        cudaEventRecord(ev[k], st);
+        if (with_sil) rc = launch_sil_kernels(sub_plan(q, b0, b1 - b0), false, st);
+    }
+    cudaEventRecord(ev[nblocks], st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (!rc && e != cudaSuccess) rc = fail(DH_ERR_CUDA, "probe sync: %s", cudaGetErrorString(e));
+    for (int k = 0; k <= nblocks; k++) ms_out_host[k] = 0.0f;
+    if (!rc) {
+        for (int k = 0; k < nblocks; k++) cudaEventElapsedTime(&ms_out_host[k], ev[k], ev[k + 1]);
+        if (with_corr) cudaEventElapsedTime(&ms_out_host[nblocks], ev[nblocks + 1], ev[nblocks + 2]);
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
+    return rc;
+}
+
+int dh_scale_apply(const dh_jointopt* p, const unsigned long long* parts_dev, int32_t world, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(parts_dev != nullptr && world >= 1, "bad arguments");
+    k_scale_apply<<<1, 32, 0, (cudaStream_t)stream>>>(*p, parts_dev, world);
+    DH_LAUNCH_OK("k_scale_apply");
+    return DH_OK;
+}
+
 int dh_jointopt_release(const dh_jointopt* p) {
+    std::lock_guard<std::mutex> lock(graph_mutex());
     auto& c = graph_cache();
     for (size_t i = 0; i < c.size();) {
         if (p == nullptr || memcmp(&c[i].plan, p, sizeof(dh_jointopt)) == 0) {

@@ -12,7 +12,10 @@ Same public interface:
 per-step host synchronisation) and fills `loss_evolution` / `board` after the loop from a device-side history.
 """
 import ctypes
+import os
 from collections import defaultdict
+
+import numpy as np
 
 import torch
 from torch import nn
@@ -23,7 +26,8 @@ from .corr import CorrespondenceTerm, plan as corr_plan
 from .geometry import matrix_to_rot6d, rot6d_to_matrix
 from .losses import Losses
 from .renderer import SilhouetteState, shared_faces
-from .sharding import FrameShard, allgather_frames, allreduce_sum_, detect_shard, exchange_halo
+from .sharding import (FrameShard, PeerMailboxes, allgather_equal, allgather_frames, allreduce_sum_, balanced_bounds,
+                       detect_shard, exchange_halo, frame_costs_from_blocks)
 
 
 class Joint_Optimizer(nn.Module):
@@ -94,10 +98,15 @@ class FusedJointOpt:
     """The fused iteration (dh_jointopt_run) bound to a Joint_Optimizer's parameters, updated in place."""
 
     def __init__(self, model, loss_weights, lr, max_iters, shard=None, group=None, nchunks=None, keep_sum=None,
-                 exchange=True, halo="p2p"):
-        """halo: how boundary poses travel between ranks when the sequence is sharded.  "p2p" (default): CUDA-IPC
-        mailboxes written by the update kernel itself over NVLink, no host work per iteration.  "nccl": one grouped
-        send/recv per iteration driven from the host (also the path the gloo CPU tests exercise)."""
+                 exchange=True, halo="p2p", corr_on=None, halo_timeout_ms=0):
+        """halo: how boundary poses (and, with optimize_object_scale, the partial scale gradients) travel between
+        ranks when the sequence is sharded.  "p2p" (default): CUDA-IPC mailboxes written by the kernels themselves
+        over NVLink, no host work per iteration; falls back to "nccl" when the ranks cannot map each other's memory.
+        "nccl": one grouped send/recv (+ one all_gather for the scale) per iteration driven from the host (also the
+        path the gloo CPU tests exercise).  exchange=False: the caller fills self.halo by hand and passes keep_sum
+        (single-process shard emulation; optimize_object_scale then needs all emulated shards stepped through
+        `step_emulated`).  corr_on: whether the correspondence term is active -- must be the same on every rank
+        (default: this model has records and lw_corr_obj > 0)."""
         lib = _lib.load()
         self.model, self.group = model, group
         rot, tr = model.rotations_object, model.translations_object
@@ -124,12 +133,29 @@ class FusedJointOpt:
         keep = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(lib.dh_masks_prepare(_lib.ptr(masks.contiguous().float()), _lib.ptr(self.mask_tri), _lib.ptr(keep),
                                         masks.numel(), st), "dh_masks_prepare")
+        del masks
         self.exchange = exchange  # False: the caller fills self.halo by hand (single-process shard emulation)
-        if keep_sum is None:
-            keep_f = keep.to(torch.float64)
-            allreduce_sum_(keep_f, self.shard, group)
-            keep_sum = float(keep_f.item())
-        self.keep_sum = float(keep_sum)
+        # builder-defined correspondence term: on only with records AND a positive weight, on EVERY rank alike
+        lw_corr = float(loss_weights.get("lw_corr_obj", 0.0))
+        has_corr = getattr(model, "corr_term", None) is not None and lw_corr > 0
+        self.corr_on = has_corr if corr_on is None else bool(corr_on)
+        if self.corr_on and not has_corr:
+            raise ValueError("corr_on=True but this rank's model has no correspondences / lw_corr_obj")
+        # one fused all-reduce for the sequence-wide constants: sum(keep), sum(w), and the ranks' view of corr_on
+        # (a rank that disagreed would otherwise hang the others in a mismatched collective later)
+        consts = torch.zeros(4, dtype=torch.float64, device=dev)
+        consts[0] = keep[0].to(torch.float64)
+        if self.corr_on:
+            consts[1] = model.corr_term.w_local.reshape(()).to(torch.float64)
+        consts[2] = 1.0 if self.corr_on else 0.0
+        consts[3] = 1.0
+        if exchange and self.shard.world > 1:
+            allreduce_sum_(consts, self.shard, group)
+        consts_h = consts.cpu().numpy() if (keep_sum is None or self.corr_on or exchange) else None
+        if exchange and self.shard.world > 1 and consts_h[2] not in (0.0, consts_h[3]):
+            raise _lib.DynhorError("the correspondence term is active on some ranks only: pass the same "
+                                   "loss_weights / correspondences to every rank")
+        self.keep_sum = float(keep_sum) if keep_sum is not None else float(consts_h[0])
         self.keep_local = keep
         self.moments = torch.empty(12, dtype=torch.float64, device=dev)
         _lib.check(lib.dh_mesh_moments(_lib.ptr(verts), V, _lib.ptr(self.moments), st), "dh_mesh_moments")
@@ -138,11 +164,12 @@ class FusedJointOpt:
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
         self.m_rot, self.v_rot, self.m_tr, self.v_tr, self.mv_scale = z(B, 6), z(B, 6), z(B, 3), z(B, 3), z(2)
         self.step = z(1, dt=torch.int32)
+        self.status = z(1, dt=torch.int32)
+        self.scale_part = z(2, dt=torch.int64)
         self.max_iters = int(max_iters)
-        self.hist = z(max(self.max_iters, 1), 4, dt=torch.float64)
+        self.hist = z(self.max_iters + 1, 4, dt=torch.float64)   # row max_iters: evaluate() / grads()
         self.halo = z(2, 9)
         self.edge = z(2, 9)
-        import os
         nchunks = nchunks or int(os.environ.get("DH_BWD_CHUNKS", "0"))  # tuning knob
         self.nchunks = int(nchunks) if nchunks else lib.dh_jointopt_default_chunks(B, self.sil.F)
         sizes = (ctypes.c_int64 * 5)()
@@ -156,42 +183,41 @@ class FusedJointOpt:
         p.adam_m_rot, p.adam_v_rot = self.m_rot.data_ptr(), self.v_rot.data_ptr()
         p.adam_m_trans, p.adam_v_trans = self.m_tr.data_ptr(), self.v_tr.data_ptr()
         p.adam_mv_scale = self.mv_scale.data_ptr()
-        p.step, p.hist, p.max_iters = self.step.data_ptr(), self.hist.data_ptr(), self.hist.shape[0]
+        p.step, p.hist, p.max_iters = self.step.data_ptr(), self.hist.data_ptr(), self.max_iters
+        p.status, p.scale_part = self.status.data_ptr(), self.scale_part.data_ptr()
+        p.halo_timeout_ms = int(halo_timeout_ms)
         p.halo_prev = self.halo[0].data_ptr() if self.shard.has_prev else None
         p.halo_next = self.halo[1].data_ptr() if self.shard.has_next else None
         p.B_total = self.shard.B_total
+        p.rank, p.world = self.shard.rank, self.shard.world
         p.keep_sum = self.keep_sum
         p.lw_sil = float(loss_weights.get("lw_sil_obj", 0.0))
         p.lw_smooth = float(loss_weights.get("lw_smooth_obj", 0.0))
         p.lr = float(lr)
         p.optimize_scale = int(bool(getattr(model, "optimize_object_scale", False)))
-        if p.optimize_scale and self.shard.world > 1:
-            raise NotImplementedError("optimize_object_scale with frame sharding (needs a scale-gradient all-reduce)")
         p.moments = self.moments.data_ptr()
         (p.Rmat, p.smooth_terms, p.loss_counts, p.partials, p.frame_terms) = [b.data_ptr() for b in self.scratch]
         p.nchunks = self.nchunks
-        # builder-defined correspondence term: on only with records AND a positive weight
-        lw_corr = float(loss_weights.get("lw_corr_obj", 0.0))
-        self.corr_on = getattr(model, "corr_term", None) is not None and lw_corr > 0
         if self.corr_on:
             ct = model.corr_term
-            w = ct.w_local.reshape(1).clone()
-            if exchange:
-                allreduce_sum_(w, self.shard, group)
-                self.corr_w_sum = float(w.item())
-            else:
-                self.corr_w_sum = ct.w_sum
+            self.corr_w_sum = float(consts_h[1]) if (exchange and consts_h is not None) else ct.w_sum
             cp = corr_plan(B, ct.records.shape[1])
             self.corr_partials = z(B, cp["nslots"], 16)
             p.corr.records, p.corr.C, p.corr.nslots = ct.records.data_ptr(), ct.records.shape[1], cp["nslots"]
             p.corr.delta, p.corr.w_sum, p.corr.lw_corr = ct.delta, self.corr_w_sum, lw_corr
             p.corr.partials = self.corr_partials.data_ptr()
         self.p = p
-        self.halo_mode = halo if (self.shard.world > 1 and exchange) else "none"
-        self._mailbox, self._peers = None, []
+        sharded = self.shard.world > 1
+        self.halo_mode = halo if (sharded and exchange) else "none"
+        self._mail, self._keep = None, []
         self._sync_halo()
         if self.halo_mode == "p2p":
             self._setup_p2p()
+        # the shared scale's gradient under sharding: exact partial sums, added up in rank order on every rank
+        if p.optimize_scale and sharded:
+            p.scale_mode = _lib.SCALE_P2P if self.halo_mode == "p2p" else _lib.SCALE_DEFERRED
+        else:
+            p.scale_mode = _lib.SCALE_LOCAL
 
     # -- sharding ---------------------------------------------------------------------------------------------
     def _sync_halo(self):
@@ -206,39 +232,28 @@ class FusedJointOpt:
         exchange_halo(self.edge[0], self.edge[1], self.shard, self.halo[0], self.halo[1], self.group)
 
     def _setup_p2p(self):
-        """Allocate this rank's mailbox, swap CUDA-IPC handles with the neighbours and seed parity-0 slots with
-        the initial halo (already exchanged once through the process group)."""
-        import torch.distributed as dist
-        lib = _lib.load()
-        mb = ctypes.c_void_p()
-        _lib.check(lib.dh_dev_alloc(ctypes.byref(mb), 4 * 128), "dh_dev_alloc")
-        self._mailbox = mb
-        handle = ctypes.create_string_buffer(64)
-        _lib.check(lib.dh_ipc_export(mb, handle), "dh_ipc_export")
-        handles = [None] * self.shard.world
-        dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
-        st = _lib.stream_ptr()
-        # slot(side, parity 0): side 0 = pose of the frame before our first, side 1 = after our last
+        """Bind this run to the process-wide mailboxes (sharding.PeerMailboxes: allocated and IPC-mapped once per
+        process), reserve its tick range and seed this rank's own slots with the initial halo (already exchanged
+        once through the process group).  No barrier: a neighbour's first publish goes to another slot."""
+        mail = PeerMailboxes.get(self.shard, self.group)
+        if mail is None:          # no peer access between the ranks' devices: host-driven exchange
+            self.halo_mode = "nccl"
+            return
+        self._mail = mail
+        base = mail.reserve(self.max_iters)
         for side in (0, 1):
-            _lib.check(lib.dh_memcpy_d2d(ctypes.c_void_p(mb.value + side * 2 * 16 * 4), _lib.ptr(self.halo[side]),
-                                         9 * 4, st), "dh_memcpy_d2d")
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)  # every mailbox is seeded before anyone may publish into it
-        peers = {}
-        for name, r in (("peer_prev", self.shard.rank - 1), ("peer_next", self.shard.rank + 1)):
-            if 0 <= r < self.shard.world:
-                ptr = ctypes.c_void_p()
-                _lib.check(lib.dh_ipc_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(ptr)),
-                           "dh_ipc_open")
-                peers[name] = ptr
-                self._peers.append(ptr)
-        self.p.mailbox = mb.value
-        self.p.peer_prev = peers["peer_prev"].value if "peer_prev" in peers else None
-        self.p.peer_next = peers["peer_next"].value if "peer_next" in peers else None
+            if (side == 0 and self.shard.has_prev) or (side == 1 and self.shard.has_next):
+                self._keep.append(mail.seed(side, base, self.halo[side]))
+        p = self.p
+        p.mailbox, p.tick_base = mail.mailbox, base
+        p.peer_prev = mail.peers[self.shard.rank - 1] if self.shard.has_prev else None
+        p.peer_next = mail.peers[self.shard.rank + 1] if self.shard.has_next else None
+        for r in range(self.shard.world):
+            p.peers[r] = mail.peers[r]
 
     # -- execution --------------------------------------------------------------------------------------------
     def run(self, n_iters, use_graph=True):
-        """n_iters fused iterations on the current stream; no host synchronisation (single rank)."""
+        """n_iters fused iterations on the current stream; no host synchronisation (single rank / p2p)."""
         lib = _lib.load()
         if self.halo_mode != "nccl":
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), int(n_iters), int(use_graph), _lib.stream_ptr()),
@@ -247,7 +262,26 @@ class FusedJointOpt:
         for _ in range(int(n_iters)):
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), 1, int(use_graph), _lib.stream_ptr()),
                        "dh_jointopt_run")
+            if self.p.scale_mode == _lib.SCALE_DEFERRED:
+                self.apply_scale(allgather_equal(self.scale_part, self.shard, self.group))
             self._sync_halo()
+
+    def apply_scale(self, parts):
+        """DH_SCALE_DEFERRED: Adam step of the shared scale from the exact partial gradients of all ranks
+        ([world, 2] int64 on the device, rank order: every rank's `scale_part` after its iteration)."""
+        parts = parts.contiguous()
+        assert parts.shape == (self.shard.world, 2) and parts.dtype == torch.int64 and parts.is_cuda
+        _lib.check(_lib.load().dh_scale_apply(ctypes.byref(self.p), _lib.ptr(parts), self.shard.world,
+                                              _lib.stream_ptr()), "dh_scale_apply")
+
+    def check_status(self):
+        """Raise if a kernel gave up waiting for a neighbour (synchronises)."""
+        code = int(self.status.item())
+        if code == _lib.STATUS_HALO_TIMEOUT:
+            raise _lib.DynhorError(f"{self.shard}: timed out waiting for a neighbouring rank's boundary pose / scale "
+                                   "gradient (a rank died or fell behind by more than halo_timeout_ms)")
+        if code:
+            raise _lib.DynhorError(f"{self.shard}: device status {code}")
 
     def grads(self):
         """Gradients of the weighted loss for the current parameters (no update)."""
@@ -261,10 +295,17 @@ class FusedJointOpt:
         return g_rot, g_tr, g_s
 
     def evaluate(self):
-        """Losses of the current parameters -> dict of floats (synchronises)."""
+        """Losses of the current parameters -> dict of one-element lists (synchronises)."""
         _lib.check(_lib.load().dh_jointopt_eval(ctypes.byref(self.p), _lib.stream_ptr()), "dh_jointopt_eval")
-        row = int(self.step.item())
-        return self._rows_to_dict(self.hist[row:row + 1].clone())
+        return self._rows_to_dict(self.hist[self.max_iters:self.max_iters + 1].clone())
+
+    def probe(self, nblocks):
+        """Milliseconds of the heavy kernels of one iteration for `nblocks` equal blocks of this rank's frames, plus
+        the correspondence kernel over all of them as the last entry (dh_jointopt_probe; parameters untouched)."""
+        ms = (ctypes.c_float * (int(nblocks) + 1))()
+        _lib.check(_lib.load().dh_jointopt_probe(ctypes.byref(self.p), int(nblocks), ms, _lib.stream_ptr()),
+                   "dh_jointopt_probe")
+        return np.asarray(list(ms), np.float64)
 
     def _rows_to_dict(self, rows):
         rows = rows.clone()
@@ -290,7 +331,8 @@ class FusedJointOpt:
 
     def history(self):
         """loss_evolution of all iterations run so far (synchronises once)."""
-        n = int(self.step.item())
+        n = min(int(self.step.item()), self.max_iters)
+        self.check_status()
         return self._rows_to_dict(self.hist[:n])
 
     KERNELS = ("pose_prep", "project", "setup_bin", "raster", "backward", "pose_update", "finalize", "corr")
@@ -303,78 +345,178 @@ class FusedJointOpt:
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}
 
     def release(self):
-        lib = _lib.load()
-        lib.dh_jointopt_release(ctypes.byref(self.p))
-        if self._mailbox is not None:
-            import torch.distributed as dist
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)  # nobody may still be publishing into a mailbox that is about to go
-            for ptr in self._peers:
-                lib.dh_ipc_close(ptr)
-            lib.dh_dev_free(self._mailbox)
-            self._mailbox, self._peers = None, []
-            self.p.mailbox = self.p.peer_prev = self.p.peer_next = None
+        """Drop the cached graph executables of this plan.  The mailboxes stay (process-wide, reused)."""
+        if getattr(self, "p", None) is not None:
+            _lib.load().dh_jointopt_release(ctypes.byref(self.p))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # pragma: no cover  (interpreter shutdown)
+            pass
+
+
+def _stack_frames(frames, key, pick=None, dtype=None):
+    """One tensor [n, ...] on the GPU from the per-frame entries `frames[i][key]` ([1, ...] each).  Device tensors are
+    concatenated on the device; pinned host tensors are copied asynchronously straight into their rows of the
+    result; pageable host tensors go through ONE pinned staging buffer and ONE host-to-device copy."""
+    ts = [f[key] if pick is None else pick(f[key]) for f in frames]
+    t0 = ts[0]
+    if t0.is_cuda:
+        out = torch.cat(ts)
+    elif t0.is_pinned() and t0.numel() * t0.element_size() >= 65536:
+        out = torch.empty((sum(int(t.shape[0]) for t in ts),) + tuple(t0.shape[1:]), dtype=t0.dtype, device="cuda")
+        row = 0
+        for t in ts:
+            out[row:row + t.shape[0]].copy_(t, non_blocking=True)
+            row += t.shape[0]
+    else:
+        n = sum(int(t.shape[0]) for t in ts)
+        stage = torch.empty((n,) + tuple(t0.shape[1:]), dtype=t0.dtype, pin_memory=True)
+        torch.cat(ts, out=stage)
+        out = stage.cuda(non_blocking=True)
+    return out if dtype is None or out.dtype == dtype else out.to(dtype)
+
+
+def _shared_faces_host(objfaces, B_total):
+    """run.py:158 stacks one identical face list per frame ([B,F,3] int64, 72 MB at 300 frames): compared with row 0
+    on the host (multi-threaded; skipped for a broadcast view) and uploaded ONCE as int32 [F,3]."""
+    f = objfaces if torch.is_tensor(objfaces) else torch.from_numpy(np.asarray(objfaces))
+    if f.ndim == 3:
+        if f.shape[0] > 1 and f.stride(0) != 0 and not torch.equal(f[1:], f[:-1]):
+            raise NotImplementedError("dynhor_b200 renders one mesh topology for all frames (run.py:158 stacks "
+                                      "identical faces); per-frame face lists are not supported")
+        f = f[0]
+    if f.ndim != 2 or f.shape[-1] != 3:
+        raise AssertionError("Invalid shape for faces")
+    return f.to(torch.int32).contiguous().cuda()
 
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
                    lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True, halo="p2p",
-                   corr_delta=1.0):
-    """jointopt.py:93-161.  Extra keyword `shard` (a sharding.FrameShard): when given (or when torch.distributed
+                   corr_delta=1.0, balance="probe"):
+    """jointopt.py:93-161.  Extra keywords: `shard` (a sharding.FrameShard): when given (or when torch.distributed
     is initialised with more than one rank) `object_parameters` is the full sequence and this rank optimises its
-    contiguous frame range; the returned model holds the gathered poses of ALL frames on every rank."""
+    contiguous frame range; the returned model holds the gathered poses of ALL frames on every rank.
+    `balance` ("probe" | "count"): how the sequence is cut when no shard is given -- by measured per-frame cost
+    (one untimed + one timed pass of the heavy kernels over equal-count ranges, then ranges of equal cost) or by
+    frame count."""
     if not torch.cuda.is_available():
         raise _lib.DynhorError("joint_optimize needs a CUDA device (dynhor_b200 has no CPU fallback)")
     if loss_weights is None:
         loss_weights = {"lw_sil_obj": 1.0, "lw_smooth_obj": 1.0}
     B_total = len(object_parameters)
+    marks = []
+
+    def mark(label):   # DH_TIMING=1: synchronised phase times in model.timing (diagnostics; off: no synchronisation)
+        if os.environ.get("DH_TIMING"):
+            import time
+            torch.cuda.synchronize()
+            marks.append((label, time.perf_counter()))
+
+    mark("start")
+    auto = shard is None
     shard = detect_shard(B_total) if shard is None else shard
     verts_object_og = tensorify(objvertices).cuda()
-    # faces: run.py:158 stacks one face list per frame; only this rank's frames are uploaded and checked
-    faces_host = tensorify(objfaces)
-    faces_local = (faces_host[shard.start:shard.stop] if faces_host.ndim == 3 else faces_host).cuda()
-    local = shard.slice(object_parameters)
-    # Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors are accepted too: the small
-    # ones are concatenated on the host, the masks go up frame by frame (no 78 MB host-side concatenation) and the
-    # ref / keep masks are derived on the device.
-    obj_trans = torch.cat([obj["translations"] for obj in local]).cuda()
-    obj_rots = torch.cat([obj["rotations"] for obj in local]).cuda()
-    obj_camintr_roi = torch.cat([obj["K_roi"][:, 0] for obj in local]).cuda()
-    obj_tar_masks = torch.cat([obj["target_masks"].cuda(non_blocking=True) for obj in local])
-    # optional per-frame key "correspondences" [1,C,6] (builder-defined term, corr.py); absent -> reference behaviour
-    corr = None
-    if all("correspondences" in obj for obj in local) and loss_weights.get("lw_corr_obj", 0) > 0:
-        corr = torch.cat([obj["correspondences"].cuda(non_blocking=True) for obj in local])
-    model = Joint_Optimizer(
-        translations_object=obj_trans, rotations_object=obj_rots, verts_object_og=verts_object_og,
-        faces_object=faces_local, target_masks_object=obj_tar_masks, camintr_rois_object=obj_camintr_roi,
-        int_scale_init=1, optimize_object_scale=optimize_object_scale, correspondences=corr,
-        corr_delta=corr_delta)
-    fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard, halo=halo)
+    faces_dev = _shared_faces_host(objfaces, B_total)
+    # the correspondence term is on for everybody or for nobody: decided from the FULL list, not this rank's slice
+    corr_on = loss_weights.get("lw_corr_obj", 0) > 0 and all("correspondences" in obj for obj in object_parameters)
+
+    def build(sh, with_corr, reuse=None):
+        """Model of the frames of `sh`.  Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors
+        are accepted too.  reuse = (model, shard) of an earlier build: frames it already holds stay on the device."""
+        local = sh.slice(object_parameters)
+        trans = _stack_frames(local, "translations")
+        rots = _stack_frames(local, "rotations")
+        K = _stack_frames(local, "K_roi", pick=lambda t: t[:, 0])
+        if reuse is None:
+            masks = _stack_frames(local, "target_masks", dtype=torch.float32)
+        else:
+            m0, s0 = reuse
+            old = m0.ref_mask_object + m0.keep_mask_object - 1.0
+            lo, hi = max(sh.start, s0.start), min(sh.stop, s0.stop)
+            parts = []
+            if lo >= hi:
+                parts.append(_stack_frames(local, "target_masks", dtype=torch.float32))
+            else:
+                if sh.start < lo:
+                    parts.append(_stack_frames(object_parameters[sh.start:lo], "target_masks", dtype=torch.float32))
+                parts.append(old[lo - s0.start:hi - s0.start])
+                if hi < sh.stop:
+                    parts.append(_stack_frames(object_parameters[hi:sh.stop], "target_masks", dtype=torch.float32))
+            masks = torch.cat(parts) if len(parts) > 1 else parts[0]
+        corr = _stack_frames(local, "correspondences") if (with_corr and corr_on) else None
+        return Joint_Optimizer(
+            translations_object=trans, rotations_object=rots, verts_object_og=verts_object_og,
+            faces_object=faces_dev, target_masks_object=masks, camintr_rois_object=K,
+            int_scale_init=1, optimize_object_scale=optimize_object_scale, correspondences=corr,
+            corr_delta=corr_delta)
+
+    mark("mesh")
+    model = None
+    if auto and shard.world > 1 and balance == "probe":
+        # cost-weighted partition: time the heavy kernels block by block on the equal-count ranges, gather, re-cut
+        nblocks = max(1, min(16, (B_total // shard.world) // 32))
+        model0 = build(shard, with_corr=False)
+        lw_probe = {k: v for k, v in loss_weights.items() if k != "lw_corr_obj"}
+        with FusedJointOpt(model0, lw_probe, lr, 0, shard=shard, keep_sum=1.0, exchange=False) as probe:
+            ms = torch.from_numpy(probe.probe(nblocks)).cuda()
+        ms_all = allgather_equal(ms, shard).cpu().numpy()
+        cost = np.concatenate([frame_costs_from_blocks(ms_all[r, :nblocks], shard.bounds[r], shard.bounds[r + 1])
+                               for r in range(shard.world)])
+        new = shard.with_bounds(balanced_bounds(cost, shard.world))
+        model = model0 if (new.start, new.stop) == (shard.start, shard.stop) and not corr_on else \
+            build(new, with_corr=True, reuse=(model0, shard))
+        shard = new
+        del model0
+    mark("partition")
+    if model is None:
+        model = build(shard, with_corr=True)
+    mark("model")
+    fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard, halo=halo, corr_on=corr_on)
+    mark("fused")
     try:
-        from tqdm.auto import tqdm
-        loop = tqdm(total=num_iterations)
-    except Exception:  # pragma: no cover
-        loop = None
-    chunk = 50
-    done = 0
-    while done < num_iterations:
-        n = min(chunk, num_iterations - done)
-        fused.run(n, use_graph=use_graph)
-        done += n
+        try:
+            from tqdm.auto import tqdm
+            loop = tqdm(total=num_iterations)
+        except Exception:  # pragma: no cover
+            loop = None
+        chunk = 50
+        done = 0
+        while done < num_iterations:
+            n = min(chunk, num_iterations - done)
+            fused.run(n, use_graph=use_graph)
+            done += n
+            if loop is not None:
+                loop.update(n)
+        mark("launched")
+        loss_evolution = fused.history()  # the only host synchronisation of the loop
+        mark("loop")
         if loop is not None:
-            loop.update(n)
-    loss_evolution = fused.history()  # the only host synchronisation of the loop
-    if loop is not None:
-        if loss_evolution.get("loss"):
-            loop.set_description(f"Loss {loss_evolution['loss'][-1]:.4f}")
-        loop.close()
+            if loss_evolution.get("loss"):
+                loop.set_description(f"Loss {loss_evolution['loss'][-1]:.4f}")
+            loop.close()
+    finally:
+        fused.release()
     if board is not None:
         for k in ("loss_smooth_obj", "loss_sil_obj", "loss_corr_obj"):
             for step, val in enumerate(loss_evolution.get(k, [])):
                 board.add_scalar(k, val, step)
-    fused.release()
     if shard.world > 1:
         with torch.no_grad():
-            model.rotations_object = nn.Parameter(allgather_frames(model.rotations_object.detach(), shard))
-            model.translations_object = nn.Parameter(allgather_frames(model.translations_object.detach(), shard))
+            pose = torch.cat([model.rotations_object.detach().reshape(shard.B, 6),
+                              model.translations_object.detach().reshape(shard.B, 3)], 1)
+            pose = allgather_frames(pose, shard)   # one collective for both parameter tensors
+            model.rotations_object = nn.Parameter(pose[:, :6].reshape(-1, 3, 2).contiguous())
+            model.translations_object = nn.Parameter(pose[:, 6:].reshape(-1, 1, 3).contiguous())
+    mark("gather")
+    model.frame_shard = shard
+    model.timing = [(b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])]
     return model, loss_evolution

@@ -195,15 +195,16 @@ def make_K_roi(verts, R, T, H, W, size=REND_SIZE):
 
 
 # ----------------------------------------------------------------------------- masks
-def add_disc_occluder(masks01, seed=0, radius=40.0):
+def add_disc_occluder(masks01, seed=0, radius=40.0, frame_offset=0):
     """Tri-state target masks: a seeded disc marked -1 wherever it does not cover the object
-    (utils/maskutils.py:24-28)."""
-    rng = np.random.default_rng(seed + 2)
+    (utils/maskutils.py:24-28).  The disc of a frame depends on (seed, global frame number) only, so a rank that
+    builds frames [frame_offset, frame_offset + B) of a longer sequence gets the masks a full build would."""
     B, S, _ = masks01.shape
     yy, xx = np.mgrid[0:S, 0:S]
     out = masks01.astype(np.float32).copy()
     r = radius * S / float(REND_SIZE)
     for b in range(B):
+        rng = np.random.default_rng([seed + 2, frame_offset + b])
         cx, cy = rng.uniform(0.2 * S, 0.8 * S, size=2)
         disc = (xx - cx) ** 2 + (yy - cy) ** 2 <= r * r
         out[b][disc & (masks01[b] <= 0)] = -1.0
@@ -249,44 +250,51 @@ def make_sequence(B, H=480, W=640, mesh="uv50x100", seed=0, render_fn=None, size
         vc = (verts.astype(np.float64)[None] @ R_gt + T_gt[:, None, :]).astype(np.float32)
         sil = np.asarray(render_fn(vc, faces, K_roi, size))
         m01 = (sil > 0.5).astype(np.float32)
-        out["target_masks"] = add_disc_occluder(m01, seed, 40.0) if occluder else m01
+        out["target_masks"] = add_disc_occluder(m01, seed, 40.0, frame_offset) if occluder else m01
     return out
 
 
-def make_correspondences(seq, C, seed=0, noise_px=0.5, outliers=0.05, size=REND_SIZE):
+def make_correspondences(seq, C, seed=0, noise_px=0.5, outliers=0.05, size=REND_SIZE, frame_offset=0, device=None):
     """[BUILDER-DEFINED, SURVEY.md 8d]  Synthetic DKM-style dense correspondences for the reprojection term
     (dynhor_b200/corr.py): per frame b, C records (X[3], t[2], w) where X is a surface point of the canonical
-    mesh facing the camera in the previous frame's ground-truth pose (the "source" frame of the pair), t its
-    ground-truth projection into frame b in ROI unit-image coordinates plus N(0, noise_px^2) pixel noise, and w a
-    DKM-like certainty in (0.5, 1]; a fraction `outliers` of the targets is replaced by uniform positions.
-    Returns float32 [B,C,6]."""
-    rng = np.random.default_rng(seed + 3)
-    verts, faces = seq["verts"].astype(np.float64), seq["faces"]
-    R, T, K = seq["R_gt"].astype(np.float64), seq["T_gt"].astype(np.float64).reshape(-1, 3), seq["K_roi"]
+    mesh facing the camera in the frame's ground-truth pose, t its ground-truth projection into frame b in ROI
+    unit-image coordinates plus N(0, noise_px^2) pixel noise, and w a DKM-like certainty in (0.5, 1]; a fraction
+    `outliers` of the targets is replaced by uniform positions.  Every frame draws from its own generator seeded by
+    (seed, frame_offset + b): the records of a frame do not depend on which rank builds it.
+    Returns float32 [B,C,6] (numpy; a torch tensor on `device` when one is given -- the 50k-record configurations
+    are generated on the GPU)."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    verts = torch.from_numpy(seq["verts"].astype(np.float64)).to(dev)
+    faces = torch.from_numpy(np.asarray(seq["faces"], np.int64)).to(dev)
+    R = torch.from_numpy(seq["R_gt"].astype(np.float64)).to(dev)
+    T = torch.from_numpy(seq["T_gt"].astype(np.float64).reshape(-1, 3)).to(dev)
+    K = torch.from_numpy(seq["K_roi"].astype(np.float64)).to(dev)
     B = len(R)
     tri = verts[faces]                                           # [F,3,3]
-    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
-    out = np.empty((B, C, 6), np.float32)
+    nrm = torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    cen0 = tri.mean(1)
+    out = torch.empty((B, C, 6), dtype=torch.float32, device=dev)
     for b in range(B):
-        src = max(b - 1, 0)
-        nc = nrm @ R[src]                                        # normals in the source frame's camera space
-        cen = tri.mean(1) @ R[src] + T[src]
-        vis = np.nonzero((nc * cen).sum(-1) < 0)[0]              # faces turned towards the camera
-        f = vis[rng.integers(0, len(vis), size=C)]
-        u, v = rng.random(C), rng.random(C)
-        flip = u + v > 1.0
-        u[flip], v[flip] = 1.0 - u[flip], 1.0 - v[flip]
-        X = tri[f, 0] + u[:, None] * (tri[f, 1] - tri[f, 0]) + v[:, None] * (tri[f, 2] - tri[f, 0])
+        g = torch.Generator(device=dev).manual_seed((seed + 3) * 1000003 + frame_offset + b)
+        nc = nrm @ R[b]                                          # normals in the frame's camera space
+        cen = cen0 @ R[b] + T[b]
+        vis = torch.nonzero((nc * cen).sum(-1) < 0)[:, 0]        # faces turned towards the camera
+        f = vis[torch.randint(0, len(vis), (C,), generator=g, device=dev)]
+        uv = torch.rand((C, 2), generator=g, device=dev, dtype=torch.float64)
+        flip = uv.sum(1) > 1.0
+        uv = torch.where(flip[:, None], 1.0 - uv, uv)
+        X = tri[f, 0] + uv[:, :1] * (tri[f, 1] - tri[f, 0]) + uv[:, 1:] * (tri[f, 2] - tri[f, 0])
         c = X @ R[b] + T[b]
         x_, y_ = c[:, 0] / c[:, 2], c[:, 1] / c[:, 2]
-        Kb = K[b].astype(np.float64)
-        t = np.stack([Kb[0, 0] * x_ + Kb[0, 1] * y_ + Kb[0, 2], Kb[1, 0] * x_ + Kb[1, 1] * y_ + Kb[1, 2]], -1)
-        t += rng.normal(size=t.shape) * (noise_px / float(size))
-        bad = rng.random(C) < outliers
-        t[bad] = rng.random((int(bad.sum()), 2))
-        w = rng.uniform(0.5, 1.0, size=C)
-        out[b] = np.concatenate([X, t, w[:, None]], -1).astype(np.float32)
-    return out
+        Kb = K[b]
+        t = torch.stack([Kb[0, 0] * x_ + Kb[0, 1] * y_ + Kb[0, 2], Kb[1, 0] * x_ + Kb[1, 1] * y_ + Kb[1, 2]], -1)
+        t = t + torch.randn((C, 2), generator=g, device=dev, dtype=torch.float64) * (noise_px / float(size))
+        bad = torch.rand((C,), generator=g, device=dev) < outliers
+        t = torch.where(bad[:, None], torch.rand((C, 2), generator=g, device=dev, dtype=torch.float64), t)
+        w = 0.5 + 0.5 * torch.rand((C, 1), generator=g, device=dev, dtype=torch.float64)
+        out[b] = torch.cat([X, t, w], -1).float()
+    return out if device is not None else out.numpy()
 
 
 def to_object_parameters(seq):

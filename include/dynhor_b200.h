@@ -146,18 +146,31 @@ typedef struct dh_jointopt {
     float* adam_m_trans; float* adam_v_trans;  /* [B,3] each */
     float* adam_mv_scale;          /* [2] */
     int32_t* step;                 /* [1] device iteration counter (0 before the first step)                   */
-    double* hist;                  /* [max_iters,4] per-iteration partial sums of this rank:                     */
-                                   /*   loss_smooth_obj, loss_sil_obj, iou_object, loss_corr_obj                 */
+    double* hist;                  /* [max_iters+1,4] per-iteration partial sums of this rank:                   */
+                                   /*   loss_smooth_obj, loss_sil_obj, iou_object, loss_corr_obj; row max_iters  */
+                                   /*   belongs to dh_jointopt_eval / dh_jointopt_grads                          */
     int32_t max_iters;
     /* neighbours' boundary poses for the smoothness term (frame-range sharding) */
     const float* halo_prev;        /* [9] rot6d(6)+trans(3) of global frame first-1, or NULL at the start        */
     const float* halo_next;        /* [9] of global frame last+1, or NULL at the end                            */
     /* Optional peer-to-peer halo (one process per GPU, CUDA IPC over NVLink).  When `mailbox` is set the halo_*
      * pointers are ignored: after its Adam step each rank stores its boundary poses straight into its neighbours'
-     * mailboxes and raises a flag; the next iteration's pose kernel waits on the flag.  No host involvement. */
-    float* mailbox;                /* [DH_MAILBOX_FLOATS] this rank's mailbox (dh_dev_alloc), or NULL            */
+     * mailboxes and raises a flag; the next iteration's pose kernel waits on the flag.  No host involvement.
+     * Flags hold "ticks" = tick_base + iteration: a mailbox (and its IPC mappings) is allocated once per process
+     * and reused by later runs, each run starting at a tick_base beyond every tick of the previous one. */
+    float* mailbox;                /* [DH_MAILBOX_WORDS] this rank's mailbox (dh_dev_alloc), or NULL             */
     float* peer_prev;              /* mailbox of rank-1 mapped into this process (dh_ipc_open), NULL if none     */
     float* peer_next;              /* mailbox of rank+1, NULL if none                                           */
+    int32_t tick_base;             /* tick of this run's iteration 0                                             */
+    int32_t halo_timeout_ms;       /* a wait on a neighbour gives up after this long (0 = 60 s), records          */
+                                   /* DH_STATUS_HALO_TIMEOUT in *status and lets the kernel finish               */
+    int32_t* status;               /* [1] device word, 0 = ok; checked by the host after the run (may be NULL)   */
+    /* shared object scale under frame sharding (jointopt.py:42-46: int_scales_object is ONE parameter of the
+     * rigid Adam group, its gradient sums over all frames of all ranks) */
+    int32_t rank, world;           /* this rank / number of ranks (world <= DH_MAX_RANKS); 0 / 1 when unsharded  */
+    int32_t scale_mode;            /* DH_SCALE_LOCAL, DH_SCALE_P2P or DH_SCALE_DEFERRED                          */
+    float* peers[16];              /* DH_SCALE_P2P: mailboxes of ALL ranks (peers[rank] = own mailbox)           */
+    unsigned long long* scale_part; /* [2] DH_SCALE_DEFERRED: this rank's exact partial scale gradient (dh_fx128) */
     int32_t B_total;               /* frames in the whole sequence (all ranks)                                  */
     double keep_sum;               /* sum over ALL ranks of keep-mask pixels      utils/losses.py:71             */
     double lw_sil, lw_smooth;      /* loss weights, 0 disables a term             jointopt.py:81,86,147-150      */
@@ -181,7 +194,7 @@ int dh_jointopt_default_chunks(int32_t B, int32_t F);
 /* run n_iters fused iterations on `stream` (no host sync).  use_graph != 0: capture one iteration into a CUDA
  * graph (cached per plan address) and replay it. */
 int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, void* stream);
-/* forward only: losses of the current parameters into hist[*step] without touching parameters or step. */
+/* forward only: losses of the current parameters into hist[max_iters] without touching parameters or step. */
 int dh_jointopt_eval(const dh_jointopt* p, void* stream);
 /* gradients of the weighted loss w.r.t. rot6d [B,6] and trans [B,3] (and scale [1]) for the current
  * parameters, without an optimiser step (parity tests; also the backward of Joint_Optimizer.forward). */
@@ -190,13 +203,37 @@ int dh_jointopt_grads(const dh_jointopt* p, float* grad_rot6d, float* grad_trans
  * milliseconds of pose_prep, project, setup_bin, raster, backward (incl. its per-frame map kernel), pose_update,
  * finalize, corr.  Synchronises. */
 int dh_jointopt_profile(const dh_jointopt* p, int32_t n_iters, float* ms_out_host, void* stream);
-/* drop cached graphs */
+/* drop the cached graphs of this plan (NULL: all) */
 int dh_jointopt_release(const dh_jointopt* p);
 
-/* Mailbox layout: slot(side, parity) = 16 floats at (side*2 + parity)*16, side 0 = pose of global frame first-1,
- * side 1 = pose of global frame last+1; int32 flags at float offset 64 + side*2 + parity hold the iteration number
- * the slot is valid for. */
-#define DH_MAILBOX_FLOATS 128
+/* Mailbox layout (32-bit words; every rank owns one, written by its peers over NVLink):
+ *   [0,128)    halo slots: slot(side, tick & 3) = 16 floats at (side*4 + (tick & 3))*16; side 0 = pose of global
+ *              frame first-1, side 1 = pose of global frame last+1 (rot6d(6) + trans(3))
+ *   [128,136)  halo flags (int32): tick the slot (side, tick & 3) is valid for
+ *   [136,392)  scale slots: slot(tick & 3, rank) = 4 words (dh_fx128: hi int64, lo uint64) at 136 + ((tick&3)*16 + rank)*4
+ *   [392,456)  scale flags (int32) at 392 + (tick&3)*16 + rank
+ * Four slots per side and monotonically increasing ticks: a neighbour that is still publishing the last tick of the
+ * previous run can never touch the slot the next run seeds (tick_base advances by n_iters + 2). */
+#define DH_MAILBOX_WORDS 512
+#define DH_MAX_RANKS 16
+#define DH_SCALE_LOCAL 0     /* single rank: k_finalize applies the Adam step to the scale                         */
+#define DH_SCALE_P2P 1       /* every rank stores its exact partial gradient into all mailboxes, sums them in     */
+                             /* rank order (bit-identical on every rank) and applies the step; no host work       */
+#define DH_SCALE_DEFERRED 2  /* k_finalize only stores the partial (scale_part); the host gathers the partials of */
+                             /* all ranks and calls dh_scale_apply (the "nccl" / gloo path)                       */
+#define DH_STATUS_HALO_TIMEOUT 1
+/* Exact order-independent sum of doubles: value = hi + lo * 2^-64 (two's complement, floor).  The scale gradient is
+ * accumulated in this form so that a frame-sharded run gives the same bits as a single-GPU run whatever the
+ * partition.  parts: [world][2] u64 (hi, lo) in rank order, HOST or DEVICE memory as stated. */
+/* Adam step of the shared scale from the gathered partial gradients (device memory, [world][2]); uses *p->step as
+ * the 1-based step number (call it after the iteration's dh_jointopt_run). */
+int dh_scale_apply(const dh_jointopt* p, const unsigned long long* parts_dev, int32_t world, void* stream);
+/* Times the heavy kernels (projection, binning, raster, backward) of one iteration separately for `nblocks`
+ * contiguous, equal blocks of this plan's frames, without touching parameters or optimiser state:
+ * ms_out_host[0..nblocks) = milliseconds per block, ms_out_host[nblocks] = the correspondence kernel over all
+ * frames (0 when off).  Used to cut a sequence into frame ranges of equal COST (sharding.balanced_bounds).
+ * Synchronises the stream. */
+int dh_jointopt_probe(const dh_jointopt* p, int32_t nblocks, float* ms_out_host, void* stream);
 /* device memory that can be exported to the other ranks of the box (a dedicated cudaMalloc, zero-filled) */
 int dh_dev_alloc(void** ptr, int64_t bytes);
 int dh_dev_free(void* ptr);

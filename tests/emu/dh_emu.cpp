@@ -434,4 +434,14 @@ void emu_corr_frames(const float* records, int B, int C, const float* Rmat, cons
     }
 }
 
+// k_finalize's exact scale-gradient sum: out[0] = hi, out[1] = lo of the sum of x[0..n), *val = its double value
+void emu_fx_sum(const double* x, int n, unsigned long long* out2, double* val) {
+    Fx128 t;
+    t.hi = 0; t.lo = 0ull;
+    for (int i = 0; i < n; i++) t = fx_add(t, fx_from_double(x[i]));
+    out2[0] = (unsigned long long)t.hi;
+    out2[1] = t.lo;
+    *val = fx_to_double(t);
+}
+
 }  // extern "C"

@@ -140,6 +140,15 @@ def adam(p, g, m, v, lr, t):
                    ctypes.c_double(lr), t)
 
 
+def fx_sum(x):
+    """(hi, lo) words and double value of the exact sum of the doubles x (dh_core.h Fx128)."""
+    x = np.ascontiguousarray(x, np.float64).reshape(-1)
+    out = np.zeros(2, np.uint64)
+    val = ctypes.c_double()
+    lib().emu_fx_sum(_p(x), len(x), _p(out), ctypes.byref(val))
+    return int(out[0]), int(out[1]), float(val.value)
+
+
 def mesh_moments(verts):
     v = np.asarray(verts, np.float64)
     return np.concatenate([v.sum(0), (v[:, :, None] * v[:, None, :]).sum(0).reshape(-1)])

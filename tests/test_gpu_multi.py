@@ -1,5 +1,6 @@
 """2-GPU test (skipped on a single-GPU box): frame-sharded joint optimisation over NCCL with the peer-to-peer
-halo mailboxes and with the host-driven NCCL halo must both reproduce the single-GPU run bit for bit."""
+mailboxes and with the host-driven NCCL exchange must both reproduce the single-GPU run bit for bit -- poses, loss
+history and, with optimize_object_scale, the shared scale -- for ranges cut by count and by the cost probe."""
 import os
 import socket
 
@@ -24,7 +25,7 @@ def _gpu_render_fn(vc, faces, K, size):
                  mode="silhouettes").cpu().numpy()
 
 
-def _worker(rank, world, port, seq, halo, q):
+def _worker(rank, world, port, seq, halo, q, scale_opt=False, balance="count"):
     import torch.distributed as dist
     from dynhor_b200 import synth
     from dynhor_b200.jointopt import joint_optimize
@@ -36,16 +37,18 @@ def _worker(rank, world, port, seq, halo, q):
         params = synth.to_object_parameters(seq)
         B = len(params)
         model, evo = joint_optimize(params, objvertices=seq["verts"], objfaces=np.stack([seq["faces"]] * B),
-                                    loss_weights=LW, num_iterations=ITERS, lr=1e-4, board=None, halo=halo)
+                                    loss_weights=LW, num_iterations=ITERS, lr=1e-3 if scale_opt else 1e-4, board=None,
+                                    halo=halo, optimize_object_scale=scale_opt, balance=balance)
         if rank == 0:
             q.put((model.rotations_object.detach().cpu().numpy(), model.translations_object.detach().cpu().numpy(),
-                   evo))
+                   evo, float(model.int_scales_object.detach()), model.frame_shard.bounds))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("halo", ["p2p", "nccl"])
-def test_two_gpu_sharded_equals_single_gpu(halo):
+@pytest.mark.parametrize("halo,scale_opt,balance", [("p2p", False, "count"), ("nccl", False, "count"),
+                                                     ("p2p", True, "probe"), ("nccl", True, "probe")])
+def test_two_gpu_sharded_equals_single_gpu(halo, scale_opt, balance):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from dynhor_b200 import synth
@@ -54,7 +57,9 @@ def test_two_gpu_sharded_equals_single_gpu(halo):
     seq = synth.make_sequence(B, mesh="ico3", seed=4, render_fn=_gpu_render_fn, size=128, period=60)
     params = synth.to_object_parameters(seq)
     model, evo1 = joint_optimize(params, objvertices=seq["verts"], objfaces=np.stack([seq["faces"]] * B),
-                                 loss_weights=LW, num_iterations=ITERS, lr=1e-4, board=None)
+                                 loss_weights=LW, num_iterations=ITERS, lr=1e-3 if scale_opt else 1e-4, board=None,
+                                 optimize_object_scale=scale_opt)
+    scale1 = float(model.int_scales_object.detach())
     rot1 = model.rotations_object.detach().cpu().numpy()
     tr1 = model.translations_object.detach().cpu().numpy()
     ctx = mp.get_context("spawn")
@@ -63,14 +68,16 @@ def test_two_gpu_sharded_equals_single_gpu(halo):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, seq, halo, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, seq, halo, q, scale_opt, balance)) for r in range(2)]
     for p in procs:
         p.start()
-    rot2, tr2, evo2 = q.get(timeout=300)
+    rot2, tr2, evo2, scale2, bounds = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert rot2.shape == rot1.shape
     assert np.array_equal(rot1, rot2) and np.array_equal(tr1, tr2)
+    assert scale1 == scale2 and (scale1 != 1.0) == scale_opt          # the shared scale: same bits on every rank
+    assert bounds[0] == 0 and bounds[-1] == B and len(bounds) == 3
     assert np.allclose(evo1["loss"], evo2["loss"], rtol=1e-12)
     assert np.allclose(evo1["iou_object"], evo2["iou_object"], rtol=1e-12)
