@@ -29,7 +29,8 @@ def _nvcc():
     return "nvcc"
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, only=None):
+    """only: recompile just these sources (the other objects must exist) and relink -- kernel-variant sweeps."""
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "dynhor_b200.h")]
     newest = max(os.path.getmtime(d) for d in deps)
@@ -38,6 +39,9 @@ def build(force=False, verbose=False):
     objs = []
     for s in srcs:
         obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        if only and s not in only and os.path.exists(obj):
+            objs.append(obj)
+            continue
         cmd = [_nvcc()] + ARCH + COMMON + SOURCES[s] + os.environ.get("DH_EXTRA_NVCC_FLAGS", "").split() + \
               (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, s), "-o", obj]
@@ -53,4 +57,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    only = [a for a in sys.argv[1:] if a.endswith(".cu")]
+    print(build(force="--force" in sys.argv or bool(only), verbose="--verbose" in sys.argv, only=only or None))

@@ -34,7 +34,7 @@ using namespace dh;
 constexpr int kSH = DH_STRIP_ROWS;  // strip height in raster rows (even: a strip holds whole 2x2 pooling cells)
 constexpr int kThreads = 256;      // CTA size of the backward / elementwise kernels
 #ifndef DH_RASTER_THREADS
-#define DH_RASTER_THREADS 384
+#define DH_RASTER_THREADS 416
 #endif
 #ifndef DH_RASTER_EVEN
 #define DH_RASTER_EVEN 1
@@ -46,10 +46,10 @@ constexpr int kThreads = 256;      // CTA size of the backward / elementwise ker
 #define DH_TILE_Z 1
 #endif
 #ifndef DH_DEFER_DEPTH
-#define DH_DEFER_DEPTH 0   // 1: deferred depth (see raster_hit): ~77k -> ~200 exact depth evaluations per frame and 12 %
-#endif                     // fewer instructions, bit-exact, but not faster on B200 (1.09 vs 1.08 ms): off by default
+#define DH_DEFER_DEPTH 1   // 1: deferred depth (see raster_hit): ~77k -> ~200 exact depth evaluations per frame, 12 % fewer
+#endif                     // instructions, bit-exact.  Round 1: 1.09 vs 1.08 ms (off); round 2: 0.907 vs 0.920 ms (on)
 constexpr int kRasterWarps = DH_RASTER_THREADS / 32;
-constexpr int kRasterThreads = DH_RASTER_THREADS;  // 12 warps x 2 CTAs/SM: the 64 KB z-buffer strip caps CTAs/SM at 2
+constexpr int kRasterThreads = DH_RASTER_THREADS;  // 13 warps x 2 CTAs/SM: the 64 KB z-buffer strip caps CTAs/SM at 2
 constexpr int kOwnedSmemWords = 1024;
 constexpr int kMaxIS = 512;        // largest raster resolution (bitmaps + z-buffer strip must fit shared memory)
 
@@ -384,11 +384,13 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     for (int k = 0; k < kMaskPre; k++) m_pre[k] = 0;
     if (FUSED) {
         const int S_ = s.S, wprp_ = (S_ + 31) >> 5, rows_ = s.aa ? kSH / 2 : kSH;
+        const int sh_ = 31 - __clz(wprp_);
+        const bool pow2_ = (wprp_ & (wprp_ - 1)) == 0;   // S = 256: 8 words per row, no integer division
 #pragma unroll
         for (int k = 0; k < kMaskPre; k++) {
             const int seg = warp + k * kRasterWarps;
             if (seg < rows_ * wprp_) {
-                const int ly = seg / wprp_, x = ((seg - ly * wprp_) << 5) + lane;
+                const int ly = pow2_ ? (seg >> sh_) : seg / wprp_, x = ((seg - ly * wprp_) << 5) + lane;
                 const int yo = s.aa ? ((is - 1 - (row0 + 2 * ly)) >> 1) : (is - 1 - (row0 + ly));
                 m_pre[k] = mask_tri[((size_t)b * S_ + yo) * S_ + x];
             }
@@ -681,7 +683,7 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 //           independent of task order: bit-identical results run to run.
 //   tail    (lane = item): fixed point -> float, projection / rigid-transform backward, pose accumulators.
 #ifndef DH_BWD_THREADS
-#define DH_BWD_THREADS 288
+#define DH_BWD_THREADS 352
 #endif
 #ifndef DH_BWD_MIN_CTAS
 #define DH_BWD_MIN_CTAS 2
@@ -705,7 +707,7 @@ __device__ __forceinline__ int load_fidx(const int32_t* p) {
     return *p;
 #endif
 }
-constexpr int kBwdThreads = DH_BWD_THREADS;   // 9 warps x 2 CTAs/SM is what ~109 registers and ~112 KB smem allow
+constexpr int kBwdThreads = DH_BWD_THREADS;   // 11 warps x 2 CTAs/SM (80 registers, ~97 KB smem); 9 / 10 / 12 warps measured slower
 constexpr int kBwdWarps = kBwdThreads / 32;
 constexpr int kTaskCap = 96;
 #ifndef DH_CHUNK_FACES

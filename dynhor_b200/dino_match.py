@@ -39,9 +39,17 @@ def build_bank(feats, mask=None):
 
 def dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
     """frame_bank [Fm,K] bf16, templ_bank [N,K] bf16 (from build_bank) -> (dino_cos [Fm,N] fp32 or None,
-    topk values [Fm,k], topk indices [Fm,k] int64), largest first like torch.topk(largest=True)."""
+    topk values [Fm,k], topk indices [Fm,k] int64), largest first like torch.topk(largest=True).  With the scores:
+    the torch.library op dynhor::dino_topk (dynhor_b200/ops.py)."""
     if not (frame_bank.is_cuda and templ_bank.is_cuda):
         raise _lib.DynhorError("dynhor_b200.dino_match needs CUDA tensors (no CPU fallback)")
+    if return_scores:
+        from . import ops  # noqa: F401  (registers torch.ops.dynhor.*)
+        return torch.ops.dynhor.dino_topk(frame_bank, templ_bank, int(k))
+    return _dino_cos_topk(frame_bank, templ_bank, k, return_scores=False)
+
+
+def _dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
     assert frame_bank.dtype == torch.bfloat16 and templ_bank.dtype == torch.bfloat16
     assert frame_bank.is_contiguous() and templ_bank.is_contiguous()
     Fm, K = frame_bank.shape
@@ -62,28 +70,32 @@ def dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
 
 
 def select_view(dino_cos, topk_indices, render_rotations, rotations_init=None, former_max_idx=None, use_former=True):
-    """Candidate gating of pose_initializtion.py:298-321 for ONE frame, on the scores / top-k computed above.
-    dino_cos [N]; topk_indices [>=10] (largest first); render_rotations [N,3,3]; rotations_init [1,3,3] = the
-    previous frame's optimised rotation.  Returns max_idx (int, -1 = keep the previous rotation)."""
+    """The sequential part of the view selection (pose_initializtion.py:298-321) for ONE frame, on the scores and
+    top-k indices the kernels produced for all frames at once.
+        dino_cos [N]; topk_indices [>= 10], best first; render_rotations [N,3,3];
+        rotations_init [1,3,3] = the previous frame's optimised rotation (None on the first frame);
+        former_max_idx = the template the previous frame picked (-1: it kept its predecessor's rotation).
+    Returns the template index, or -1 = "keep the previous rotation" (:323-325).
+    Among the 5 best-scoring views (10 after a frame without a pick) the one closest in angle to the previous pose
+    wins unless it is more than 85 degrees from that pose or from the previous pick; otherwise the view nearest to
+    the previous pose is taken if it is within 15 degrees, within 30 degrees of the previous pick and scores no worse
+    than one standard deviation below the best score."""
     if not use_former or rotations_init is None:
         return int(topk_indices[0])
-    rel_angle_full = rotation_angle_difference(rotations_init.clone(), render_rotations.transpose(1, 2).clone())
-    if former_max_idx != -1:
-        former_rel_angle_full = rotation_angle_difference(
-            render_rotations[former_max_idx:former_max_idx + 1].transpose(1, 2).clone(),
-            render_rotations.transpose(1, 2).clone())
-        cos_topk_num = 5
-    else:
-        former_rel_angle_full = torch.zeros_like(rel_angle_full)
-        cos_topk_num = 10
-    indices = topk_indices[:cos_topk_num]
-    rel_angle = rel_angle_full[indices]
-    max_idx = indices[torch.argmin(rel_angle)].item()
-    if rel_angle_full[max_idx] > 85.0 or former_rel_angle_full[max_idx] > 85.0:
-        max_idx = -1
-    if max_idx == -1 and torch.min(rel_angle_full) < 15.0:
-        max_idx = int(torch.argmin(rel_angle_full))
-        if (former_max_idx != -1 and former_rel_angle_full[max_idx].item() > 30.0) or \
-                dino_cos[max_idx] < (torch.max(dino_cos) - torch.std(dino_cos)):
-            max_idx = -1
-    return int(max_idx)
+    views = render_rotations.transpose(1, 2)
+    to_prev = rotation_angle_difference(rotations_init, views)           # every template against the previous pose
+    has_former = former_max_idx != -1
+    to_former = rotation_angle_difference(views[former_max_idx:former_max_idx + 1], views) if has_former \
+        else torch.zeros_like(to_prev)
+    shortlist = topk_indices[:5 if has_former else 10]
+    pick = int(shortlist[torch.argmin(to_prev[shortlist])])
+    if not (to_prev[pick] > 85.0 or to_former[pick] > 85.0):
+        return pick
+    near = int(torch.argmin(to_prev))
+    if not (to_prev[near] < 15.0):
+        return -1
+    if has_former and to_former[near].item() > 30.0:
+        return -1
+    if dino_cos[near] < dino_cos.max() - dino_cos.std():
+        return -1
+    return near

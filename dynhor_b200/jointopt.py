@@ -209,7 +209,7 @@ class FusedJointOpt:
         self.p = p
         sharded = self.shard.world > 1
         self.halo_mode = halo if (sharded and exchange) else "none"
-        self._mail, self._keep = None, []
+        self._mail, self._keep, self._handle = None, [], None
         self._sync_halo()
         if self.halo_mode == "p2p":
             self._setup_p2p()
@@ -253,7 +253,15 @@ class FusedJointOpt:
 
     # -- execution --------------------------------------------------------------------------------------------
     def run(self, n_iters, use_graph=True):
-        """n_iters fused iterations on the current stream; no host synchronisation (single rank / p2p)."""
+        """n_iters fused iterations on the current stream; no host synchronisation (single rank / p2p).  Dispatched
+        as the torch.library op dynhor::jointopt_run, which declares the parameters it updates in place."""
+        from . import ops
+        if self._handle is None:
+            self._handle = ops.register_fused(self)
+        torch.ops.dynhor.jointopt_run(self.model.rotations_object.detach(), self.model.translations_object.detach(),
+                                      self.scale.detach(), self._handle, int(n_iters), bool(use_graph))
+
+    def _run(self, n_iters, use_graph=True):
         lib = _lib.load()
         if self.halo_mode != "nccl":
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), int(n_iters), int(use_graph), _lib.stream_ptr()),
@@ -373,10 +381,13 @@ def _stack_frames(frames, key, pick=None, dtype=None):
         out = torch.cat(ts)
     elif t0.is_pinned() and t0.numel() * t0.element_size() >= 65536:
         out = torch.empty((sum(int(t.shape[0]) for t in ts),) + tuple(t0.shape[1:]), dtype=t0.dtype, device="cuda")
-        row = 0
-        for t in ts:
-            out[row:row + t.shape[0]].copy_(t, non_blocking=True)
-            row += t.shape[0]
+        if all(t.shape[0] == 1 for t in ts):
+            torch._foreach_copy_(list(out.split(1)), ts, non_blocking=True)   # one dispatch for all the copies
+        else:
+            row = 0
+            for t in ts:
+                out[row:row + t.shape[0]].copy_(t, non_blocking=True)
+                row += t.shape[0]
     else:
         n = sum(int(t.shape[0]) for t in ts)
         stage = torch.empty((n,) + tuple(t0.shape[1:]), dtype=t0.dtype, pin_memory=True)

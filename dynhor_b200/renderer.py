@@ -5,7 +5,8 @@ Replaces, for camera_mode="projection" and mode="silhouettes":
     renderer(verts, faces, mode="silhouettes") -> [B, image_size, image_size]  utils/losses.py:68
     nr.projection(verts, K, R, t, dist_coeffs, orig_size)                      utils/losses.py:48-55
 The rasteriser forward and its pseudo-gradient backward are the CUDA kernels of libdynhor_b200.so
-(dh_sil_forward / dh_sil_backward); everything fails loudly without them.
+(dh_sil_forward / dh_sil_backward), reached through the torch.library ops dynhor::sil_forward / dynhor::sil_backward
+(dynhor_b200/ops.py); everything fails loudly without them.
 """
 import ctypes
 
@@ -107,27 +108,6 @@ class SilhouetteState:
         return gv
 
 
-class SilhouetteFn(torch.autograd.Function):
-    """rend = silhouettes(verts); backward = the renderer's edge-scan pseudo-gradient."""
-
-    @staticmethod
-    def forward(ctx, verts, state):
-        rend, v = state.forward(verts)
-        ctx.state = state
-        ctx.version = state.version
-        ctx.save_for_backward(v)
-        return rend
-
-    @staticmethod
-    def backward(ctx, grad_rend):
-        (v,) = ctx.saved_tensors
-        st = ctx.state
-        if st.version != ctx.version:  # the state was reused by a later forward: rebuild its maps
-            st.forward(v)
-            ctx.version = st.version
-        return st.backward(v, grad_rend), None
-
-
 class Renderer(torch.nn.Module):
     """`neural_renderer.Renderer` for the silhouette mode the reference uses (losses.py:36-40,68)."""
 
@@ -152,16 +132,14 @@ class Renderer(torch.nn.Module):
         self.near, self.far = near, far
         self.rasterizer_eps = DEFAULT_EPS
         self._state = None
-        self._state_key = None
+        self._faces_key, self._faces_i32 = None, None
 
-    def _get_state(self, B, V, faces, K):
-        f = shared_faces(faces)
-        key = (B, V, f.shape[0], K.data_ptr(), K._version, faces.data_ptr(), faces._version)
-        if self._state is None or self._state_key != key:
-            self._state = SilhouetteState(B, V, f, K, self.image_size, self.anti_aliasing, self.near, self.far,
-                                          self.rasterizer_eps, float(self.orig_size))
-            self._state_key = key
-        return self._state
+    def _faces(self, faces):
+        """[B,F,3] / [F,3] -> the shared int32 [F,3] list, checked once per faces tensor (not per call)."""
+        key = (faces.data_ptr(), faces._version, tuple(faces.shape))
+        if self._faces_key != key:
+            self._faces_i32, self._faces_key = shared_faces(faces), key
+        return self._faces_i32
 
     def forward(self, vertices, faces, textures=None, mode=None, K=None, R=None, t=None, dist_coeffs=None,
                 orig_size=None):
@@ -185,6 +163,13 @@ class Renderer(torch.nn.Module):
             eye = torch.eye(3, device=R.device, dtype=R.dtype).expand_as(R)
             if not (bool((R == eye).all()) and bool((t == 0).all())):
                 vertices = torch.matmul(vertices, R.transpose(2, 1)) + t
-        B, V = vertices.shape[0], vertices.shape[1]
-        state = self._get_state(B, V, faces, K)
-        return SilhouetteFn.apply(vertices, state)
+        if not vertices.is_cuda:
+            raise _lib.DynhorError("dynhor_b200 renderer needs CUDA tensors (no CPU fallback)")
+        from . import ops   # registers torch.ops.dynhor.*
+        f = self._faces(faces)
+        args = (int(self.image_size), bool(self.anti_aliasing), float(self.near), float(self.far),
+                float(self.rasterizer_eps), float(self.orig_size))
+        # torch.library custom op: C-ABI forward, edge-scan pseudo-gradient registered as its autograd formula
+        rend = torch.ops.dynhor.sil_forward(vertices, f, K, *args)
+        self._state = ops.silhouette_state(vertices, f, K, *args)   # the scratch maps of this call (tests, debugging)
+        return rend

@@ -1,9 +1,9 @@
 """oracle/dino_oracle.py -- TEST INFRASTRUCTURE ONLY (CPU oracle; never a product path).
 
 The view-selection score and top-k of ObjTracker/pose_initializtion.py:295-296,299,309 on CPU, expression kept
-verbatim (one frame against N templates), fp32.  Pinned by tests/golden/dino_small.npz, generated by
-tests/golden/make_golden.py from this same expression (the reference has no importable function for it: it is
-inline code inside find_optimal_pose, which needs pytorch3d/detectron2 to import).
+verbatim (one frame against N templates), fp32.  PARITY UNPINNED beyond that: the reference has no importable
+function for it (it is inline code inside find_optimal_pose, which needs pytorch3d / detectron2 to import) and no
+test or fixture; the expression itself is the contract.
 """
 import torch
 

@@ -614,8 +614,8 @@ def test_adam_step_kernel_vs_torch_adam(lr):
             bar = 1e-6 * lr + np.spacing(np.abs(ref.detach().numpy()))
             assert (d <= bar).all(), (t, float(d.max()), lr)
             st = opt.state[ref]
-            assert torch.allclose(m.cpu(), st["exp_avg"], rtol=1e-6, atol=0)
-            assert torch.allclose(v.cpu(), st["exp_avg_sq"], rtol=1e-6, atol=0)
+            for ours, theirs in ((m, st["exp_avg"]), (v, st["exp_avg_sq"])):   # lerp / addcmul roundings: ~1 ulp of
+                assert torch.allclose(ours.cpu(), theirs, rtol=1e-6, atol=1e-6 * float(theirs.abs().max()))  # the state
 
 
 @pytest.mark.parametrize("name", ["s64_b5", "s64_b4_scale"])

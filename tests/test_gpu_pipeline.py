@@ -48,3 +48,31 @@ def test_masks_to_target_masks_to_joint_optimisation():
     iou = np.asarray(evo["iou_object"])
     assert iou[0] > 0.6 and iou[-1] > iou[0] + 0.03 and iou[-1] > 0.93, (iou[0], iou[-1])
     assert evo["loss_sil_obj"][-1] < 0.5 * evo["loss_sil_obj"][0]
+
+
+def test_registered_ops_on_the_device():
+    """torch.library ops (dynhor_b200/ops.py): opcheck (schema, fake-tensor consistency, autograd registration) with
+    real CUDA inputs, and the op path == the module path."""
+    from torch.library import opcheck
+    import dynhor_b200.ops  # noqa: F401
+    from dynhor_b200 import synth
+    from dynhor_b200.dino_match import build_bank
+    from dynhor_b200.renderer import Renderer
+    seq = synth.make_sequence(3, mesh="ico2", seed=1, render_fn=None, size=64)
+    vc = torch.from_numpy((seq["verts"].astype(np.float64)[None] @ seq["R_gt"].astype(np.float64)
+                           + seq["T_gt"].astype(np.float64)).astype(np.float32)).cuda()
+    faces = torch.from_numpy(seq["faces"]).to(torch.int32).cuda()
+    K = torch.from_numpy(seq["K_roi"]).cuda()
+    args = (vc.requires_grad_(True), faces, K, 64, True, 0.1, 100.0, 1e-4, 1.0)
+    opcheck(torch.ops.dynhor.sil_forward.default, args,
+            test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    rend = torch.ops.dynhor.sil_forward(*args)
+    mod = Renderer(image_size=64, K=K, R=torch.eye(3)[None].cuda(), t=torch.zeros(1, 3).cuda(), orig_size=1)
+    assert torch.equal(mod(vc.detach(), faces, mode="silhouettes"), rend) and float(rend.sum()) > 0
+    g = torch.rand_like(rend)
+    (gv,) = torch.autograd.grad(rend, vc, g)
+    assert torch.equal(gv, torch.ops.dynhor.sil_backward(vc.detach(), faces, K, g, 64, True, 0.1, 100.0, 1e-4, 1.0))
+    assert float(gv.abs().sum()) > 0
+    d = synth.make_dino_features(40, 6, 24, 64, seed=2, device="cuda")
+    fb, tb = build_bank(d["frames"], d["masks"]), build_bank(d["templ"])
+    opcheck(torch.ops.dynhor.dino_topk.default, (fb, tb, 5), test_utils=("test_schema", "test_faketensor"))

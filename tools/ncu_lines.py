@@ -97,6 +97,35 @@ def main():
                 tot[i] += vals[i]
         print(f"   total warp-inst {tot[0]:.3e}  thread-inst {tot[1]:.3e}  avg lanes {tot[1] / max(tot[0], 1):.1f}  "
               f"samples {tot[2]}")
+        if "--regions" in sys.argv:
+            # --regions FILE:a-b=name,FILE:c-d=name,...  -> one row per named line range (+ the rest per file)
+            spec = sys.argv[sys.argv.index("--regions") + 1]
+            regs = []
+            for part in spec.split(","):
+                rng, name = part.split("=")
+                f, ab = rng.split(":")
+                a, b = ab.split("-")
+                regs.append((f, int(a), int(b), name))
+            ragg = defaultdict(lambda: [0, 0, 0])
+            for loc, v in agg.items():
+                key = "other" if loc is None else f"rest of {loc[0]}"
+                if loc is not None:
+                    for f, a, b, name in regs:
+                        if loc[0] == f and a <= loc[1] <= b:
+                            key = f"{name} {a}-{b}"
+                            break
+                for i in range(3):
+                    ragg[key][i] += v[i]
+            print("   region                                   warp-inst%  lanes  samples%")
+            for key, v in sorted(ragg.items(), key=lambda kv: -kv[1][0]):
+                print(f"   {key:40s} {100.0 * v[0] / max(tot[0], 1):8.1f}  {v[1] / max(v[0], 1):5.1f}  "
+                      f"{100.0 * v[2] / max(tot[2], 1):8.1f}")
+            continue
+        if "--dump" in sys.argv:
+            for loc, v in sorted(agg.items(), key=lambda kv: (kv[0] is None, kv[0])):
+                name = f"{loc[0]}:{loc[1]}" if loc else "?"
+                print(f"   {name:24s} {v[0]:12d} {v[1] / max(v[0], 1):5.1f} {v[2]:8d}")
+            continue
         print("   file:line                warp-inst%  lanes  samples%")
         for loc, v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
             name = f"{loc[0]}:{loc[1]}" if loc else "?"
