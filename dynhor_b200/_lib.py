@@ -58,6 +58,7 @@ class DhJointOpt(ctypes.Structure):
         ("Rmat", c_p), ("smooth_terms", c_p), ("loss_counts", c_p), ("partials", c_p), ("frame_terms", c_p),
         ("nchunks", c_i),
         ("corr", DhCorr),
+        ("loss_mode", c_i), ("lw_offscreen", c_d), ("offscreen", c_p), ("frame_coef", c_p),
     ]
 
 
@@ -104,6 +105,7 @@ MAILBOX_WORDS = 512      # DH_MAILBOX_WORDS
 MAX_RANKS = 16           # DH_MAX_RANKS
 SCALE_LOCAL, SCALE_P2P, SCALE_DEFERRED = 0, 1, 2
 STATUS_HALO_TIMEOUT = 1
+LOSS_JOINT, LOSS_STAGE1 = 0, 1
 
 _LIB = None
 

@@ -5,13 +5,15 @@
 // dynhor_b200.h, oracle/corr_oracle.py) and the term is off unless the caller passes records and lw_corr_obj.
 //
 // k_corr is the one purely HBM-bound kernel of the iteration: 24 bytes per record are read once, ~60 flops each.
-//   * persistent grid (3 CTAs per SM); the B * ceil(C/1024) record tiles are cut into gridDim.x equal contiguous
-//     ranges, so every CTA streams the same number of bytes (no wave tail);
+//   * persistent grid (3 CTAs per SM); the B * ceil(C/1024) record tiles are cut into gridDim.x contiguous ranges of
+//     (nearly) equal length whose ends are moved to SEGMENT boundaries (a segment = 8 consecutive tiles of one frame);
+//     a segment is therefore always summed by one CTA, in one fixed order, whatever B and the grid are: a frame's
+//     result does not depend on how many frames share the launch (frame-sharded runs reproduce single-GPU bits);
 //   * tiles (1024 records = 24 KB) arrive through cp.async.bulk (TMA, no tensor map needed for a 1-D copy) into a
 //     3-stage shared-memory ring guarded by mbarriers: one thread issues, 256 threads consume;
 //   * shared-memory reads are 8-byte accesses at an odd stride (3 float2 per record): conflict-free;
-//   * 13 accumulators per thread, reduced per (frame, CTA) with warp shuffles in a fixed order and stored to the
-//     frame's partial-sum slot: no atomics, bit-reproducible.
+//   * 13 accumulators per thread, reduced per segment with warp shuffles in a fixed order and stored to the
+//     segment's slot of the frame: no atomics, bit-reproducible.
 #include "dh_common.h"
 #include "dh_core.h"
 
@@ -21,6 +23,7 @@ using namespace dh;
 
 constexpr int kCorrThreads = 256;
 constexpr int kCorrTile = 1024;                       // records per stage
+constexpr int kSegTiles = 8;                          // tiles per segment (the unit of summation)
 #ifndef DH_CORR_STAGES
 #define DH_CORR_STAGES 3
 #endif
@@ -63,14 +66,22 @@ struct CorrPlan { int grid, nslots, tpf; };
 __host__ __device__ inline CorrPlan corr_plan(int B, int C, int sms) {
     CorrPlan p;
     p.tpf = (C + kCorrTile - 1) / kCorrTile;
-    const long long T = (long long)B * p.tpf;
+    p.nslots = (p.tpf + kSegTiles - 1) / kSegTiles;   // segments per frame
+    const long long segs = (long long)B * p.nslots;
     long long g = (long long)sms * kCorrCtasPerSm;
-    if (g > T) g = T;
+    if (g > segs) g = segs;
     if (g < 1) g = 1;
     p.grid = (int)g;
-    const int m = (int)(T / g);                       // smallest range, >= 1 tile
-    p.nslots = (p.tpf + m - 1) / m + 1;
     return p;
+}
+
+// First tile of CTA c's range: the cut c * T / G moved forward to the next segment start.
+__host__ __device__ inline long long corr_cut(long long c, long long T, long long G, int tpf) {
+    const long long t = c * T / G;
+    const long long b = t / tpf;
+    const int k = (int)(t - b * tpf);
+    const int ks = ((k + kSegTiles - 1) / kSegTiles) * kSegTiles;   // segment starts inside a frame: 0, 8, 16, ...
+    return b * tpf + (ks < tpf ? ks : tpf);
 }
 
 // tile t of the flattened (frame, tile-in-frame) list -> records pointer and count
@@ -147,7 +158,7 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
     __shared__ float red[kCorrThreads / 32][13];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long T = (long long)B * tpf, G = gridDim.x;
-    const long long t0 = (long long)blockIdx.x * T / G, t1 = ((long long)blockIdx.x + 1) * T / G;
+    const long long t0 = corr_cut(blockIdx.x, T, G, tpf), t1 = corr_cut((long long)blockIdx.x + 1, T, G, tpf);
     const int ntiles = (int)(t1 - t0);
     if (tid == 0) {
         for (int i = 0; i < kCorrStages; i++) mbar_init(smem_u32(&bars[i]), 1);
@@ -170,10 +181,12 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
     for (int i = 0; i < ntiles; i++) {
         const long long t = t0 + i;
         const int b = (int)(t / tpf), k = (int)(t - (long long)b * tpf);
-        if (b != cur_b) {  // first tile of a frame segment: its pose and intrinsics
-            cur_b = b;
+        if (k % kSegTiles == 0) {
 #pragma unroll
             for (int j = 0; j < 13; j++) acc[j] = bc(0.0f);
+        }
+        if (b != cur_b) {  // first tile of a frame: its pose and intrinsics
+            cur_b = b;
 #pragma unroll
             for (int j = 0; j < 9; j++) P.Rs[j] = bc(s_abs * Rmat[9 * b + j]);
 #pragma unroll
@@ -198,8 +211,8 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
             mbar_expect_tx(smem_u32(&bars[stage]), (uint32_t)nr * kRecBytes);
             bulk_load(smem_u32(ring + stage * kStageBytes), src, (uint32_t)nr * kRecBytes, smem_u32(&bars[stage]));
         }
-        // last tile this CTA holds of frame b: reduce and store the segment's sums into the frame's slot
-        if (i == ntiles - 1 || k == tpf - 1) {
+        // last tile of a segment: reduce and store its sums into the segment's slot of frame b
+        if (k % kSegTiles == kSegTiles - 1 || k == tpf - 1) {
 #pragma unroll
             for (int j = 0; j < 13; j++) {
                 float v = acc[j].x + acc[j].y;
@@ -211,9 +224,7 @@ k_corr(const float* __restrict__ records, int B, int C, int tpf, int nslots, con
                 float v = 0.0f;
                 if (tid < 13)
                     for (int w = 0; w < kCorrThreads / 32; w++) v += red[w][tid];
-                const long long first = (((long long)b * tpf + 1) * G - 1) / T;   // first CTA that holds a tile of b
-                const int slot = (int)(blockIdx.x - first);
-                partials[((size_t)b * nslots + slot) * 16 + tid] = v;
+                partials[((size_t)b * nslots + k / kSegTiles) * 16 + tid] = v;
             }
             __syncthreads();
         }

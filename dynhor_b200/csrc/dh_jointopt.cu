@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kThreads)
 k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const float* __restrict__ trans,
           const float* __restrict__ scale, const float* __restrict__ K, float orig, float4* __restrict__ proj,
           int V, int32_t* __restrict__ bin_count, int nstrips, int32_t* __restrict__ loss_counts,
-          uint32_t* __restrict__ owned, int owned_words) {
+          uint32_t* __restrict__ owned, int owned_words, float* __restrict__ offscreen = nullptr,
+          float lw_offscreen = 0.0f, float far_ = 0.0f) {
     const int b = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < owned_words; i += gridDim.x * blockDim.x)
         owned[(size_t)b * owned_words + i] = 0u;
@@ -159,6 +160,29 @@ k_project(const float* __restrict__ verts, const float* __restrict__ Rmat, const
     float u, w;
     project_vertex(c, Km, orig, &u, &w);
     proj[(size_t)b * V + v] = make_float4(u, w, c[2], 0.0f);
+    if (FROM_POSE && offscreen != nullptr) {
+        // stage-1 off-screen penalty (pose_initializtion.py:119-141): how far the projected vertex sticks out of
+        // [-1,1]^2 x (0, far), and its gradient through the projection and the rigid transform.  Zero for any sane
+        // pose, so the (float, order-dependent) atomics below are off the common path.
+        const float ex = fmaxf(u - 1.0f, 0.0f) + fmaxf(-1.0f - u, 0.0f), ey = fmaxf(w - 1.0f, 0.0f) + fmaxf(-1.0f - w, 0.0f);
+        const float ez = fmaxf(-c[2], 0.0f) + fmaxf(c[2] - far_, 0.0f);
+        const float loss = ex + ey + ez;
+        if (loss > 0.0f) {
+            const float gu = lw_offscreen * ((u > 1.0f ? 1.0f : 0.0f) - (u < -1.0f ? 1.0f : 0.0f));
+            const float gv = lw_offscreen * ((w > 1.0f ? 1.0f : 0.0f) - (w < -1.0f ? 1.0f : 0.0f));
+            const float gz = lw_offscreen * ((c[2] > far_ ? 1.0f : 0.0f) - (c[2] < 0.0f ? 1.0f : 0.0f));
+            float gc[3];
+            project_vertex_backward(c, Km, orig, gu, gv, gc);
+            gc[2] += gz;
+            float* o = offscreen + (size_t)b * 16;
+            const float s_abs = fabsf(scale[0]);
+            const float vo[3] = {verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]};
+            for (int j = 0; j < 3; j++) atomicAdd(o + j, gc[j]);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) atomicAdd(o + 3 + 3 * i + j, (s_abs * vo[i]) * gc[j]);
+            atomicAdd(o + 13, loss);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ binning
@@ -798,8 +822,13 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
+// frame_coef != NULL (stage-1 IoU loss, pose_initializtion.py:143-155): the loss 1 - I / (U + 1e-6) of a frame has only
+// two gradient values -- -lw / (U + eps) on target pixels, +lw I / (U + eps)^2 elsewhere (times keep) -- known once the
+// whole frame is rasterised; they are stored per frame, in the units the backward uses for the masked-L2 loss
+// (pixel gradient = 2 * coefficient), together with the frame's gradient bound gmax.
 __global__ void __launch_bounds__(kNegThreads)
-k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
+k_neg_maps(const dh_sil s, int build_lists, int list_cap, const int32_t* __restrict__ loss_counts,
+           float* __restrict__ frame_coef, float lw_iou) {
     extern __shared__ uint32_t nm_words[];  // [is][wpr + 1] row-major; the column-side CTA transposes it in place
                                             // (rows padded by one word: a thread per line and the block transposes
                                             // stay conflict-free); then the frame's coverage bitmap [is][wpr]
@@ -811,6 +840,13 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int axis_lo = blockIdx.y, axis_hi = blockIdx.y;
     const int warp = tid >> 5, lane = tid & 31;
+    if (frame_coef != nullptr && blockIdx.y == 0 && tid == 0) {
+        const float I = (float)loss_counts[b * 4 + 1] * 0.25f, U = (float)loss_counts[b * 4 + 2] * 0.25f + 0.000001f;
+        const float g_neg = lw_iou / U, g_pos = (lw_iou * I / U) / U;
+        frame_coef[2 * b + 0] = 0.5f * g_neg;
+        frame_coef[2 * b + 1] = 0.5f * g_pos;
+        s.gmax[b] = fmaxf(g_neg, g_pos);
+    }
     uint32_t* words = nm_words;
     const int wps = wpr + 1;
     uint32_t* wordsT = nm_words;            // after the in-place transpose
@@ -924,7 +960,8 @@ struct NegLists {   // both axes behind one base pointer (indexing an array of p
 };
 template <bool FUSED, bool LISTS>
 __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m,
-                                             const NegLists& nl, float eps, float fpscale, float gcoef) {
+                                             const NegLists& nl, float eps, float fpscale, float gcoef,
+                                             float gcoef_pos) {
     const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1;
     const int d0 = LISTS ? (int)((t >> 9) & 511u) : (int)((t >> 9) & 1023u);
     const int resume = LISTS ? (int)(t >> 18) : (int)(t >> 19);
@@ -1063,7 +1100,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             if (!alpha_at(m, r, c)) continue;
             if (!pos_at(m, r, c)) continue;
             if (m.fidx[r * is + c] != fn) continue;
-            const float diff = (1.0f - 0.0f) * grad_value<FUSED>(m, r, c, false, gcoef);
+            const float diff = (1.0f - 0.0f) * grad_value<FUSED>(m, r, c, false, gcoef_pos);
             if (diff <= 0.0f) continue;
             sa += edge_term_fast(ec.ka, diff, d1, d1_cross, eps, two_over_is);
             sb += edge_term_fast(ec.kb, diff, d1, d1_cross, eps, two_over_is);
@@ -1082,7 +1119,8 @@ template <bool FUSED, bool LISTS>
 __global__ void __launch_bounds__(kBwdThreads, DH_BWD_MIN_CTAS)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
-           float* __restrict__ grad_verts, int nchunks, float gcoef, int only_overflow) {
+           float* __restrict__ grad_verts, int nchunks, float gcoef_all, int only_overflow,
+           const float* __restrict__ frame_coef) {
     extern __shared__ __align__(16) uint32_t smw[];
     __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
@@ -1108,6 +1146,9 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         if (over == LISTS) return;
     }
     const float gmax = s.gmax[b];
+    // dL/dpixel coefficients: one number for the masked-L2 loss; per frame (wanted / unwanted pixels) for the IoU loss
+    const float gcoef = frame_coef ? frame_coef[2 * b] : gcoef_all;
+    const float gcoef_pos = frame_coef ? frame_coef[2 * b + 1] : gcoef_all;
 
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
     const int per = (s.F + nchunks - 1) / nchunks;
@@ -1366,7 +1407,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                 n_tasks -= 32;
                 const uint2 tk = W.tq[n_tasks + lane];
                 const float dc = __uint_as_float(tk.y);
-                const uint32_t cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef);
+                const uint32_t cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef, gcoef_pos);
                 __syncwarp();
                 const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
                 if (cont) {
@@ -1385,7 +1426,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
             if (lane < nt) {
                 const uint2 tk = W.tq[n_tasks + lane];
                 dc = __uint_as_float(tk.y);
-                cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef);
+                cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef, gcoef_pos);
             }
             __syncwarp();
             const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
@@ -1507,6 +1548,8 @@ __global__ void k_pose_prep(const dh_jointopt p) {
     for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
     rot6d_to_R(r6, Rm);
     for (int i = 0; i < 9; i++) p.Rmat[9 * b + i] = Rm[i];
+    if (p.offscreen != nullptr)
+        for (int i = 0; i < 16; i++) p.offscreen[(size_t)b * 16 + i] = 0.0f;
     const float* hp = p.halo_prev;
     const float* hn = p.halo_next;
     float hbuf[2][9];
@@ -1568,6 +1611,13 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
         gs += coef * sgn * dot;
         corr_loss = q[12];
     }
+    double off_loss = 0.0;
+    if (p.offscreen != nullptr && mode != 2) {   // stage-1 off-screen penalty: accumulated by k_project
+        const float* o = p.offscreen + (size_t)b * 16;
+        for (int i = 0; i < 3; i++) gT[i] += (double)o[i];
+        for (int i = 0; i < 9; i++) G[i] += (double)o[3 + i];
+    }
+    if (p.offscreen != nullptr) off_loss = (double)p.offscreen[(size_t)b * 16 + 13];
     float r6[6];
     for (int i = 0; i < 6; i++) r6[i] = p.rot6d[6 * b + i];
     double g6[6];
@@ -1580,6 +1630,7 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
     ft[2] = st[13];
     ft[3] = gs;
     ft[4] = corr_loss;
+    ft[5] = off_loss;
 
     if (mode == 2) return;
     if (mode == 1) {
@@ -1589,7 +1640,7 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
     }
     const int t = *p.step + 1;
     float step_rot, step_tr, bc2s;
-    adam_bias(t, p.lr * 10.0, &step_rot, &bc2s);
+    adam_bias(t, p.lr * (p.loss_mode == DH_LOSS_STAGE1 ? 1.0 : 10.0), &step_rot, &bc2s);   // one group in stage 1
     adam_bias(t, p.lr, &step_tr, &bc2s);
     for (int i = 0; i < 6; i++)
         adam_update(&p.rot6d[6 * b + i], &p.adam_m_rot[6 * b + i], &p.adam_v_rot[6 * b + i], (float)g6[i],
@@ -1616,12 +1667,12 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int 
     __shared__ double red[kThreads / 32][4];
     __shared__ Fx128 redg[kThreads / 32];
     __shared__ Fx128 s_parts[DH_MAX_RANKS];
-    double a[4] = {0.0, 0.0, 0.0, 0.0};   // 16*SSE, iou, pair_sse, corr loss
+    double a[4] = {0.0, 0.0, 0.0, 0.0};   // 16*SSE, iou, pair_sse (stage 1: off-screen loss), corr loss
     Fx128 g;
     g.hi = 0; g.lo = 0ull;
     for (int b = threadIdx.x; b < p.sil.B; b += kThreads) {
         const double* ft = p.frame_terms + (size_t)b * 8;
-        a[0] += ft[0]; a[1] += ft[1]; a[2] += ft[2]; a[3] += ft[4];
+        a[0] += ft[0]; a[1] += ft[1]; a[2] += (p.loss_mode == DH_LOSS_STAGE1) ? ft[5] : ft[2]; a[3] += ft[4];
         g = fx_add(g, fx_from_double(ft[3]));
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1649,9 +1700,15 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int 
         if (mode != 0 || step < p.max_iters) {
             double* h = p.hist + (size_t)row * 4;
             const double N = (double)(p.B_total - 1) * (double)p.sil.V * 3.0;
-            h[0] = (p.B_total > 1) ? t[2] / N : 0.0;
-            h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
-            h[2] = t[1] / (double)p.B_total;
+            if (p.loss_mode == DH_LOSS_STAGE1) {   // sums over the frames of (off-screen penalty, 1 - IoU); mean IoU
+                h[0] = t[2];
+                h[1] = (double)p.sil.B - t[1];
+                h[2] = t[1] / (double)p.B_total;
+            } else {
+                h[0] = (p.B_total > 1) ? t[2] / N : 0.0;
+                h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
+                h[2] = t[1] / (double)p.B_total;
+            }
             h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0) ? t[3] / p.corr.w_sum : 0.0;
         }
         redg[0] = tg;   // this rank's exact partial
@@ -1779,9 +1836,11 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     const dh_sil& s = p.sil;
     const int is = raster_size(s), nstrips = is / kSH, B = s.B;
     dim3 gv((s.V + kThreads - 1) / kThreads, B);
+    const bool stage1 = p.loss_mode == DH_LOSS_STAGE1;
     k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
                                               reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
-                                              p.loss_counts, s.owned, (2 * s.F + 31) / 32);
+                                              p.loss_counts, s.owned, (2 * s.F + 31) / 32,
+                                              stage1 ? p.offscreen : nullptr, (float)p.lw_offscreen, s.far_);
     DH_LAUNCH_OK("k_project");
     DH_REC(2);
     int rc = launch_forward_common(s, st);
@@ -1798,7 +1857,9 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     if (forward_only) return DH_OK;
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
     if (rc) return rc;
-    k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap());
+    float* fcoef = stage1 ? p.frame_coef : nullptr;
+    k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap(), p.loss_counts, fcoef,
+                                                                        (float)p.lw_sil);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
     rc = set_smem(k_backward<true, true>, sl);
@@ -1806,11 +1867,11 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     rc = set_smem(k_backward<true, false>, sb);
     if (rc) return rc;
     k_backward<true, true><<<dim3(p.nchunks, B), kBwdThreads, sl, st>>>(
-        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0);
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0, fcoef);
     DH_LAUNCH_OK("k_backward<lists>");
     // frames with more contributing pixels than the lists hold (only these CTAs do any work)
     k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
-        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1);
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1, fcoef);
     DH_LAUNCH_OK("k_backward<bitmaps>");
     return DH_OK;
 }
@@ -1876,6 +1937,8 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
     q.Rmat += o * 9;
     q.loss_counts += o * 4;
     q.partials += o * p.nchunks * 16;
+    if (q.offscreen != nullptr) q.offscreen += o * 16;
+    if (q.frame_coef != nullptr) q.frame_coef += o * 2;
     return q;
 }
 
@@ -1894,6 +1957,12 @@ int check_plan(const dh_jointopt* p) {
                "nchunks must be >= ceil(F / 1024)");
     DH_REQUIRE(p->B_total >= p->sil.B, "B_total < B");
     DH_REQUIRE(p->max_iters >= 0, "max_iters < 0");
+    DH_REQUIRE(p->loss_mode == DH_LOSS_JOINT || p->loss_mode == DH_LOSS_STAGE1, "bad loss_mode");
+    if (p->loss_mode == DH_LOSS_STAGE1) {
+        DH_REQUIRE(p->sil.aa == 0, "stage-1 IoU loss: the reference renders it without anti-aliasing");
+        DH_REQUIRE(p->offscreen != nullptr && p->frame_coef != nullptr, "stage-1: offscreen / frame_coef are NULL");
+        DH_REQUIRE(!(p->lw_smooth > 0.0) && !p->optimize_scale, "stage-1: no smoothness term, no scale");
+    }
     DH_REQUIRE(p->scale_mode == DH_SCALE_LOCAL || p->scale_mode == DH_SCALE_P2P || p->scale_mode == DH_SCALE_DEFERRED,
                "bad scale_mode");
     if (p->optimize_scale && p->scale_mode == DH_SCALE_P2P) {
@@ -1992,14 +2061,14 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     t.gpool = const_cast<float*>(grad_rend);
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(t));
     if (rc) return rc;
-    k_neg_maps<<<dim3(t.B, 2), kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0, 0);
+    k_neg_maps<<<dim3(t.B, 2), kNegThreads, neg_maps_smem_bytes(t), st>>>(t, 0, 0, nullptr, nullptr, 0.0f);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sb = bwd_smem_bytes(t);
     rc = set_smem(k_backward<false, false>, sb);
     if (rc) return rc;
     const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
     k_backward<false, false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(
-        t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0);
+        t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0, nullptr);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
 }

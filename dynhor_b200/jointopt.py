@@ -98,7 +98,7 @@ class FusedJointOpt:
     """The fused iteration (dh_jointopt_run) bound to a Joint_Optimizer's parameters, updated in place."""
 
     def __init__(self, model, loss_weights, lr, max_iters, shard=None, group=None, nchunks=None, keep_sum=None,
-                 exchange=True, halo="p2p", corr_on=None, halo_timeout_ms=0):
+                 exchange=True, halo="p2p", corr_on=None, halo_timeout_ms=0, stage1=False):
         """halo: how boundary poses (and, with optimize_object_scale, the partial scale gradients) travel between
         ranks when the sequence is sharded.  "p2p" (default): CUDA-IPC mailboxes written by the kernels themselves
         over NVLink, no host work per iteration; falls back to "nccl" when the ranks cannot map each other's memory.
@@ -106,7 +106,10 @@ class FusedJointOpt:
         path the gloo CPU tests exercise).  exchange=False: the caller fills self.halo by hand and passes keep_sum
         (single-process shard emulation; optimize_object_scale then needs all emulated shards stepped through
         `step_emulated`).  corr_on: whether the correspondence term is active -- must be the same on every rank
-        (default: this model has records and lw_corr_obj > 0)."""
+        (default: this model has records and lw_corr_obj > 0).
+        stage1=True: the silhouette term of the per-frame pose initialisation instead of jointopt's losses
+        (DH_LOSS_STAGE1, include/dynhor_b200.h): loss_weights = {"lw_sil_obj": weight of 1 - IoU,
+        "lw_offscreen": weight of the off-screen penalty}, no anti-aliasing, one Adam group, frames independent."""
         lib = _lib.load()
         self.model, self.group = model, group
         rot, tr = model.rotations_object, model.translations_object
@@ -125,7 +128,8 @@ class FusedJointOpt:
         assert verts.ndim == 2 and verts.shape[-1] == 3, "Invalid shape for vertices"
         V = verts.shape[0]
         faces = shared_faces(model.faces_object)
-        self.sil = SilhouetteState(B, V, faces, model.camintr_rois_object, S, True, orig_size=1.0)
+        self.stage1 = bool(stage1)
+        self.sil = SilhouetteState(B, V, faces, model.camintr_rois_object, S, not self.stage1, orig_size=1.0)
         self.verts = verts
         st = _lib.stream_ptr()
         # static inputs
@@ -198,6 +202,12 @@ class FusedJointOpt:
         p.moments = self.moments.data_ptr()
         (p.Rmat, p.smooth_terms, p.loss_counts, p.partials, p.frame_terms) = [b.data_ptr() for b in self.scratch]
         p.nchunks = self.nchunks
+        if self.stage1:
+            if p.lw_smooth > 0 or p.optimize_scale or self.corr_on or self.shard.world > 1:
+                raise ValueError("stage-1 mode: silhouette IoU + off-screen penalty only, frames are independent")
+            self.offscreen, self.frame_coef = z(B, 16), z(B, 2)
+            p.loss_mode, p.lw_offscreen = _lib.LOSS_STAGE1, float(loss_weights.get("lw_offscreen", 0.0))
+            p.offscreen, p.frame_coef = self.offscreen.data_ptr(), self.frame_coef.data_ptr()
         if self.corr_on:
             ct = model.corr_term
             self.corr_w_sum = float(consts_h[1]) if (exchange and consts_h is not None) else ct.w_sum
@@ -322,6 +332,13 @@ class FusedJointOpt:
         rows = rows.cpu().numpy()
         lw = self.loss_weights
         evo = defaultdict(list)
+        if self.stage1:   # rows: sum of off-screen penalties, sum of (1 - IoU), mean IoU
+            for r in rows:
+                evo["offscreen"].append(float(r[0]))
+                evo["iou_loss"].append(float(r[1]))
+                evo["iou_object"].append(float(r[2]))
+                evo["loss"].append(float(r[1]) * lw.get("lw_sil_obj", 0.0) + float(r[0]) * lw.get("lw_offscreen", 0.0))
+            return dict(evo)
         for r in rows:
             total = 0.0
             if lw.get("lw_smooth_obj", 0) > 0:
@@ -342,6 +359,16 @@ class FusedJointOpt:
         n = min(int(self.step.item()), self.max_iters)
         self.check_status()
         return self._rows_to_dict(self.hist[:n])
+
+    def frame_losses(self):
+        """Per-frame terms of the LAST evaluated iteration (the parameters before its update, like the `losses` vector
+        the reference keeps at pose_initializtion.py:352-356) -> dict of [B] float64 tensors (synchronises nothing)."""
+        ft = self.scratch[4].view(torch.float64).view(-1, 8)
+        lw = self.loss_weights
+        out = {"iou": ft[:, 1].clone(), "offscreen": ft[:, 5].clone()}
+        if self.stage1:
+            out["loss"] = lw.get("lw_sil_obj", 0.0) * (1.0 - ft[:, 1]) + lw.get("lw_offscreen", 0.0) * ft[:, 5]
+        return out
 
     KERNELS = ("pose_prep", "project", "setup_bin", "raster", "backward", "pose_update", "finalize", "corr")
 

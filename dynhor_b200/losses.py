@@ -34,6 +34,16 @@ def batch_mask_iou(ref, pred, eps=0.000001):
     return per_frame(both) / (per_frame(either) + eps)
 
 
+def offscreen_penalty(uvz, far):
+    """[B,V,3] projected vertices (u, v in NDC, depth) -> [B]: by how much they leave [-1, 1]^2 x (0, far), summed over
+    the vertices of each frame (losses.py:42-64 sums it over everything, pose_initializtion.py:119-141 per candidate)."""
+    uv, z = uvz[..., :2], uvz[..., 2:]
+    zero = torch.zeros_like(z)
+    beyond = torch.max(uv - 1, zero).sum(dim=(1, 2)) + torch.max(-1 - uv, zero).sum(dim=(1, 2))
+    depth = torch.max(-z, zero).sum(dim=(1, 2)) + torch.max(z - far, zero).sum(dim=(1, 2))
+    return beyond + depth
+
+
 class Losses():
     """Holds the target masks and the silhouette renderer of one sequence."""
 
@@ -49,12 +59,7 @@ class Losses():
     def compute_offscreen_loss(self, verts):
         """How far the projected vertices stick out of the view volume ([-1, 1]^2 x (0, far)), summed."""
         r = self.sil_renderer
-        uvz = projection(verts, r.K, r.R, r.t, r.dist_coeffs, orig_size=1)
-        uv, z = uvz[..., :2], uvz[..., 2:]
-        zero = torch.zeros_like(z)
-        excess = [torch.max(uv - 1, zero), torch.max(-1 - uv, zero),       # beyond +1, below -1
-                  torch.max(-z, zero), torch.max(z - r.far, zero)]         # behind the camera, beyond far
-        return excess[0].sum() + excess[1].sum() + excess[2].sum() + excess[3].sum()
+        return offscreen_penalty(projection(verts, r.K, r.R, r.t, r.dist_coeffs, orig_size=1), r.far).sum()
 
     def compute_sil_loss(self, verts, faces):
         """Masked L2 between the rendered silhouettes and the target, per kept pixel and per frame, plus the IoU."""

@@ -119,8 +119,9 @@ typedef struct dh_corr {
     float* partials;               /* [B,nslots,16] scratch: dT(3), X (x) dc (9), loss (1), pad(3)               */
 } dh_corr;
 
-/* Launch plan of the streaming kernel: the B*ceil(C/1024) record tiles are cut into `grid` contiguous, equal
- * ranges (one persistent CTA each, 3 per SM), so a frame is seen by at most `nslots` CTAs.
+/* Launch plan of the streaming kernel: a frame's ceil(C/1024) record tiles form `nslots` segments of 8 tiles; every
+ * segment is summed by one CTA in one fixed order (so a frame's sums do not depend on B or on the grid), the
+ * B*nslots segments are dealt to `grid` persistent CTAs (3 per SM) in contiguous, nearly equal ranges.
  * out3 = grid, nslots, tiles per frame.  sm_count 0 = ask the current device (148 if there is none). */
 int dh_corr_plan(int32_t B, int32_t C, int32_t sm_count, int32_t* out3);
 /* Un-normalised partial sums for the poses (Rmat [B,9], trans [B,3], scale [1]) and intrinsics K [B,9]:
@@ -182,10 +183,22 @@ typedef struct dh_jointopt {
     double* smooth_terms;          /* [B,16]: gT(3) gR(9) gs(1) pair_sse(1) pad(2)                               */
     int32_t* loss_counts;          /* [B,4]: 16*SSE, 4*inter, 4*union, pad                                       */
     float* partials;               /* [B,nchunks,16] per-CTA pose-gradient partial sums                          */
-    double* frame_terms;           /* [B,8]: 16*SSE, iou, pair_sse, scale-grad, corr loss sum, pad(3)            */
+    double* frame_terms;           /* [B,8]: 16*SSE, iou, pair_sse, scale-grad, corr loss sum, off-screen, pad(2) */
     int32_t nchunks;
     dh_corr corr;                  /* optional correspondence term (corr.records == NULL or lw_corr == 0: off)   */
+    /* Stage-1 mode: the silhouette term of the per-frame pose initialisation,
+     * ObjTracker.coarse_forward + the loop of find_optimal_pose (pose_initializtion.py:143-155,346-360), batched over
+     * frames x initialisations.  loss_mode DH_LOSS_STAGE1: per frame lw_sil * (1 - IoU(keep * silhouette, ref)) +
+     * lw_offscreen * off-screen penalty of the projected vertices (:119-141), rendered WITHOUT anti-aliasing
+     * (sil.aa must be 0, :98-105), no smoothness term, ONE Adam group (rotations and translations share lr, :346).
+     * hist rows then hold: sum of the off-screen penalties, sum of (1 - IoU), mean IoU, 0. */
+    int32_t loss_mode;             /* DH_LOSS_JOINT (jointopt.py) or DH_LOSS_STAGE1                              */
+    double lw_offscreen;           /* 100000 in the reference (:154)                                             */
+    float* offscreen;              /* [B,16] scratch: dT(3) dR(9) pad(1) penalty(1) pad(2), stage 1 only          */
+    float* frame_coef;             /* [B,2]  scratch: per-frame dL/dpixel coefficients of the IoU loss            */
 } dh_jointopt;
+#define DH_LOSS_JOINT 0
+#define DH_LOSS_STAGE1 1
 
 /* bytes of the dh_jointopt scratch arrays: out[5] = Rmat, smooth_terms, loss_counts, partials, frame_terms */
 int dh_jointopt_scratch_bytes(int32_t B, int32_t nchunks, int64_t* out5);

@@ -160,10 +160,7 @@ def geometry_case(ref):
     print("geometry ->", path)
 
 
-def stage1_case():
-    """ObjTracker.coarse_forward + the mode="coarse" loop of find_optimal_pose (pose_initializtion.py:143-155,
-    346-358), reference code unmodified.  pose_initializtion.py imports pytorch3d / detectron2 names at module
-    level (:17-30); they are only used by the textured `forward` path, so empty stand-in modules are enough."""
+def import_pose_initializtion():
     for name, attrs in {
         "pytorch3d": [], "pytorch3d.renderer": ["PerspectiveCameras", "RasterizationSettings", "MeshRenderer",
                                                 "MeshRasterizer", "SoftPhongShader", "SoftSilhouetteShader",
@@ -177,6 +174,14 @@ def stage1_case():
             setattr(m, a, type(a, (), {"__init__": lambda self, *a, **k: None}))
         sys.modules.setdefault(name, m)
     import pose_initializtion as ref_pi  # noqa
+    return ref_pi
+
+
+def stage1_case():
+    """ObjTracker.coarse_forward + the mode="coarse" loop of find_optimal_pose (pose_initializtion.py:143-155,
+    346-358), reference code unmodified.  pose_initializtion.py imports pytorch3d / detectron2 names at module
+    level (:17-30); they are only used by the textured `forward` path, so empty stand-in modules are enough."""
+    ref_pi = import_pose_initializtion()
     B, size = 1, 128
     seq = synth.make_sequence(3, mesh="ico3", seed=6, render_fn=oracle_render_fn, size=size)
     f = 1  # one frame, like the reference's per-frame loop
@@ -210,7 +215,57 @@ def stage1_case():
     print("stage1_coarse ->", path, "loss", losses[0], "->", losses[-1], "iou", ious[0], "->", ious[-1])
 
 
+def stage1_multi_case():
+    """The same reference code with num_initializations = 4 (one ObjTracker, four candidate poses of one frame,
+    pose_initializtion.py:329-360), an occluder in the target mask, and one candidate pushed partly out of the view so
+    that the off-screen penalty (:119-141, weight 100000 at :154) and its gradient are exercised."""
+    ref_pi = import_pose_initializtion()
+    size, n = 128, 4     # (not 3: geometry.py:24 calls torch.cross without dim, which picks the batch axis at B = 3)
+    seq = synth.make_sequence(n, mesh="ico3", seed=8, render_fn=oracle_render_fn, size=size, occluder=True)
+    f = 0
+    K = torch.from_numpy(seq["K_roi"][f:f + 1].copy())
+    # four candidates around frame f's pose: its perturbed initial pose and the neighbouring frames' rotations
+    rot6d = torch.from_numpy(seq["rot6d_init"].copy())
+    trans = torch.from_numpy(seq["T_init"][f:f + 1].copy()).repeat(n, 1, 1)
+    trans[3, 0, 0] += 0.45      # slides a part of the object out of the view: off-screen penalty > 0
+    model = ref_pi.ObjTracker(ref_image=seq["target_masks"][f], vertices=torch.from_numpy(seq["verts"]),
+                              faces=torch.from_numpy(seq["faces"])[None], textures=None, dino_model=None,
+                              gt_dino_feat=torch.zeros(1), rotation_init=rot6d, translation_init=trans,
+                              num_initializations=n, K=K)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    losses, ious, per_init = [], [], []
+    g0 = None
+    for it in range(5):
+        opt.zero_grad()
+        loss_dict, iou = model.coarse_forward()
+        lv = sum(loss_dict.values())
+        total = lv.sum()
+        total.backward()
+        if it == 0:
+            g0 = (model.rotations.grad.numpy().copy(), model.translations.grad.numpy().copy())
+            off0 = loss_dict["offscreen"].detach().numpy().copy()
+        opt.step()
+        losses.append(float(total.detach()))
+        per_init.append(lv.detach().numpy().copy())
+        ious.append(iou.numpy().copy())
+    print('offscreen0', off0)
+    assert off0[3] > 0 and off0[0] == 0
+    path = os.path.join(ROOT, "tests", "golden", "stage1_multi.npz")
+    np.savez_compressed(path, verts=seq["verts"], faces=seq["faces"].astype(np.int32), K_roi=K.numpy(),
+                        target_mask=seq["target_masks"][f].astype(np.int8), rot6d_init=rot6d.numpy(),
+                        trans_init=trans.numpy(), lr=np.float64(0.01), ref_loss=np.asarray(losses),
+                        ref_loss_per_init=np.asarray(per_init), ref_offscreen0=off0,
+                        ref_iou=np.asarray(ious), ref_grad_rot=g0[0], ref_grad_trans=g0[1],
+                        ref_final_rot=model.rotations.detach().numpy(),
+                        ref_final_trans=model.translations.detach().numpy())
+    print("stage1_multi ->", path, "loss", losses[0], "->", losses[-1], "offscreen0", off0, "iou", ious[0], "->", ious[-1])
+
+
 def main():
+    if "--stage1-multi" in sys.argv:   # added in round 2; the other fixtures are not regenerated
+        import_reference()
+        stage1_multi_case()
+        return
     ref = import_reference()
     stage1_case()
     geometry_case(ref)

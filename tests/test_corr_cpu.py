@@ -57,27 +57,41 @@ def test_zero_weight_and_exact_hit_records_contribute_nothing():
     assert np.all(s == 0.0)
 
 
+SEG = 8   # kSegTiles (dh_corr.cu): tiles per segment, the unit one CTA always sums as a whole
+
+
+def _cut(c, T, G, tpf):
+    """dh_corr.cu::corr_cut: CTA c's first tile = the equal cut c*T/G moved forward to the next segment start."""
+    t = c * T // G
+    b, k = divmod(t, tpf)
+    ks = -(-k // SEG) * SEG
+    return b * tpf + min(ks, tpf)
+
+
 @pytest.mark.parametrize("B,C,sms", [(300, 10000, 148), (4, 100, 148), (512, 50000, 148), (1, 5000, 148), (7, 2050, 2),
-                                      (64, 10000, 148), (3, 2, 148)])
-def test_plan_covers_every_tile_once_with_distinct_slots(B, C, sms):
+                                      (64, 10000, 148), (3, 2, 148), (2048, 50000, 148), (1907, 50000, 148)])
+def test_plan_covers_every_tile_once_and_never_splits_a_segment(B, C, sms):
+    """Every record tile is streamed by exactly one CTA, and a segment (8 consecutive tiles of one frame, slot =
+    segment number) is never cut: a frame's partial sums are formed the same way whatever B and the grid are, which
+    is what makes a frame-sharded run reproduce the single-GPU bits."""
     from dynhor_b200.corr import plan
     p = plan(B, C, sms)
     G, nslots, tpf = p["grid"], p["nslots"], p["tiles_per_frame"]
-    assert tpf == -(-C // 1024) and 1 <= G <= max(1, 3 * sms)
+    assert tpf == -(-C // 1024) and nslots == -(-tpf // SEG) and 1 <= G <= max(1, 3 * sms)
     T = B * tpf
     seen = np.zeros(T, int)
-    slots = set()
+    owner = {}
     for i in range(G):
-        t0, t1 = i * T // G, (i + 1) * T // G
-        assert t1 > t0
+        t0, t1 = _cut(i, T, G, tpf), _cut(i + 1, T, G, tpf)
+        assert t1 >= t0
         seen[t0:t1] += 1
-        for b in sorted({t // tpf for t in range(t0, t1)}):
-            first = ((b * tpf + 1) * G - 1) // T
-            slot = i - first
-            assert 0 <= slot < nslots, (b, i, first, nslots)
-            assert (b, slot) not in slots
-            slots.add((b, slot))
-    assert np.all(seen == 1)
+        for t in range(t0, t1):
+            b, k = divmod(t, tpf)
+            assert owner.setdefault((b, k // SEG), i) == i      # one CTA per segment
+    assert np.all(seen == 1) and len(owner) == B * nslots
+    if G > 1:   # balanced up to one segment
+        sizes = [_cut(i + 1, T, G, tpf) - _cut(i, T, G, tpf) for i in range(G)]
+        assert max(sizes) - min(sizes) <= 2 * SEG
 
 
 def test_synthetic_correspondences_are_consistent_with_the_ground_truth():

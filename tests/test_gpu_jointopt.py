@@ -235,7 +235,8 @@ def _model_from_seq(seq, scale_opt=False):
         faces_object=torch.from_numpy(np.stack([seq["faces"]] * B)),
         camintr_rois_object=torch.cat([p["K_roi"][:, 0] for p in params]),
         target_masks_object=torch.cat([p["target_masks"] for p in params]),
-        int_scale_init=1, optimize_object_scale=scale_opt)
+        int_scale_init=1, optimize_object_scale=scale_opt,
+        correspondences=torch.from_numpy(seq["correspondences"]) if "correspondences" in seq else None)
 
 
 @pytest.fixture(scope="module")

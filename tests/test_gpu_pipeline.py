@@ -68,10 +68,12 @@ def test_registered_ops_on_the_device():
             test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
     rend = torch.ops.dynhor.sil_forward(*args)
     mod = Renderer(image_size=64, K=K, R=torch.eye(3)[None].cuda(), t=torch.zeros(1, 3).cuda(), orig_size=1)
-    assert torch.equal(mod(vc.detach(), faces, mode="silhouettes"), rend) and float(rend.sum()) > 0
+    assert torch.equal(mod(vc.detach(), faces, mode="silhouettes"), rend.detach()) and float(rend.detach().sum()) > 0
     g = torch.rand_like(rend)
     (gv,) = torch.autograd.grad(rend, vc, g)
-    assert torch.equal(gv, torch.ops.dynhor.sil_backward(vc.detach(), faces, K, g, 64, True, 0.1, 100.0, 1e-4, 1.0))
+    # (the composable backward scatters per-vertex gradients with float atomics: equal up to summation order)
+    gv2 = torch.ops.dynhor.sil_backward(vc.detach(), faces, K, g, 64, True, 0.1, 100.0, 1e-4, 1.0)
+    assert torch.allclose(gv, gv2, rtol=1e-4, atol=1e-4 * float(gv.abs().max()))
     assert float(gv.abs().sum()) > 0
     d = synth.make_dino_features(40, 6, 24, 64, seed=2, device="cuda")
     fb, tb = build_bank(d["frames"], d["masks"]), build_bank(d["templ"])

@@ -48,13 +48,19 @@ def seq24():
 
 
 @pytest.mark.parametrize("bounds", [[0, 12, 24], [0, 5, 6, 24], [0, 1, 9, 17, 24]])
-@pytest.mark.parametrize("scale_opt", [False, True])
-def test_emulated_shards_equal_single(seq24, bounds, scale_opt):
+@pytest.mark.parametrize("scale_opt,with_corr", [(False, False), (True, False), (True, True)])
+def test_emulated_shards_equal_single(seq24, bounds, scale_opt, with_corr):
     """Any contiguous partition (cost-weighted ranges are ragged) gives the single-shard bits -- poses AND the shared
-    object scale (jointopt.py:42-46), whose gradient is summed exactly across the shards."""
+    object scale (jointopt.py:42-46), whose gradient is summed exactly across the shards; with the correspondence
+    term as well (its per-frame sums are formed segment by segment, independently of how many frames share a launch:
+    9000 records = 9 tiles = 2 segments per frame here)."""
+    from dynhor_b200 import synth
     from dynhor_b200.jointopt import FusedJointOpt
     from dynhor_b200.sharding import FrameShard
     lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0}
+    if with_corr:
+        lw["lw_corr_obj"] = 0.01
+        seq24 = dict(seq24, correspondences=synth.make_correspondences(seq24, 9000, seed=2, size=128))
     iters, B, lr = 8, 24, 1e-3
     m1 = _model_from_seq(seq24, scale_opt=scale_opt)
     f1 = FusedJointOpt(m1, lw, lr, iters)
@@ -66,6 +72,8 @@ def test_emulated_shards_equal_single(seq24, bounds, scale_opt):
         sh = FrameShard(r, world, B, bounds=bounds)
         models.append(_model_from_seq(_sub(seq24, sh), scale_opt=scale_opt))
         fused.append(FusedJointOpt(models[-1], lw, lr, iters, shard=sh, keep_sum=f1.keep_sum, exchange=False))
+        if with_corr:
+            fused[-1].p.corr.w_sum = f1.corr_w_sum      # the sequence-wide sum of weights (an all-reduce in a real run)
     _run_emulated(models, fused, iters)
     assert torch.equal(torch.cat([m.rotations_object.detach() for m in models]), m1.rotations_object.detach())
     assert torch.equal(torch.cat([m.translations_object.detach() for m in models]), m1.translations_object.detach())

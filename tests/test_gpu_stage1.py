@@ -1,0 +1,128 @@
+"""GPU parity of the fused stage-1 iteration (dh_jointopt_run with loss_mode DH_LOSS_STAGE1: anti_aliasing=False raster,
+1 - IoU loss, off-screen penalty, edge-scan backward, one-group Adam) -- SURVEY.md 8f rank 1 -- against
+  (a) runs of the reference's own pose_initializtion.ObjTracker.coarse_forward + Adam loop (tests/golden/stage1_*.npz),
+  (b) oracle/stage1_oracle.py on a reference-sized frame (5k-vertex mesh, 256x256 ROI), teacher-forced.
+Bars: IoU of identical coverage exact, losses 1e-4, gradients 1e-3 per candidate."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, rel_err
+from test_gpu_jointopt import _oracle_render_fn
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL, GRAD_RTOL, TRAJ_RTOL = 1e-4, 1e-3, 5e-3
+
+
+def _fused_from_golden(g, iters):
+    from dynhor_b200.jointopt import FusedJointOpt
+    from dynhor_b200.pose_init import OFFSCREEN_WEIGHT, _Candidates
+    n = len(g["rot6d_init"])
+    model = _Candidates(torch.from_numpy(g["rot6d_init"]), torch.from_numpy(g["trans_init"]),
+                        torch.from_numpy(g["verts"]), torch.from_numpy(g["faces"].astype(np.int64)),
+                        torch.from_numpy(g["K_roi"]).expand(n, 3, 3).contiguous(),
+                        torch.from_numpy(g["target_mask"].astype(np.float32))[None].expand(n, -1, -1))
+    lw = {"lw_sil_obj": 1.0, "lw_offscreen": OFFSCREEN_WEIGHT}
+    return model, FusedJointOpt(model, lw, float(g["lr"]), iters, stage1=True)
+
+
+@pytest.mark.parametrize("name", ["stage1_coarse", "stage1_multi"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_stage1_vs_reference_run(name, use_graph):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    iters = len(g["ref_loss"])
+    model, fused = _fused_from_golden(g, iters)
+    # iteration 0: identical parameters -> per-iteration bars
+    g_rot, g_tr, _ = fused.grads()
+    for c in range(len(g["rot6d_init"])):
+        assert rel_err(g_rot[c].cpu().numpy(), g["ref_grad_rot"][c]) < GRAD_RTOL, c
+        assert rel_err(g_tr[c].cpu().numpy(), g["ref_grad_trans"][c]) < GRAD_RTOL, c
+    first = fused.frame_losses()
+    assert np.array_equal(first["iou"].float().cpu().numpy(), g["ref_iou"][0])      # identical coverage: exact
+    if "ref_offscreen0" in g.files:
+        off = 100000.0 * first["offscreen"].cpu().numpy()
+        assert (off[:3] == 0).all() and abs(off[3] - g["ref_offscreen0"][3]) <= LOSS_RTOL * g["ref_offscreen0"][3]
+        assert np.allclose(first["loss"].cpu().numpy(), g["ref_loss_per_init"][0], rtol=LOSS_RTOL)
+    fused.run(iters, use_graph=use_graph)
+    h = fused.history()
+    assert abs(h["loss"][0] - g["ref_loss"][0]) <= LOSS_RTOL * g["ref_loss"][0]
+    assert np.allclose(h["loss"], g["ref_loss"], rtol=TRAJ_RTOL)
+    assert np.allclose(h["iou_object"], g["ref_iou"].mean(1), atol=1e-3)
+    lr = float(g["lr"])
+    assert np.abs(model.rotations_object.detach().cpu().numpy() - g["ref_final_rot"]).max() < 0.25 * iters * lr
+    assert np.abs(model.translations_object.detach().cpu().numpy() - g["ref_final_trans"]).max() < 0.25 * iters * lr
+    # first Adam step (t = 1): every parameter moves by lr * sign(gradient) -- one group, same lr for rotations and
+    # translations (pose_initializtion.py:346), unlike jointopt's 10x rotation group
+    m2, f2 = _fused_from_golden(g, 1)
+    f2.run(1, use_graph=False)
+    d_rot = (m2.rotations_object.detach().cpu().numpy() - g["rot6d_init"])
+    live = np.abs(g["ref_grad_rot"]) > 1e-3 * np.abs(g["ref_grad_rot"]).max()
+    assert np.allclose(d_rot[live], -lr * np.sign(g["ref_grad_rot"][live]), rtol=1e-3)
+
+
+def test_fused_stage1_teacher_forced_vs_oracle_reference_size():
+    """custom_shoes-shaped candidates (V = 5002, F = 10000, 256x256 ROI, no anti-aliasing): at every iteration the
+    fused path gets the oracle's parameters; losses, IoU, gradients and the Adam step are compared."""
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import FusedJointOpt
+    from dynhor_b200.pose_init import OFFSCREEN_WEIGHT, _Candidates
+    from oracle import stage1_oracle
+    seq = synth.make_sequence(3, mesh="uv50x100", seed=12, render_fn=_oracle_render_fn, period=300)
+    n, lr = 3, 1e-2
+    rot0, tr0 = seq["rot6d_init"].copy(), seq["T_init"].copy()
+    tr0[2, 0, 1] += 0.3      # one candidate partly out of the view
+    orc = stage1_oracle.Stage1Oracle(seq["target_masks"], seq["verts"], seq["faces"], rot0, tr0, seq["K_roi"], lr=lr)
+    model = _Candidates(torch.from_numpy(rot0), torch.from_numpy(tr0), torch.from_numpy(seq["verts"]),
+                        torch.from_numpy(seq["faces"]), torch.from_numpy(seq["K_roi"]),
+                        torch.from_numpy(seq["target_masks"]))
+    fused = FusedJointOpt(model, {"lw_sil_obj": 1.0, "lw_offscreen": OFFSCREEN_WEIGHT}, lr, 8, stage1=True)
+    for it in range(4):
+        with torch.no_grad():
+            model.rotations_object.copy_(orc.rotations.detach().cuda())
+            model.translations_object.copy_(orc.translations.detach().cuda())
+        g_rot, g_tr, _ = fused.grads()
+        fl = fused.frame_losses()
+        lv, iou, off, grads = orc.step()
+        assert np.array_equal(fl["iou"].float().cpu().numpy(), iou.numpy()), it
+        assert np.allclose(fl["loss"].cpu().numpy(), lv.numpy(), rtol=LOSS_RTOL), it
+        assert off[2] > 0 and np.allclose(fl["offscreen"].cpu().numpy(), off.numpy(), rtol=LOSS_RTOL), it
+        for c in range(n):
+            assert rel_err(g_rot[c].cpu().numpy(), grads[0][c].numpy()) < GRAD_RTOL, (it, c)
+            assert rel_err(g_tr[c].cpu().numpy(), grads[1][c].numpy()) < GRAD_RTOL, (it, c)
+        fused.run(1, use_graph=False)
+        for ours, theirs, gk in ((model.rotations_object, orc.rotations, grads[0]),
+                                 (model.translations_object, orc.translations, grads[1])):
+            a, b = ours.detach().cpu().numpy(), theirs.detach().numpy()
+            gk = gk.numpy().reshape(a.shape)
+            live = np.abs(gk) > 1e-3 * np.abs(gk).max()
+            assert (np.abs(a - b)[live] <= 1e-3 * lr + np.spacing(np.abs(b))[live]).all(), it
+
+
+def test_objtracker_module_fused_and_composable_paths_agree():
+    """ObjTracker.optimize() (fused) against the reference loop on the same module (coarse_forward + backward +
+    torch.optim.Adam on the renderer op), candidates sorted by their last loss like :368-372."""
+    from dynhor_b200.pose_init import ObjTracker, coarse_optimize, optimize_coarse
+    g = np.load(os.path.join(GOLDEN, "stage1_multi.npz"))
+    kw = dict(ref_image=g["target_mask"].astype(np.float32), vertices=torch.from_numpy(g["verts"]),
+              faces=torch.from_numpy(g["faces"].astype(np.int64))[None], rotation_init=torch.from_numpy(g["rot6d_init"]),
+              translation_init=torch.from_numpy(g["trans_init"]), num_initializations=4, K=torch.from_numpy(g["K_roi"]))
+    iters, lr = 5, float(g["lr"])
+    a = ObjTracker(**kw)
+    hist = a.optimize(num_iterations=iters, lr=lr, sort_best=True)
+    assert np.allclose(hist["loss"], g["ref_loss"], rtol=TRAJ_RTOL)
+    assert bool((a.losses[1:] >= a.losses[:-1]).all())                      # best first
+    assert np.allclose(np.sort(a.losses.cpu().numpy()), np.sort(g["ref_loss_per_init"][-1]), rtol=TRAJ_RTOL)
+    b = ObjTracker(**kw)
+    trace = optimize_coarse(b, num_iterations=iters, lr=lr)
+    assert np.allclose([t[0] for t in trace], g["ref_loss"], rtol=TRAJ_RTOL)
+    order = np.argsort(g["ref_loss_per_init"][-1])
+    assert np.abs(a.rotations.detach().cpu().numpy() - b.rotations.detach().cpu().numpy()[order]).max() < 0.25 * iters * lr
+    with pytest.raises(NotImplementedError):
+        a.forward()
+    # batched entry point == module
+    out = coarse_optimize(torch.from_numpy(g["target_mask"].astype(np.float32)), g["verts"], g["faces"].astype(np.int64),
+                          g["rot6d_init"], g["trans_init"], g["K_roi"], iters, lr)
+    assert torch.equal(out["rotations"][torch.argsort(out["losses"])], a.rotations.detach())

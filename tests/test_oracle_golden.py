@@ -59,3 +59,33 @@ def test_oracle_rasteriser_maps_pinned(name):
     maps = nr_oracle.rasterize_forward_np(nr_oracle.vertices_to_faces(proj, faces2).numpy(), size * 2)
     assert np.array_equal(maps["face_index"], g["orc_face_index0"])
     assert np.array_equal(maps["alpha"] > 0.5, golden_alpha(g))
+
+
+@pytest.mark.parametrize("name", ["stage1_coarse", "stage1_multi"])
+def test_stage1_oracle_vs_reference_run(name):
+    """oracle/stage1_oracle.py against the runs of the reference's own pose_initializtion.ObjTracker.coarse_forward +
+    Adam loop stored by tests/golden/make_golden.py (one candidate; four candidates with an occluder and one of
+    them partly off-screen)."""
+    import os
+    from helpers import GOLDEN
+    from oracle import stage1_oracle
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n = len(g["rot6d_init"])
+    orc = stage1_oracle.Stage1Oracle(np.repeat(g["target_mask"][None].astype(np.float32), n, 0), g["verts"],
+                                     g["faces"].astype(np.int64), g["rot6d_init"], g["trans_init"], g["K_roi"],
+                                     lr=float(g["lr"]))
+    for it in range(len(g["ref_loss"])):
+        lv, iou, off, grads = orc.step()
+        assert np.isclose(float(lv.sum()), g["ref_loss"][it], rtol=1e-6)
+        assert np.allclose(iou.numpy(), g["ref_iou"][it], rtol=1e-6)
+        if it == 0:
+            assert np.allclose(grads[0].numpy(), g["ref_grad_rot"], rtol=1e-5, atol=1e-7 * np.abs(g["ref_grad_rot"]).max())
+            assert np.allclose(grads[1].numpy(), g["ref_grad_trans"], rtol=1e-5,
+                               atol=1e-7 * np.abs(g["ref_grad_trans"]).max())
+            if "ref_offscreen0" in g.files:
+                assert np.allclose(OFF * off.numpy(), g["ref_offscreen0"], rtol=1e-6)
+    assert np.allclose(orc.rotations.detach().numpy(), g["ref_final_rot"], atol=1e-6)
+    assert np.allclose(orc.translations.detach().numpy(), g["ref_final_trans"], atol=1e-6)
+
+
+OFF = 100000.0
