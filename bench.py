@@ -246,7 +246,8 @@ def host_parameters(seq, start, B_total, C):
 def run_ours(args):
     import torch.distributed as dist
     from dynhor_b200.jointopt import FusedJointOpt, joint_optimize
-    from dynhor_b200.sharding import FrameShard, allgather_equal, balanced_bounds, frame_costs_from_blocks
+    from dynhor_b200.sharding import (FrameShard, allgather_equal, balanced_bounds, frame_costs_from_blocks,
+                                       rescale_costs)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,7 +284,7 @@ def run_ours(args):
         shard = FrameShard(0, 1, es.B)
     else:
         seq = None
-    probe_ms = None
+    probe_ms, calib_ms = None, None
     if world > 1 and args.balance == "probe":
         seq0 = make_range(shard.start, shard.stop, B_total, 0)
         nblocks = max(1, min(16, (B_total // world) // 32))
@@ -295,6 +296,21 @@ def run_ours(args):
         probe_ms = [float(ms_all[r, :nblocks].sum()) for r in range(world)]
         shard = shard.with_bounds(balanced_bounds(cost, world))
         del seq0, pr
+        # second cut, like joint_optimize's: 16 iterations on the probed ranges, every rank's own time per iteration
+        # (device clock, waits excluded) rescales the cost profile; the calibration run is thrown away
+        seq1 = make_range(shard.start, shard.stop, B_total, C)
+        with FusedJointOpt(model_from(seq1), lw, LR, 16, shard=shard, halo=args.halo) as cal:
+            cal.run(16)
+            t = torch.tensor([float(np.mean(cal.compute_ms(8, 16)))], dtype=torch.float64, device="cuda")
+            cal.check_status()
+        t_all = allgather_equal(t, shard).reshape(-1).cpu().numpy()
+        calib_ms = [float(v) for v in t_all]
+        if t_all.max() > 1.03 * t_all.mean():
+            nb = balanced_bounds(rescale_costs(cost, shard.bounds, t_all), world)
+            if nb != shard.bounds:
+                shard, seq1 = shard.with_bounds(nb), None
+        seq = seq1
+        del seq1, cal
     if seq is None:
         seq = make_range(shard.start, shard.stop, B_total, C)
     Bl = shard.B
@@ -324,6 +340,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     value = B_total * args.steps / (ms / 1000.0)
     hist = fused.history()
+    own = torch.tensor([float(np.mean(fused.compute_ms(args.warmup, args.warmup + args.steps)))], dtype=torch.float64,
+                       device="cuda")
+    rank_ms = [float(v) for v in allgather_equal(own, shard).reshape(-1).cpu().numpy()]
 
     # ---- per-kernel times (CUDA events on the launch stream) -> roofline of the dominant kernel
     # (the eager profile runs whole iterations: in a sharded run every rank does it, in lockstep like the timed loop)
@@ -455,7 +474,9 @@ def run_ours(args):
                        "frames_total": B_total, "frames_this_rank": Bl, "correspondences_per_frame": C,
                        "parallelism": f"frame-shard x{world}",
                        "partition": {"by": args.balance if world > 1 else "single", "bounds": shard.bounds,
-                                     "probe_ms_per_equal_range": probe_ms},
+                                     "probe_ms_per_equal_range": probe_ms,
+                                     "ms_per_probed_range_after_16_iterations": calib_ms},
+                       "own_ms_per_step_by_rank": rank_ms,
                        "trajectory_period_frames": B_total,
                        "halo": halo_used,
                        "l2": "per-step working set (face-index maps + bins, > 1 MB/frame) exceeds the 126 MB L2; "

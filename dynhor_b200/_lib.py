@@ -58,7 +58,7 @@ class DhJointOpt(ctypes.Structure):
         ("Rmat", c_p), ("smooth_terms", c_p), ("loss_counts", c_p), ("partials", c_p), ("frame_terms", c_p),
         ("nchunks", c_i),
         ("corr", DhCorr),
-        ("loss_mode", c_i), ("lw_offscreen", c_d), ("offscreen", c_p), ("frame_coef", c_p),
+        ("loss_mode", c_i), ("lw_offscreen", c_d), ("offscreen", c_p), ("frame_coef", c_p), ("iter_ns", c_p),
     ]
 
 

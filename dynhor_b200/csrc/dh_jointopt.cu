@@ -1565,6 +1565,9 @@ __global__ void k_pose_prep(const dh_jointopt p) {
             hn = hbuf[1];
         }
     }
+    // iteration clock (optional): the moment this rank's own work of the iteration can start = after its waits
+    if (p.iter_ns != nullptr && (b == 0 || b == B - 1) && *p.step < p.max_iters)
+        atomicMax(p.iter_ns + 2 * (size_t)*p.step, globaltimer_ns());
     smooth_terms_frame(b, B, p.rot6d, p.trans, hp, hn, p.scale[0], p.moments, p.sil.V, p.B_total, p.lw_smooth,
                        p.smooth_terms + (size_t)b * 16);
 }
@@ -1750,7 +1753,10 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int 
             }
         }
     }
-    if (threadIdx.x == 0) *p.step = step + 1;
+    if (threadIdx.x == 0) {
+        if (p.iter_ns != nullptr && step < p.max_iters) p.iter_ns[2 * (size_t)step + 1] = globaltimer_ns();
+        *p.step = step + 1;
+    }
 }
 
 // DH_SCALE_DEFERRED: the partials of all ranks (gathered by the host side) -> Adam step of the scale.

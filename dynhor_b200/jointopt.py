@@ -27,7 +27,7 @@ from .geometry import matrix_to_rot6d, rot6d_to_matrix
 from .losses import Losses
 from .renderer import SilhouetteState, shared_faces
 from .sharding import (FrameShard, PeerMailboxes, allgather_equal, allgather_frames, allreduce_sum_, balanced_bounds,
-                       detect_shard, exchange_halo, frame_costs_from_blocks)
+                       detect_shard, exchange_halo, frame_costs_from_blocks, rescale_costs)
 
 
 class Joint_Optimizer(nn.Module):
@@ -98,7 +98,7 @@ class FusedJointOpt:
     """The fused iteration (dh_jointopt_run) bound to a Joint_Optimizer's parameters, updated in place."""
 
     def __init__(self, model, loss_weights, lr, max_iters, shard=None, group=None, nchunks=None, keep_sum=None,
-                 exchange=True, halo="p2p", corr_on=None, halo_timeout_ms=0, stage1=False):
+                 exchange=True, halo="p2p", corr_on=None, halo_timeout_ms=0, stage1=False, start_step=0):
         """halo: how boundary poses (and, with optimize_object_scale, the partial scale gradients) travel between
         ranks when the sequence is sharded.  "p2p" (default): CUDA-IPC mailboxes written by the kernels themselves
         over NVLink, no host work per iteration; falls back to "nccl" when the ranks cannot map each other's memory.
@@ -109,7 +109,9 @@ class FusedJointOpt:
         (default: this model has records and lw_corr_obj > 0).
         stage1=True: the silhouette term of the per-frame pose initialisation instead of jointopt's losses
         (DH_LOSS_STAGE1, include/dynhor_b200.h): loss_weights = {"lw_sil_obj": weight of 1 - IoU,
-        "lw_offscreen": weight of the off-screen penalty}, no anti-aliasing, one Adam group, frames independent."""
+        "lw_offscreen": weight of the off-screen penalty}, no anti-aliasing, one Adam group, frames independent.
+        start_step: iterations already done on these parameters by an earlier plan (a re-partition in the middle of
+        a run): the iteration counter -- Adam's t, the history row, the mailbox ticks -- continues from there."""
         lib = _lib.load()
         self.model, self.group = model, group
         rot, tr = model.rotations_object, model.translations_object
@@ -168,10 +170,14 @@ class FusedJointOpt:
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
         self.m_rot, self.v_rot, self.m_tr, self.v_tr, self.mv_scale = z(B, 6), z(B, 6), z(B, 3), z(B, 3), z(2)
         self.step = z(1, dt=torch.int32)
+        self.start_step = int(start_step)
+        if self.start_step:
+            self.step.fill_(self.start_step)
         self.status = z(1, dt=torch.int32)
         self.scale_part = z(2, dt=torch.int64)
         self.max_iters = int(max_iters)
         self.hist = z(self.max_iters + 1, 4, dt=torch.float64)   # row max_iters: evaluate() / grads()
+        self.iter_ns = z(max(self.max_iters, 1), 2, dt=torch.int64)
         self.halo = z(2, 9)
         self.edge = z(2, 9)
         nchunks = nchunks or int(os.environ.get("DH_BWD_CHUNKS", "0"))  # tuning knob
@@ -189,6 +195,7 @@ class FusedJointOpt:
         p.adam_mv_scale = self.mv_scale.data_ptr()
         p.step, p.hist, p.max_iters = self.step.data_ptr(), self.hist.data_ptr(), self.max_iters
         p.status, p.scale_part = self.status.data_ptr(), self.scale_part.data_ptr()
+        p.iter_ns = self.iter_ns.data_ptr()
         p.halo_timeout_ms = int(halo_timeout_ms)
         p.halo_prev = self.halo[0].data_ptr() if self.shard.has_prev else None
         p.halo_next = self.halo[1].data_ptr() if self.shard.has_next else None
@@ -253,7 +260,7 @@ class FusedJointOpt:
         base = mail.reserve(self.max_iters)
         for side in (0, 1):
             if (side == 0 and self.shard.has_prev) or (side == 1 and self.shard.has_next):
-                self._keep.append(mail.seed(side, base, self.halo[side]))
+                self._keep.append(mail.seed(side, base + self.start_step, self.halo[side]))
         p = self.p
         p.mailbox, p.tick_base = mail.mailbox, base
         p.peer_prev = mail.peers[self.shard.rank - 1] if self.shard.has_prev else None
@@ -360,6 +367,14 @@ class FusedJointOpt:
         self.check_status()
         return self._rows_to_dict(self.hist[:n])
 
+    def compute_ms(self, first=0, last=None):
+        """This rank's own time per iteration in milliseconds, waits on the neighbours excluded (device clock between
+        the end of the halo wait and the end of the iteration), for iterations [first, last) -> float64 array.
+        Synchronises."""
+        n = min(int(self.step.item()), self.max_iters)
+        t = self.iter_ns[first:n if last is None else min(last, n)].cpu().numpy()
+        return (t[:, 1] - t[:, 0]) * 1e-6
+
     def frame_losses(self):
         """Per-frame terms of the LAST evaluated iteration (the parameters before its update, like the `losses` vector
         the reference keeps at pose_initializtion.py:352-356) -> dict of [B] float64 tensors (synchronises nothing)."""
@@ -439,13 +454,13 @@ def _shared_faces_host(objfaces, B_total):
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
                    lr=1e-4, board=None, optimize_object_scale=False, shard=None, use_graph=True, halo="p2p",
-                   corr_delta=1.0, balance="probe"):
+                   corr_delta=1.0, balance="probe", _rebalance_to=None):
     """jointopt.py:93-161.  Extra keywords: `shard` (a sharding.FrameShard): when given (or when torch.distributed
     is initialised with more than one rank) `object_parameters` is the full sequence and this rank optimises its
     contiguous frame range; the returned model holds the gathered poses of ALL frames on every rank.
     `balance` ("probe" | "count"): how the sequence is cut when no shard is given -- by measured per-frame cost
     (one untimed + one timed pass of the heavy kernels over equal-count ranges, then ranges of equal cost) or by
-    frame count."""
+    frame count.  (_rebalance_to: bounds the mid-run re-partition must move to -- tests only.)"""
     if not torch.cuda.is_available():
         raise _lib.DynhorError("joint_optimize needs a CUDA device (dynhor_b200 has no CPU fallback)")
     if loss_weights is None:
@@ -467,6 +482,23 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
     # the correspondence term is on for everybody or for nobody: decided from the FULL list, not this rank's slice
     corr_on = loss_weights.get("lw_corr_obj", 0) > 0 and all("correspondences" in obj for obj in object_parameters)
 
+    def frames_on_device(sh, key, have=None, **kw):
+        """[sh.B, ...] tensor of per-frame entry `key`; `have` = (tensor, shard) of an earlier upload whose frames are
+        reused (device-side slice), only the frames it lacks are uploaded."""
+        if have is None or have[0] is None:
+            return _stack_frames(sh.slice(object_parameters), key, **kw)
+        old, s0 = have
+        lo, hi = max(sh.start, s0.start), min(sh.stop, s0.stop)
+        if lo >= hi:
+            return _stack_frames(sh.slice(object_parameters), key, **kw)
+        parts = []
+        if sh.start < lo:
+            parts.append(_stack_frames(object_parameters[sh.start:lo], key, **kw))
+        parts.append(old[lo - s0.start:hi - s0.start])
+        if hi < sh.stop:
+            parts.append(_stack_frames(object_parameters[hi:sh.stop], key, **kw))
+        return torch.cat(parts) if len(parts) > 1 else parts[0]
+
     def build(sh, with_corr, reuse=None):
         """Model of the frames of `sh`.  Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors
         are accepted too.  reuse = (model, shard) of an earlier build: frames it already holds stay on the device."""
@@ -474,23 +506,16 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
         trans = _stack_frames(local, "translations")
         rots = _stack_frames(local, "rotations")
         K = _stack_frames(local, "K_roi", pick=lambda t: t[:, 0])
-        if reuse is None:
-            masks = _stack_frames(local, "target_masks", dtype=torch.float32)
-        else:
-            m0, s0 = reuse
-            old = m0.ref_mask_object + m0.keep_mask_object - 1.0
-            lo, hi = max(sh.start, s0.start), min(sh.stop, s0.stop)
-            parts = []
-            if lo >= hi:
-                parts.append(_stack_frames(local, "target_masks", dtype=torch.float32))
-            else:
-                if sh.start < lo:
-                    parts.append(_stack_frames(object_parameters[sh.start:lo], "target_masks", dtype=torch.float32))
-                parts.append(old[lo - s0.start:hi - s0.start])
-                if hi < sh.stop:
-                    parts.append(_stack_frames(object_parameters[hi:sh.stop], "target_masks", dtype=torch.float32))
-            masks = torch.cat(parts) if len(parts) > 1 else parts[0]
-        corr = _stack_frames(local, "correspondences") if (with_corr and corr_on) else None
+        m0, s0 = reuse if reuse is not None else (None, None)
+        old_masks = None if m0 is None else m0.ref_mask_object + m0.keep_mask_object - 1.0
+        masks = frames_on_device(sh, "target_masks", (old_masks, s0), dtype=torch.float32)
+        corr = None
+        if with_corr and corr_on:
+            old_corr = m0.corr_term.records if (m0 is not None and getattr(m0, "corr_term", None) is not None) else None
+            C = int(local[0]["correspondences"].shape[1])
+            if old_corr is not None and old_corr.shape[1] != C:
+                old_corr = old_corr[:, :C]       # (pad_records appended a zero-weight record to an odd C)
+            corr = frames_on_device(sh, "correspondences", (old_corr, s0))
         return Joint_Optimizer(
             translations_object=trans, rotations_object=rots, verts_object_og=verts_object_og,
             faces_object=faces_dev, target_masks_object=masks, camintr_rois_object=K,
@@ -498,7 +523,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
             corr_delta=corr_delta)
 
     mark("mesh")
-    model = None
+    model, cost = None, None
     if auto and shard.world > 1 and balance == "probe":
         # cost-weighted partition: time the heavy kernels block by block on the equal-count ranges, gather, re-cut
         nblocks = max(1, min(16, (B_total // shard.world) // 32))
@@ -520,20 +545,60 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
     mark("model")
     fused = FusedJointOpt(model, loss_weights, lr, num_iterations, shard=shard, halo=halo, corr_on=corr_on)
     mark("fused")
+
+    def rebalance(fused, model, shard, done):
+        """Second cut, from the run itself: every rank's own time per iteration (the kernels' device clock, waits on
+        the neighbours excluded) over the last iterations rescales the probe's per-frame costs inside its range; if the
+        slowest rank is more than 3 % above the mean the ranges are re-cut and the moved frames change hands -- poses
+        and Adam moments through one all-gather, masks / correspondences from the host list (only the frames a rank
+        did not hold).  The iteration counter, history rows and the shared scale carry over."""
+        t = torch.tensor([float(np.mean(fused.compute_ms(max(done - 8, 0), done)))], dtype=torch.float64, device="cuda")
+        t_all = allgather_equal(t, shard).reshape(-1).cpu().numpy()
+        if _rebalance_to is None and not (t_all.max() > 1.03 * t_all.mean()):
+            return fused, model, shard
+        new = shard.with_bounds(_rebalance_to if _rebalance_to is not None else
+                                balanced_bounds(rescale_costs(cost, shard.bounds, t_all), shard.world))
+        if new.bounds == shard.bounds:
+            return fused, model, shard
+        B = shard.B
+        state = torch.cat([model.rotations_object.detach().reshape(B, 6), model.translations_object.detach().reshape(B, 3),
+                           fused.m_rot, fused.v_rot, fused.m_tr, fused.v_tr], 1)
+        state = allgather_frames(state, shard)[new.start:new.stop]
+        model2 = build(new, with_corr=True, reuse=(model, shard))
+        with torch.no_grad():
+            model2.rotations_object.copy_(state[:, 0:6].reshape(-1, 3, 2))
+            model2.translations_object.copy_(state[:, 6:9].reshape(-1, 1, 3))
+            model2.int_scales_object.copy_(model.int_scales_object)
+        fused2 = FusedJointOpt(model2, loss_weights, lr, num_iterations, shard=new, halo=halo, corr_on=corr_on,
+                               start_step=done)
+        fused2.m_rot.copy_(state[:, 9:15])
+        fused2.v_rot.copy_(state[:, 15:21])
+        fused2.m_tr.copy_(state[:, 21:24])
+        fused2.v_tr.copy_(state[:, 24:27])
+        fused2.mv_scale.copy_(fused.mv_scale)
+        fused2.hist[:done].copy_(fused.hist[:done])     # partial sums of the old range: the sum over ranks is unchanged
+        fused.check_status()
+        fused.release()
+        return fused2, model2, new
+
     try:
         try:
             from tqdm.auto import tqdm
             loop = tqdm(total=num_iterations)
         except Exception:  # pragma: no cover
             loop = None
+        can_rebalance = cost is not None and num_iterations >= 64
         chunk = 50
         done = 0
         while done < num_iterations:
-            n = min(chunk, num_iterations - done)
+            n = min(16 if (can_rebalance and done == 0) else chunk, num_iterations - done)
             fused.run(n, use_graph=use_graph)
             done += n
             if loop is not None:
                 loop.update(n)
+            if can_rebalance and done == 16:
+                fused, model, shard = rebalance(fused, model, shard, done)
+                mark("rebalance")
         mark("launched")
         loss_evolution = fused.history()  # the only host synchronisation of the loop
         mark("loop")

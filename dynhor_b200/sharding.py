@@ -106,6 +106,16 @@ def frame_costs_from_blocks(block_ms, start, stop, extra_ms=0.0):
     return cost + float(extra_ms) / B
 
 
+def rescale_costs(frame_cost, bounds, rank_ms):
+    """Per-frame costs whose sum over every rank's current range equals that rank's MEASURED time per iteration
+    (rank_ms, waits excluded): the probe's cost profile inside a range, the run's own clock between ranges."""
+    c = np.asarray(frame_cost, np.float64).copy()
+    for r, ms in enumerate(rank_ms):
+        a, b = bounds[r], bounds[r + 1]
+        c[a:b] *= float(ms) / max(c[a:b].sum(), 1e-30)
+    return c
+
+
 def exchange_halo(first_pose, last_pose, shard, halo_prev, halo_next, group=None):
     """Send this rank's first frame pose to rank-1 and last frame pose to rank+1; receive theirs into
     halo_prev / halo_next (9 floats each: rot6d row-major [3,2] then translation).  One grouped p2p batch."""
@@ -246,7 +256,9 @@ class PeerMailboxes:
 
     def reserve(self, n_ticks):
         """First tick of a run that will use at most n_ticks iterations.  Every rank makes the same calls in the
-        same order, so the bases agree without communication."""
+        same order, so the bases agree without communication.  A run has to be over on ALL ranks before the next one
+        is seeded (any collective after it -- the history all-reduce, a barrier -- guarantees that): its last publish
+        may share a slot with the next run's seed."""
         base = self.next_tick
         self.next_tick = base + int(n_ticks) + 4
         if self.next_tick > 2 ** 31 - 2 ** 24:  # pragma: no cover  (flags are int32; ~2e9 iterations per process)

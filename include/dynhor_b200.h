@@ -196,6 +196,10 @@ typedef struct dh_jointopt {
     double lw_offscreen;           /* 100000 in the reference (:154)                                             */
     float* offscreen;              /* [B,16] scratch: dT(3) dR(9) pad(1) penalty(1) pad(2), stage 1 only          */
     float* frame_coef;             /* [B,2]  scratch: per-frame dL/dpixel coefficients of the IoU loss            */
+    /* Optional iteration clock: [max_iters,2] zero-initialised u64, per iteration (globaltimer ns) the moment this
+     * rank's own work could start (after its waits on the neighbours) and the moment it ended.  Their difference is the
+     * rank's compute time without the waiting: what a cost-weighted re-partition needs.  NULL = off. */
+    unsigned long long* iter_ns;
 } dh_jointopt;
 #define DH_LOSS_JOINT 0
 #define DH_LOSS_STAGE1 1
