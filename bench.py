@@ -447,6 +447,8 @@ def run_ours(args):
     e2e = {"value": B_total * e2e_iters / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
            "d2h_bytes_per_step": d2h / e2e_iters, "iterations": e2e_iters, "seconds": dt,
            "final_loss": evo["loss"][-1]}
+    if getattr(model2, "timing", None):     # DH_TIMING=1: synchronised phase times of this rank's call (diagnostics)
+        e2e["phases_ms"] = {k: round(v, 2) for k, v in model2.timing}
 
     secondary = {}
     cb = None

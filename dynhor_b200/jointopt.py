@@ -438,18 +438,36 @@ def _stack_frames(frames, key, pick=None, dtype=None):
     return out if dtype is None or out.dtype == dtype else out.to(dtype)
 
 
-def _shared_faces_host(objfaces, B_total):
-    """run.py:158 stacks one identical face list per frame ([B,F,3] int64, 72 MB at 300 frames): compared with row 0
-    on the host (multi-threaded; skipped for a broadcast view) and uploaded ONCE as int32 [F,3]."""
-    f = objfaces if torch.is_tensor(objfaces) else torch.from_numpy(np.asarray(objfaces))
-    if f.ndim == 3:
-        if f.shape[0] > 1 and f.stride(0) != 0 and not torch.equal(f[1:], f[:-1]):
+class _SharedFaces:
+    """run.py:158 stacks one identical face list per frame ([B,F,3] int64: 72 MB at 300 frames, 1 GB at 4096).  The
+    list is uploaded ONCE as int32 [F,3]; the rows are compared with row 0 on the host only for the frames a rank
+    actually owns (so the ranks of a sharded run split the check), skipped altogether for a broadcast view."""
+
+    def __init__(self, objfaces):
+        f = objfaces if torch.is_tensor(objfaces) else torch.from_numpy(np.asarray(objfaces))
+        self.rows = f if (f.ndim == 3 and f.shape[0] > 1 and f.stride(0) != 0) else None
+        one = f[0] if f.ndim == 3 else f
+        if one.ndim != 2 or one.shape[-1] != 3:
+            raise AssertionError("Invalid shape for faces")
+        self.first = one
+        self.dev = one.to(torch.int32).contiguous().cuda()
+        self.checked = []
+
+    def check(self, start, stop):
+        if self.rows is None:
+            return
+        stop = min(stop, self.rows.shape[0])
+        for a, b in self.checked:          # only what no earlier call covered
+            if a <= start < b:
+                start = b
+            if a < stop <= b:
+                stop = a
+        if start >= stop:
+            return
+        if not torch.equal(self.rows[start:stop], self.first.expand(stop - start, -1, -1)):
             raise NotImplementedError("dynhor_b200 renders one mesh topology for all frames (run.py:158 stacks "
                                       "identical faces); per-frame face lists are not supported")
-        f = f[0]
-    if f.ndim != 2 or f.shape[-1] != 3:
-        raise AssertionError("Invalid shape for faces")
-    return f.to(torch.int32).contiguous().cuda()
+        self.checked.append((start, stop))
 
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
@@ -478,7 +496,8 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
     auto = shard is None
     shard = detect_shard(B_total) if shard is None else shard
     verts_object_og = tensorify(objvertices).cuda()
-    faces_dev = _shared_faces_host(objfaces, B_total)
+    faces = _SharedFaces(objfaces)
+    faces_dev = faces.dev
     # the correspondence term is on for everybody or for nobody: decided from the FULL list, not this rank's slice
     corr_on = loss_weights.get("lw_corr_obj", 0) > 0 and all("correspondences" in obj for obj in object_parameters)
 
@@ -503,6 +522,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
         """Model of the frames of `sh`.  Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors
         are accepted too.  reuse = (model, shard) of an earlier build: frames it already holds stay on the device."""
         local = sh.slice(object_parameters)
+        faces.check(sh.start, sh.stop)
         trans = _stack_frames(local, "translations")
         rots = _stack_frames(local, "rotations")
         K = _stack_frames(local, "K_roi", pick=lambda t: t[:, 0])

@@ -454,6 +454,14 @@ def test_error_behaviour():
         f = torch.zeros(2, 5, 3, dtype=torch.int64).cuda()
         f[1, 0, 0] = 1
         shared_faces(f)
+    # the drop-in call checks the stacked face lists it is given (run.py:158) for the frames it owns
+    from dynhor_b200.jointopt import joint_optimize
+    g = load_golden("s64_b5")
+    params = object_parameters_from_golden(g)
+    faces = np.stack([g["faces"].astype(np.int64)] * len(params))
+    faces[3, 7] = faces[3, 7][::-1]
+    with pytest.raises(NotImplementedError):
+        joint_optimize(params, objvertices=g["verts"], objfaces=faces, loss_weights=_lw(g), num_iterations=1, lr=1e-4)
 
 
 def test_stage1_coarse_silhouette_term_vs_reference_run():
