@@ -69,6 +69,42 @@ def _dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
     return scores, vals, idx.long()
 
 
+def merge_topk(vals_by_rank, idx_by_rank, offsets, k):
+    """Top-k over templates sharded across ranks: every rank scored its own slice of the bank (pose_initializtion.py:
+    295-296 is independent per template) and kept its k best per frame; the world x k candidates of a frame are merged
+    here -- largest value first, lowest GLOBAL template index on ties, the kernel's own order.
+        vals_by_rank / idx_by_rank: [world, Fm, k] (idx local to the rank's slice); offsets[r] = first template of
+        rank r.  Returns (values [Fm,k], global indices [Fm,k] int64)."""
+    W, Fm, kk = vals_by_rank.shape
+    off = torch.as_tensor(offsets, dtype=torch.int64, device=idx_by_rank.device).reshape(W, 1, 1)
+    v = vals_by_rank.permute(1, 0, 2).reshape(Fm, W * kk)
+    g = (idx_by_rank.to(torch.int64) + off).permute(1, 0, 2).reshape(Fm, W * kk)
+    order = torch.argsort(g, dim=1, stable=True)                 # by index first ...
+    v, g = torch.gather(v, 1, order), torch.gather(g, 1, order)
+    order = torch.argsort(v, dim=1, descending=True, stable=True)   # ... then a stable sort by value keeps it on ties
+    return torch.gather(v, 1, order)[:, :k], torch.gather(g, 1, order)[:, :k]
+
+
+def dino_topk_sharded(frame_bank, templ_bank_local, k, rank, world, n_local_by_rank, group=None):
+    """The reference-sized bank (6000 templates x 1369 x 768 bf16 = 12.6 GB) split over the GPUs of the box: this
+    rank scores `templ_bank_local` (its contiguous slice), then one all_gather of the [Fm,k] lists and `merge_topk`.
+    No scores matrix is returned (it would be [Fm, N_total] gathered from every rank)."""
+    import torch.distributed as dist
+    _, vals, idx = dino_cos_topk(frame_bank, templ_bank_local, min(k, templ_bank_local.shape[0]), return_scores=False)
+    if vals.shape[1] < k:   # a slice with fewer than k templates: pad with -inf candidates
+        pad = k - vals.shape[1]
+        vals = torch.cat([vals, vals.new_full((vals.shape[0], pad), float("-inf"))], 1)
+        idx = torch.cat([idx, idx.new_zeros((idx.shape[0], pad))], 1)
+    if world == 1:
+        return vals, idx
+    vs = [torch.empty_like(vals) for _ in range(world)]
+    is_ = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(vs, vals.contiguous(), group=group)
+    dist.all_gather(is_, idx.contiguous(), group=group)
+    offsets = [int(sum(n_local_by_rank[:r])) for r in range(world)]
+    return merge_topk(torch.stack(vs), torch.stack(is_), offsets, k)
+
+
 def select_view(dino_cos, topk_indices, render_rotations, rotations_init=None, former_max_idx=None, use_former=True):
     """The sequential part of the view selection (pose_initializtion.py:298-321) for ONE frame, on the scores and
     top-k indices the kernels produced for all frames at once.

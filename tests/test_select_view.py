@@ -103,3 +103,30 @@ def test_every_reference_path_is_hit_and_random_cases_agree():
             "top5+far_former+near_rejected_former", "top5+far_prev+near_accepted", "top5+far_prev+near_rejected_cos"}
     missing = {n for n in need if not any(s == n or s.startswith(n) for s in seen)}
     assert not missing, (missing, sorted(seen))
+
+
+def test_merge_topk_of_sharded_template_banks():
+    """Templates sharded over ranks: merging the per-rank top-k lists equals the top-k of the whole bank, ties going
+    to the lowest global index (the kernel's order)."""
+    from dynhor_b200.dino_match import merge_topk
+    g = torch.Generator().manual_seed(0)
+    Fm, k = 7, 5
+    sizes = [11, 3, 9, 20]                      # ragged slices, one smaller than k
+    scores = torch.rand(Fm, sum(sizes), generator=g)
+    scores[:, 12] = scores[:, 30]               # exact ties across ranks
+    scores[0, :4] = 2.0                         # and inside one
+    vals, idxs, off = [], [], []
+    a = 0
+    for n in sizes:
+        sl = scores[:, a:a + n]
+        kk = min(k, n)
+        order = torch.argsort(sl, dim=1, descending=True, stable=True)[:, :kk]
+        v, i = torch.gather(sl, 1, order), order
+        if kk < k:
+            v = torch.cat([v, torch.full((Fm, k - kk), float("-inf"))], 1)
+            i = torch.cat([i, torch.zeros(Fm, k - kk, dtype=torch.int64)], 1)
+        vals.append(v), idxs.append(i), off.append(a)
+        a += n
+    mv, mi = merge_topk(torch.stack(vals), torch.stack(idxs), off, k)
+    order = torch.argsort(scores, dim=1, descending=True, stable=True)[:, :k]
+    assert torch.equal(mi, order) and torch.equal(mv, torch.gather(scores, 1, order))
