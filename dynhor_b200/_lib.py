@@ -99,6 +99,7 @@ SIGNATURES = {
     "dh_dino_topk": (c_i, [c_p, c_p, c_i, c_i, c_l, c_i, c_p, c_p, c_p, c_p, c_l, c_p]),
     "dh_dino_prescale": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "dh_roi_process": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "dh_roi_process_f32": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
 MAILBOX_WORDS = 512      # DH_MAILBOX_WORDS

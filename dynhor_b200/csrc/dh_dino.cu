@@ -7,9 +7,12 @@
 //               tcgen05.mma (one elected thread, accumulators in TMEM) -> tcgen05.ld epilogue.  The output is only
 //               N x Fm (1000 x 300) while K is ~5e5, so the grid splits K: one CTA per (128-template tile, 320-frame
 //               tile, K slice), each streaming its slice once; partial tiles go to a small fp32 workspace.
-// k_dino_reduce_topk  split-K reduction of the partial tiles and the per-frame top-k selection (torch.topk / argmax
-//               semantics of pose_initializtion.py:299,309; ties -> lowest index) in one launch, one CTA per 8 frames;
-//               k_dino_reduce + k_dino_topk: the same as two kernels, for more than 6144 templates.
+// k_dino_reduce split-K reduction of the partial tiles into scores [Fm, N] (coalesced both ways via a smem transpose).
+// k_dino_topk   per frame: top-k selection (torch.topk / argmax semantics of pose_initializtion.py:299,309;
+//               ties -> lowest index).
+// (Round 2 measured the two tail kernels merged into one -- a CTA per 8 frames reducing its 32-byte sectors of the
+//  workspace and selecting from shared memory: 0.372 ms per batch against 0.312 ms, too few CTAs to hide the strided
+//  reads -- and kept them apart.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -285,56 +288,6 @@ k_dino_topk(const float* __restrict__ scores, int N, int k, float* __restrict__ 
     }
 }
 
-// Split-K reduction AND top-k in one kernel (N <= kFuseMaxN templates): one CTA per 8 consecutive frames.
-//   phase 1: scores[f0 + j][n] = sum_slices partial[slice][n][f0 + j] into shared memory -- the 8 frames of a
-//            template are one 32-byte sector of the workspace, so the strided read wastes nothing -- and, when asked
-//            for, out to scores [Fm, N] with the templates contiguous;
-//   phase 2: warp j selects the top-k of frame f0 + j by k rounds of warp-wide arg-max over its row (largest value,
-//            lowest index on ties: torch.topk(largest=True)'s order on tie-free data, pose_initializtion.py:299,309).
-// Replaces the k_dino_reduce + k_dino_topk pair (two launches, the [Fm, N] matrix written and read back through
-// L2): 37.5 us -> measured in profiles/r2_dino.md.
-constexpr int kFuseFrames = 8;
-constexpr int kFuseMaxN = 6144;   // 8 x 6144 x 4 B = 192 KB of shared memory: the reference's 6000 templates fit
-__global__ void __launch_bounds__(256)
-k_dino_reduce_topk(const float* __restrict__ partial, int nslices, int m_pad, int ldc, int N, int Fm, int k,
-                   float* __restrict__ scores, float* __restrict__ topk_vals, int32_t* __restrict__ topk_idx) {
-    extern __shared__ float s_rows[];   // [8][N]
-    const int f0 = blockIdx.x * kFuseFrames, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < N * kFuseFrames; i += 256) {
-        const int n = i >> 3, j = i & 7;
-        float acc = 0.0f;
-        if (f0 + j < Fm)
-            for (int sl = 0; sl < nslices; sl++) acc += partial[((size_t)sl * m_pad + n) * ldc + f0 + j];
-        s_rows[j * N + n] = acc;
-    }
-    __syncthreads();
-    if (scores != nullptr)
-        for (int j = 0; j < kFuseFrames && f0 + j < Fm; j++)
-            for (int n = tid; n < N; n += 256) scores[(size_t)(f0 + j) * N + n] = s_rows[j * N + n];
-    const int f = f0 + warp;
-    if (f >= Fm) return;
-    float* row = s_rows + warp * N;
-    for (int r = 0; r < k; r++) {
-        float bv = -3.0e38f;
-        int bi = 0x7FFFFFFF;
-        for (int n = lane; n < N; n += 32) {
-            const float v = row[n];
-            if (v > bv) { bv = v; bi = n; }      // ascending n: the first (lowest) index of equal values stays
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) {
-            topk_vals[(size_t)f * k + r] = bv;
-            topk_idx[(size_t)f * k + r] = bi;
-            if (bi < N) row[bi] = -3.0e38f;
-        }
-        __syncwarp();
-    }
-}
-
 // feats [n, P, D] fp32 -> bf16 [n, P*D]: each patch vector divided by its L2 norm, times mask[n,p] / sum_p mask[n,:]
 // when a mask is given.  One warp per (n, p) patch.
 __global__ void __launch_bounds__(256)
@@ -451,7 +404,7 @@ int make_plan(int32_t N, int32_t Fm, int64_t Kdim, Plan* pl) {
     const int tiles = pl->m_tiles * pl->n_pairs;
     int ns = sms / tiles;
     if (ns < 1) ns = 1;
-    if (2 * tiles > sms) {
+    if (4 * tiles > sms) {
         // many output tiles (the reference's 6000 templates: 48 tiles): several waves.  Pick the K split whose last wave
         // is fullest, among splits that keep at least 64 k-blocks (8 pipeline refills) per CTA.
         double best = -1.0;
@@ -526,14 +479,6 @@ int dh_dino_topk(const void* templ_bf16, const void* frames_bf16, int32_t N, int
         if (rc) return rc;
     }
     DH_LAUNCH_OK("k_dino_gemm");
-    if (N <= kFuseMaxN && getenv("DH_DINO_SPLIT_TAIL") == nullptr) {
-        const size_t sm = (size_t)kFuseFrames * N * sizeof(float);
-        DH_CUDA(cudaFuncSetAttribute(k_dino_reduce_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_dino_reduce_topk<<<(Fm + kFuseFrames - 1) / kFuseFrames, 256, sm, st>>>(
-            (const float*)workspace, pl.nslices, pl.m_pad, pl.ldc, N, Fm, k, scores, topk_vals, topk_idx);
-        DH_LAUNCH_OK("k_dino_reduce_topk");
-        return DH_OK;
-    }
     k_dino_reduce<<<dim3((N + 31) / 32, (Fm + 31) / 32), 256, 0, st>>>((const float*)workspace, pl.nslices, pl.m_pad,
                                                                        pl.ldc, N, Fm, score_buf);
     DH_LAUNCH_OK("k_dino_reduce");

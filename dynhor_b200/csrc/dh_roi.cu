@@ -121,6 +121,53 @@ k_roi_crop(const uint8_t* __restrict__ obj_bits, const uint8_t* __restrict__ han
     }
 }
 
+// The same crops for rendered TEMPLATE views (pose_initializtion.py:188-246, compute_prior_features): float RGBA
+// renderings and a float depth map instead of a uint8 photograph, no occluder.  images: [B,H,W,pitch] floats (RGB in
+// channels 0..2), depth: [B,H,W] or NULL.  crop_image [B,3,S,S] is white where the crop mask is 0 (:215), crop_depth
+// [B,S,S] is the plain ROIAlign of the depth (:213-214).
+__global__ void __launch_bounds__(kThreads)
+k_roi_crop_f32(const uint8_t* __restrict__ obj_bits, const float* __restrict__ images, int pitch,
+               const float* __restrict__ depth, int H, int W, int S, float pad, float expansion,
+               const int32_t* __restrict__ bounds, float* __restrict__ bbox, float* __restrict__ square_bbox,
+               uint8_t* __restrict__ crop_mask, float* __restrict__ crop_image, float* __restrict__ crop_depth) {
+    const int b = blockIdx.y;
+    const int idx = blockIdx.x * kThreads + threadIdx.x;
+    const int r0 = bounds[4 * b + 0], r1 = bounds[4 * b + 1], c0 = bounds[4 * b + 2], c1 = bounds[4 * b + 3];
+    const bool empty = r1 < 0;
+    float bb[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, xyxy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!empty) roi_boxes(r0, r1, c0, c1, H, W, pad, expansion, bb, sq, xyxy);
+    if (idx < 4) {
+        bbox[4 * b + idx] = bb[idx];
+        square_bbox[4 * b + idx] = sq[idx];
+    }
+    if (idx >= S * S) return;
+    const size_t o = (size_t)b * S * S + idx;
+    if (empty) {
+        crop_mask[o] = 0;
+        for (int c = 0; c < 3; c++) crop_image[((size_t)b * 3 + c) * S * S + idx] = 1.0f;
+        if (crop_depth) crop_depth[o] = 0.0f;
+        return;
+    }
+    const int ph = idx / S, pw = idx - ph * S;
+    const RoiGeom g = roi_geom(xyxy, S);
+    const uint8_t* ob = obj_bits + (size_t)b * H * W;
+    const bool obit = roi_align_cell(g, ph, pw, H, W, [&](int y, int x) { return (float)__ldg(ob + (size_t)y * W + x); }) >= 0.5f;
+    crop_mask[o] = obit ? 1 : 0;
+    float v[3] = {1.0f, 1.0f, 1.0f};
+    if (obit) {
+        const float* im = images + (size_t)b * H * W * pitch;
+        roi_align_cell3(g, ph, pw, H, W, [&](int y, int x, float* px) {
+            const float* q = im + ((size_t)y * W + x) * pitch;
+            px[0] = __ldg(q); px[1] = __ldg(q + 1); px[2] = __ldg(q + 2);
+        }, v);
+    }
+    for (int c = 0; c < 3; c++) crop_image[((size_t)b * 3 + c) * S * S + idx] = v[c];
+    if (crop_depth != nullptr) {
+        const float* dp = depth + (size_t)b * H * W;
+        crop_depth[o] = roi_align_cell(g, ph, pw, H, W, [&](int y, int x) { return __ldg(dp + (size_t)y * W + x); });
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -141,6 +188,24 @@ int dh_roi_process(const uint8_t* obj_bits, const uint8_t* hand_bits, const uint
         obj_bits, hand_bits, images_hwc, H, W, S, pad, expansion, bounds, bbox, square_bbox, crop_mask, target,
         target_tri, crop_image);
     DH_LAUNCH_OK("k_roi_crop");
+    return DH_OK;
+}
+
+int dh_roi_process_f32(const uint8_t* obj_bits, const float* images, int32_t pitch, const float* depth, int32_t B,
+                       int32_t H, int32_t W, int32_t S, float pad, float expansion, int32_t* bounds, float* bbox,
+                       float* square_bbox, uint8_t* crop_mask, float* crop_image, float* crop_depth, void* stream) {
+    DH_REQUIRE(obj_bits && images && bounds && bbox && square_bbox && crop_mask && crop_image, "NULL input / output");
+    DH_REQUIRE(B > 0 && H > 0 && W > 0 && S > 0 && B <= 65535 && pitch >= 3, "bad sizes");
+    DH_REQUIRE((crop_depth == nullptr) == (depth == nullptr), "depth and crop_depth go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_roi_init<<<(4 * B + kThreads - 1) / kThreads, kThreads, 0, st>>>(bounds, B);
+    DH_LAUNCH_OK("k_roi_init");
+    k_roi_bounds<<<dim3((H + kRowsPerCta - 1) / kRowsPerCta, B), kThreads, 0, st>>>(obj_bits, H, W, bounds);
+    DH_LAUNCH_OK("k_roi_bounds");
+    k_roi_crop_f32<<<dim3((S * S + kThreads - 1) / kThreads, B), kThreads, 0, st>>>(
+        obj_bits, images, pitch, depth, H, W, S, pad, expansion, bounds, bbox, square_bbox, crop_mask, crop_image,
+        crop_depth);
+    DH_LAUNCH_OK("k_roi_crop_f32");
     return DH_OK;
 }
 

@@ -18,7 +18,7 @@ import yaml
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from dynhor_b200 import synth  # noqa: E402
+from dynhor_b200 import poses_io, synth  # noqa: E402
 from dynhor_b200.geometry import rot6d_to_matrix  # noqa: E402
 from dynhor_b200.jointopt import joint_optimize  # noqa: E402
 from dynhor_b200.renderer import Renderer  # noqa: E402
@@ -74,16 +74,10 @@ if __name__ == "__main__":
         lr=config["system"]["joint_lr"],
         board=board,
     )
-    obj_rot = rot6d_to_matrix(model.rotations_object).transpose(1, 2)  # object -> camera (run.py:166)
-    obj_trans = model.translations_object
-    obj_rot_np = obj_rot.detach().cpu().numpy()
-    obj_trans_np = obj_trans.detach().cpu().numpy()
     camintr = synth.full_frame_K(args.height, args.width)
     if rank == 0:
-        os.makedirs(os.path.join(sample_folder, "obj_infos"), exist_ok=True)
-        for i in range(args.frames):
-            np.savez(os.path.join(sample_folder, "obj_infos/{:06d}.npz".format(i)),
-                     R=obj_rot_np[i], T=obj_trans_np[i], K=camintr)
+        # run.py:166-179: one obj_infos/<frame id>.npz per frame (R object -> camera, T, K)
+        poses_io.save_obj_infos(model, camintr, ["rgb/{:06d}.jpg".format(i) for i in range(args.frames)], sample_folder)
         err0 = np.abs(seq["R_init"] - seq["R_gt"]).max()
         err1 = np.abs(rot6d_to_matrix(model.rotations_object).detach().cpu().numpy() - seq["R_gt"]).max()
         print(f"{args.frames} frames, {num_iterations} iterations: loss {loss_evolution['loss'][0]:.5f} -> "

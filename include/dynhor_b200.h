@@ -302,6 +302,16 @@ int dh_roi_process(const uint8_t* obj_bits, const uint8_t* hand_bits, const uint
                    float* square_bbox, uint8_t* crop_mask, float* target, int8_t* target_tri, float* crop_image,
                    void* stream);
 
+/* The same crops for rendered TEMPLATE views: pose_initializtion.py:188-246 (compute_prior_features) builds, per view,
+ * the tight box of the rendering's alpha == 1 mask (+5 px, clamped to the render size), the square box x1.3, and
+ * ROIAlign crops of the mask, the float RGB rendering (white outside the mask, :215) and the depth map -- one view at
+ * a time, before a batch-1 DINOv2 forward.  Here: all views of a batch in three launches.
+ *   obj_bits [B,H,W] u8 (rendering alpha == 1), images [B,H,W,pitch] f32 (RGB in channels 0..2, pitch 4 for RGBA),
+ *   depth [B,H,W] f32 or NULL;  crop_image [B,3,S,S] f32, crop_depth [B,S,S] f32 or NULL; the rest as above. */
+int dh_roi_process_f32(const uint8_t* obj_bits, const float* images, int32_t pitch, const float* depth, int32_t B,
+                       int32_t H, int32_t W, int32_t S, float pad, float expansion, int32_t* bounds, float* bbox,
+                       float* square_bbox, uint8_t* crop_mask, float* crop_image, float* crop_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,28 @@ def test_registered_ops_on_the_device():
     d = synth.make_dino_features(40, 6, 24, 64, seed=2, device="cuda")
     fb, tb = build_bank(d["frames"], d["masks"]), build_bank(d["templ"])
     opcheck(torch.ops.dynhor.dino_topk.default, (fb, tb, 5), test_utils=("test_schema", "test_faketensor"))
+
+
+def test_overlay_of_saved_poses(tmp_path):
+    """vis.py:41-55 on the CUDA renderer: the overlay of a saved pose covers the object's mask in the frame."""
+    import types
+    from dynhor_b200 import poses_io, synth
+    from dynhor_b200.renderer import Renderer
+    B, H, W = 2, 480, 640
+    verts, faces = synth.icosphere_mesh(3, seed=2)
+    R, T = synth.gt_trajectory(B, period=40)
+    m = types.SimpleNamespace(rotations_object=torch.from_numpy(np.ascontiguousarray(R[:, :, :2])).float().cuda(),
+                              translations_object=torch.from_numpy(T).float().reshape(B, 1, 3).cuda())
+    paths = ["rgb/%04d.jpg" % i for i in range(B)]
+    poses_io.save_obj_infos(m, synth.full_frame_K(H, W), paths, str(tmp_path))
+    infos = poses_io.load_obj_infos(str(tmp_path), paths)
+    frames = np.full((B, H, W, 3), 200, np.uint8)
+    out = poses_io.overlay_mesh(frames, infos, verts, faces)
+    changed = (out != frames).any(-1)
+    # ground truth: where the projected vertices fall
+    K = synth.full_frame_K(H, W).astype(np.float64)
+    for b in range(B):
+        uv = (verts.astype(np.float64) @ R[b] + T[b]) @ K.T
+        uv = uv[:, :2] / uv[:, 2:3]
+        inside = changed[b][np.clip(uv[:, 1].round().astype(int), 0, H - 1), np.clip(uv[:, 0].round().astype(int), 0, W - 1)]
+        assert inside.mean() > 0.9 and 0.01 < changed[b].mean() < 0.5
