@@ -16,6 +16,7 @@
 //   k_pose_update  per frame: + smoothness gradient, Gram-Schmidt backward, two-group Adam (jointopt.py:135-141)
 //   k_finalize     per-iteration loss / IoU sums -> history row, step counter, optional scale update
 // Compiled with --fmad=false: see dh_core.h for the fp32 contract.
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -1838,29 +1839,34 @@ struct IterEvents { cudaEvent_t ev[9]; };
 
 // The silhouette term's kernels of one iteration for the plan's frames: projection, binning, raster (+ fused loss
 // epilogue) and, unless forward_only, the per-frame map kernel and the two backward kernels.
-int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st, IterEvents* evs = nullptr) {
+// part: 0 = everything, 1 = projection / binning / raster only, 2 = map kernel + backward only (pipelined groups).
+int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st, IterEvents* evs = nullptr,
+                       int part = 0) {
     const dh_sil& s = p.sil;
     const int is = raster_size(s), nstrips = is / kSH, B = s.B;
     dim3 gv((s.V + kThreads - 1) / kThreads, B);
     const bool stage1 = p.loss_mode == DH_LOSS_STAGE1;
+    // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
+    const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
+    int rc = DH_OK;
+    if (part != 2) {
     k_project<true><<<gv, kThreads, 0, st>>>(p.verts_og, p.Rmat, p.trans, p.scale, s.K, s.orig_size,
                                               reinterpret_cast<float4*>(s.proj), s.V, s.bin_count, nstrips,
                                               p.loss_counts, s.owned, (2 * s.F + 31) / 32,
                                               stage1 ? p.offscreen : nullptr, (float)p.lw_offscreen, s.far_);
     DH_LAUNCH_OK("k_project");
     DH_REC(2);
-    int rc = launch_forward_common(s, st);
+    rc = launch_forward_common(s, st);
     if (rc) return rc;
     DH_REC(3);
     const size_t zb = raster_smem_bytes(s);
     rc = set_smem(k_raster<true>, zb);
     if (rc) return rc;
-    // dL/drend = gcoef * (k/2), gcoef = (lw / B) / keep_sum in fp32 like autograd (losses.py:69-75)
-    const float gcoef = ((float)p.lw_sil / (float)p.B_total) / (float)p.keep_sum;
     k_raster<true><<<dim3(nstrips, B), kRasterThreads, zb, st>>>(s, p.mask_tri, gcoef, nullptr, p.loss_counts);
     DH_LAUNCH_OK("k_raster");
     DH_REC(4);
-    if (forward_only) return DH_OK;
+    }
+    if (forward_only || part == 1) return DH_OK;
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
     if (rc) return rc;
     float* fcoef = stage1 ? p.frame_coef : nullptr;
@@ -1879,38 +1885,6 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
         s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1, fcoef);
     DH_LAUNCH_OK("k_backward<bitmaps>");
-    return DH_OK;
-}
-
-int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
-                     cudaStream_t st, IterEvents* evs = nullptr) {
-    const dh_sil& s = p.sil;
-    const int B = s.B;
-    const bool with_sil = p.lw_sil > 0.0;
-    DH_REC(0);
-    k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
-    DH_LAUNCH_OK("k_pose_prep");
-    DH_REC(1);
-    const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
-    if (with_corr) {
-        const int rc = launch_corr(p.corr.records, B, p.corr.C, p.Rmat, p.trans, p.scale, s.K, s.S, p.corr.delta,
-                                   p.corr.partials, p.corr.nslots, st);
-        if (rc) return rc;
-    }
-    DH_REC(8);
-    if (with_sil) {
-        const int rc = launch_sil_kernels(p, mode == 2, st, evs);
-        if (rc) return rc;
-    } else {
-        DH_REC(2); DH_REC(3); DH_REC(4);
-    }
-    DH_REC(5);
-    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
-    DH_LAUNCH_OK("k_pose_update");
-    DH_REC(6);
-    k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
-    DH_LAUNCH_OK("k_finalize");
-    DH_REC(7);
     return DH_OK;
 }
 
@@ -1946,6 +1920,38 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
     if (q.offscreen != nullptr) q.offscreen += o * 16;
     if (q.frame_coef != nullptr) q.frame_coef += o * 2;
     return q;
+}
+
+int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
+                     cudaStream_t st, IterEvents* evs = nullptr) {
+    const dh_sil& s = p.sil;
+    const int B = s.B;
+    const bool with_sil = p.lw_sil > 0.0;
+    DH_REC(0);
+    k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
+    DH_LAUNCH_OK("k_pose_prep");
+    DH_REC(1);
+    const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
+    if (with_corr) {
+        const int rc = launch_corr(p.corr.records, B, p.corr.C, p.Rmat, p.trans, p.scale, s.K, s.S, p.corr.delta,
+                                   p.corr.partials, p.corr.nslots, st);
+        if (rc) return rc;
+    }
+    DH_REC(8);
+    if (with_sil) {
+        const int rc = launch_sil_kernels(p, mode == 2, st, evs);
+        if (rc) return rc;
+    } else {
+        DH_REC(2); DH_REC(3); DH_REC(4);
+    }
+    DH_REC(5);
+    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
+    DH_LAUNCH_OK("k_pose_update");
+    DH_REC(6);
+    k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
+    DH_LAUNCH_OK("k_finalize");
+    DH_REC(7);
+    return DH_OK;
 }
 
 int check_plan(const dh_jointopt* p) {

@@ -6,6 +6,9 @@ Replaces the two steps of pose_initializtion.py:286-321 that are data-parallel o
     torch.argmax(dino_cos) / torch.topk(dino_cos, k, largest=True)            pose_initializtion.py:299,309
 The scores depend only on (frame features, template bank), not on the previous frame, so all frames are scored in
 one GEMM; the sequential candidate gating (:300-321) stays on the host in `select_view`.
+Tolerance: the banks are bf16 and fold the reference's `+ 1e-6` away, so scores agree with the fp32 expression to about
+2e-3 absolute; top-k is index-exact where consecutive scores differ by more than that.  `rescore_topk_fp32` restores
+the reference's order (and exact scores) among the k candidates of a frame when that matters.
 Everything here needs CUDA tensors and the native library; there is no CPU fallback.
 """
 import ctypes
@@ -67,6 +70,26 @@ def _dino_cos_topk(frame_bank, templ_bank, k, return_scores=True):
                                 _lib.ptr(vals), _lib.ptr(idx), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                "dh_dino_topk")
     return scores, vals, idx.long()
+
+
+def rescore_topk_fp32(frame_feats, frame_masks, templ_feats, topk_idx):
+    """The bf16 banks drop the reference's +1e-6 in the denominator and round every product to 8 mantissa bits: scores
+    agree to ~2e-3, which can reorder candidates whose fp32 scores are closer than that (and `select_view` compares
+    scores against max - std).  This re-scores only the k candidates of every frame with the reference expression
+    itself (pose_initializtion.py:295-296, fp32, eps 1e-6) and re-sorts them -- k x P x D work per frame instead of
+    N x P x D.  frame_feats [Fm,P,D] and frame_masks [Fm,P] on the GPU; templ_feats [N,P,D] fp32 on any device (only
+    the candidate rows are fetched); topk_idx [Fm,k].  Returns (values [Fm,k] fp32, indices [Fm,k]) best first."""
+    Fm, k = topk_idx.shape
+    dev = frame_feats.device
+    rows = templ_feats[topk_idx.reshape(-1).to(templ_feats.device)].to(dev, non_blocking=True).float()
+    rows = rows.reshape(Fm, k, *rows.shape[1:])                                          # [Fm,k,P,D]
+    g = frame_feats.float()[:, None]                                                    # [Fm,1,P,D]
+    m = frame_masks.float()[:, None]                                                    # [Fm,1,P]
+    cos = (m * (g * rows).sum(-1) / (g.norm(dim=-1) * rows.norm(dim=-1) + 1e-6)).sum(-1) / m.sum(-1)
+    order = torch.argsort(topk_idx, dim=1, stable=True)           # lowest index first, then a stable sort by score:
+    cos, idx = torch.gather(cos, 1, order), torch.gather(topk_idx, 1, order)            # ties keep the lowest index
+    order = torch.argsort(cos, dim=1, descending=True, stable=True)
+    return torch.gather(cos, 1, order), torch.gather(idx, 1, order)
 
 
 def merge_topk(vals_by_rank, idx_by_rank, offsets, k):

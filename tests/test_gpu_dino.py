@@ -99,3 +99,28 @@ def test_dino_cluster_variants(cluster, monkeypatch):
     template count that needs padded tiles (N = 1100 -> 9 tiles -> 10/12/16 with clusters of 2/4/8)."""
     monkeypatch.setenv("DH_DINO_CLUSTER", cluster)
     _run(1100, 50, 24, 64, 5, seed=5)
+
+
+def test_fp32_rescoring_restores_the_reference_order_on_near_ties():
+    """bf16 banks can swap candidates whose fp32 scores are closer than ~2e-3.  Templates 1..4 are copies of
+    template 0 with a perturbation small enough that their fp32 scores differ by ~1e-4: the kernel's order among them
+    is arbitrary at bf16 precision, rescore_topk_fp32 must return the oracle's."""
+    from dynhor_b200.dino_match import build_bank, dino_cos_topk, rescore_topk_fp32
+    from oracle import dino_oracle
+    g = torch.Generator().manual_seed(4)
+    N, Fm, P, D, k = 64, 6, 40, 64, 5
+    templ = torch.nn.functional.normalize(torch.randn(N, P, D, generator=g), dim=-1)
+    frames = torch.nn.functional.normalize(templ[:Fm] + 0.3 * torch.randn(Fm, P, D, generator=g), dim=-1)
+    for f in range(Fm):                       # k near-duplicates of every frame's best template
+        for j in range(1, k):
+            templ[8 + f * k + j] = torch.nn.functional.normalize(templ[f] + 2e-3 * j * torch.randn(P, D, generator=g), dim=-1)
+    masks = (torch.rand(Fm, P, generator=g) < 0.7).float()
+    masks[:, 0] = 1
+    s_o, v_o, i_o = dino_oracle.dino_cos_topk(frames, masks, templ, k)
+    gaps = (v_o[:, :-1] - v_o[:, 1:]).min()
+    assert 0 < float(gaps) < 2e-3                                  # the near-ties are there, below bf16 resolution
+    _, v, i = dino_cos_topk(build_bank(frames.cuda(), masks.cuda()), build_bank(templ.cuda()), k)
+    assert torch.equal(torch.sort(i.cpu(), 1).values, torch.sort(i_o, 1).values)   # same candidate SET
+    v2, i2 = rescore_topk_fp32(frames.cuda(), masks.cuda(), templ, i)               # templates stay on the host
+    assert torch.equal(i2.cpu(), i_o)
+    assert torch.allclose(v2.cpu(), v_o, atol=1e-6)
