@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Key metrics of every kernel in an ncu report -> markdown table (for profiles/).
 
-    python tools/ncu_summary.py REPORT.ncu-rep [KERNEL_REGEX]"""
+    python tools/ncu_summary.py REPORT.ncu-rep [KERNEL_REGEX] [--json FRAMES SOURCE_NOTE]
+
+--json: also rewrites profiles/alu.json (thread-instructions per frame, issue-slot utilisation, lanes per instruction
+of the raster / backward kernels: bench.py's instruction roofline) and profiles/traffic.json (DRAM bytes per frame)
+from this report, FRAMES = frames per launch of the captured run."""
 import csv
 import io
 import re
@@ -51,6 +55,31 @@ def main():
             else:
                 cells.append("-")
         print(f"| {short} | " + " | ".join(cells) + " |")
+    if "--json" in sys.argv:
+        import json
+        import os
+        frames = int(sys.argv[sys.argv.index("--json") + 1])
+        note = sys.argv[sys.argv.index("--json") + 2]
+        names = [(r"k_raster<(\(bool\))?1>", "raster"), (r"k_backward<(\(bool\))?1, (\(bool\))?1>", "backward"),
+                 (r"k_corr", "corr"), (r"k_setup_bin", "setup_bin"), (r"k_neg_maps", "neg_maps")]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        alu, traffic = {}, {"_note": note}
+        for r in rows[2:]:
+            key = next((v for k, v in names if re.search(k, r[ix["Kernel Name"]])), None)
+            if key is None or key in alu:
+                continue
+            g = lambda m: float(r[ix[m]])  # noqa: E731
+            gb = lambda m: float(r[ix[m]]) * scale.get(units[ix[m]], 1.0)  # noqa: E731
+            warp_inst = g("smsp__inst_executed.sum")
+            lanes = g("smsp__thread_inst_executed_per_inst_executed.ratio")
+            alu[key] = {"thread_inst_per_frame": warp_inst * lanes / frames,
+                        "warp_inst_per_frame": warp_inst / frames,
+                        "issue_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "lanes": lanes, "source": note}
+            traffic[key] = {"dram_bytes_per_frame": (gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")) / frames}
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        json.dump(alu, open(os.path.join(root, "profiles", "alu.json"), "w"), indent=1)
+        json.dump(traffic, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
