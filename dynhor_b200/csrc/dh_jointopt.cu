@@ -782,6 +782,9 @@ __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long lon
 #ifndef DH_LISTS_GLOBAL
 #define DH_LISTS_GLOBAL 1   // 1: the backward reads the pixel lists from global memory through L1; 0: staged in smem
 #endif
+#ifndef DH_ALPHA_GLOBAL
+#define DH_ALPHA_GLOBAL 0   // 1 (list path): the backward reads the coverage bitmap from global memory through L1 instead of
+#endif                      // staging its 32 KB per CTA: smaller CTAs, more of them per SM
 constexpr int kNegThreads = 512;
 constexpr int kNLStart = 520;              // >= kMaxIS + 1, keeps the entries 16-byte aligned
 constexpr int kNLAxis = DH_LISTS_GLOBAL ? 32768 : 8192;  // u16 per (frame, axis)
@@ -1132,11 +1135,12 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     const int wpr = is >> 5, wprp = (S + 31) >> 5;
     BwdWarp* s_warp = reinterpret_cast<BwdWarp*>(smw);   // per-warp queues first (static smem is capped at 48 KB)
     BwdSpans* s_spans = reinterpret_cast<BwdSpans*>(smw + kBwdWarps * (sizeof(BwdWarp) / sizeof(uint32_t)));
-    uint32_t* s_alpha = smw + kBwdWarps * ((sizeof(BwdWarp) + (LISTS ? sizeof(BwdSpans) : 0)) / sizeof(uint32_t));
-    uint32_t* s_negT = s_alpha + is * wpr;                  // bitmap path
+    uint32_t* s_alpha_smem = smw + kBwdWarps * ((sizeof(BwdWarp) + (LISTS ? sizeof(BwdSpans) : 0)) / sizeof(uint32_t));
+    const uint32_t* s_alpha = (LISTS && DH_ALPHA_GLOBAL) ? s.alpha_bits + (size_t)blockIdx.y * is * wpr : s_alpha_smem;
+    uint32_t* s_negT = s_alpha_smem + is * wpr;             // bitmap path
     uint32_t* s_negp = s_negT + is * wpr;
 #if !DH_LISTS_GLOBAL
-    uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha + is * wpr);  // list path: 2 x (starts, entries)
+    uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha_smem + is * wpr);  // list path: 2 x (starts, entries)
 #endif
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -1188,8 +1192,9 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     if (LISTS) {
         // coverage bitmap + the two line lists (16-byte copies; only the entries in use)
         const uint4* ga4 = reinterpret_cast<const uint4*>(s.alpha_bits + (size_t)b * is * wpr);
-        uint4* sa4 = reinterpret_cast<uint4*>(s_alpha);
-        for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
+        uint4* sa4 = reinterpret_cast<uint4*>(s_alpha_smem);
+        if (!DH_ALPHA_GLOBAL)
+            for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
 #if DH_LISTS_GLOBAL
         nl.base = g_lists;   // the lists stay in global memory (L1-cached reads)
 #else
@@ -1207,7 +1212,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint32_t* ga = s.alpha_bits + (size_t)b * is * wpr;
         const uint32_t* gt = s.negT + (size_t)b * is * wpr;
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
-        for (int i = tid; i < is * wpr; i += kBwdThreads) { s_alpha[i] = ga[i]; s_negT[i] = gt[i]; }
+        for (int i = tid; i < is * wpr; i += kBwdThreads) { s_alpha_smem[i] = ga[i]; s_negT[i] = gt[i]; }
         for (int i = tid; i < S * wprp; i += kBwdThreads) s_negp[i] = gn[i];
         for (int i = tid; i < is; i += kBwdThreads) {
             s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
@@ -1809,7 +1814,8 @@ size_t bwd_smem_bytes(const dh_sil& s) {
 }
 size_t bwd_lists_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
-    return kBwdWarps * (sizeof(BwdWarp) + sizeof(BwdSpans)) + (size_t)(is * (is / 32)) * sizeof(uint32_t) +
+    return kBwdWarps * (sizeof(BwdWarp) + sizeof(BwdSpans)) +
+           (DH_ALPHA_GLOBAL ? 16 : (size_t)(is * (is / 32)) * sizeof(uint32_t)) +
            (DH_LISTS_GLOBAL ? 0 : (size_t)2 * kNLAxis * sizeof(uint16_t));
 }
 size_t neg_maps_smem_bytes(const dh_sil& s) {

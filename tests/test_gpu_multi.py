@@ -25,12 +25,14 @@ def _gpu_render_fn(vc, faces, K, size):
                  mode="silhouettes").cpu().numpy()
 
 
-def _worker(rank, world, port, seq, halo, q, scale_opt=False, balance="count", iters=10):
+def _worker(rank, world, port, seq, halo, q, scale_opt=False, balance="count", iters=10, no_p2p=False):
     import torch.distributed as dist
     from dynhor_b200 import synth
     from dynhor_b200.jointopt import joint_optimize
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    if no_p2p:
+        os.environ["DH_FORCE_NO_P2P"] = "1"   # pretend the devices cannot map each other's memory
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -49,7 +51,7 @@ def _worker(rank, world, port, seq, halo, q, scale_opt=False, balance="count", i
 
 @pytest.mark.parametrize("halo,scale_opt,balance,iters", [("p2p", False, "count", 10), ("nccl", False, "count", 10),
                                                            ("p2p", True, "probe", 10), ("nccl", True, "probe", 10),
-                                                           ("p2p", True, "probe", 70)])
+                                                           ("p2p", True, "probe", 70), ("p2p-unavailable", True, "probe", 10)])
 def test_two_gpu_sharded_equals_single_gpu(halo, scale_opt, balance, iters):
     """iters = 70: long enough for the mid-run re-partition (after 16 iterations the ranges are re-cut from the ranks'
     own clocks and frames change hands together with their Adam moments) -- still the single-GPU bits."""
@@ -72,7 +74,10 @@ def test_two_gpu_sharded_equals_single_gpu(halo, scale_opt, balance, iters):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, seq, halo, q, scale_opt, balance, iters)) for r in range(2)]
+    no_p2p = halo == "p2p-unavailable"    # halo="p2p" requested, no peer access: every rank falls back to the NCCL exchange
+    halo = "p2p" if no_p2p else halo
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, seq, halo, q, scale_opt, balance, iters, no_p2p))
+             for r in range(2)]
     for p in procs:
         p.start()
     rot2, tr2, evo2, scale2, bounds = q.get(timeout=300)
