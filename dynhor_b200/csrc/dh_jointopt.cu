@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kRasterThreads, DH_RASTER_MIN_CTAS)
 k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float* __restrict__ rend,
          int32_t* __restrict__ loss_counts) {
     extern __shared__ unsigned long long zbuf[];  // [kSH][is]
-    __shared__ uint32_t abits[kSH][kMaxIS / 32];
+    __shared__ __align__(16) uint32_t abits[kSH][kMaxIS / 32];
     __shared__ int red[3][kRasterThreads / 32];
     __shared__ int s_next[2];
     __shared__ uint32_t s_tilez[kMaxIS / 16];
@@ -388,7 +388,8 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     // a strip no face reaches (above / below the object: about a fifth of them) skips the z-buffer altogether
     const bool empty_strip = (bin_counts.x | bin_counts.y) == 0;
     if (!empty_strip) {
-        for (int i = tid; i < kSH * is; i += kRasterThreads) zbuf[i] = DH_ZKEY_EMPTY;
+        ulonglong2* z2 = reinterpret_cast<ulonglong2*>(zbuf);   // 16-byte stores: kSH * is is even, the strip is 16-byte aligned
+        for (int i = tid; i < kSH * is / 2; i += kRasterThreads) z2[i] = make_ulonglong2(DH_ZKEY_EMPTY, DH_ZKEY_EMPTY);
         for (int i = tid; i < is; i += kRasterThreads) s_ndc[i] = pix_to_ndc(i, is);
     }
     if (owned_smem)
@@ -595,7 +596,34 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             abits_g[i] = 0u;
         }
     }
-    for (int seg = warp; seg < kSH * wpr && !empty_strip; seg += kRasterWarps) {   // one warp = 32 consecutive pixels
+    if (!empty_strip && (wpr & 3) == 0) {
+        // one warp = 128 consecutive pixels of a row per trip, lane l taking pixels l, l + 32, l + 64, l + 96: four
+        // independent 8-byte z-buffer reads in flight, coalesced face-index stores, one ballot per coverage word
+        const int groups = wpr >> 2;
+        for (int seg = warp; seg < kSH * groups; seg += kRasterWarps) {
+            const int r = wpr_pow2 ? (seg >> (wpr_sh - 2)) : seg / groups, g4 = seg - r * groups;
+            const int i0 = r * is + (g4 << 7) + lane;
+            unsigned long long key[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) key[j] = zbuf[i0 + 32 * j];
+            uint32_t word[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool cov = key[j] != DH_ZKEY_EMPTY;
+                const int fn = cov ? (int32_t)((uint32_t)key[j] & ~kDeferBit) : -1;
+                fidx[i0 + 32 * j] = fn;
+                const int fn_left = __shfl_up_sync(0xffffffffu, fn, 1);
+                if (cov && (lane == 0 || fn_left != fn))
+                    atomicOr(owned_smem ? &s_owned[fn >> 5] : &g_owned[fn >> 5], 1u << (fn & 31));
+                word[j] = __ballot_sync(0xffffffffu, cov);
+            }
+            if (lane == 0) {
+                *reinterpret_cast<uint4*>(&abits[r][g4 << 2]) = make_uint4(word[0], word[1], word[2], word[3]);
+                *reinterpret_cast<uint4*>(&abits_g[r * wpr + (g4 << 2)]) = make_uint4(word[0], word[1], word[2], word[3]);
+            }
+        }
+    }
+    for (int seg = warp; seg < kSH * wpr && !empty_strip && (wpr & 3) != 0; seg += kRasterWarps) {   // narrow rasters
         const int r = wpr_pow2 ? (seg >> wpr_sh) : seg / wpr, cw = seg - r * wpr;
         const int i = r * is + (cw << 5) + lane;
         const unsigned long long key = zbuf[i];
@@ -647,7 +675,8 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             sse += k * k;
             inter += ref ? pop : 0;
             uni += 4 * ref + (keep ? pop : 0) - (ref ? pop : 0);
-            s.gpool[o] = gcoef * ((float)k * 0.5f);
+            // dL/drend = gcoef * (k / 2) is not materialised: the backward rebuilds it from the coverage bitmap and
+            // the two sign bitmaps below (grad_from_pop)
             const uint32_t pw = __ballot_sync(0xffffffffu, k > 0);
             const uint32_t nw = __ballot_sync(0xffffffffu, k < 0);
             if (lane == 0) {
@@ -1911,7 +1940,6 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
     s.alpha_bits += o * is * wpr;
     s.pos_pool += o * S * wprp;
     s.neg_pool += o * S * wprp;
-    s.gpool += o * S * S;
     s.gmax += o;
     s.owned += o * ((2 * F + 31) / 32);
     s.negT += o * is * wpr;
@@ -2035,7 +2063,7 @@ int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa,
     out13[4] = (int64_t)B * is * (is / 32) * 4;
     out13[5] = (int64_t)B * S * wprp * 4;
     out13[6] = out13[5];
-    out13[7] = (int64_t)B * S * S * 4;
+    out13[7] = 16;   // gpool: the fused path no longer materialises dL/drend, the API path reads the caller's grad_rend
     out13[10] = (int64_t)B * is * (is / 32) * 4;
     out13[11] = (int64_t)B * 2 * is * 2;
     out13[12] = (int64_t)B * 2 * kNLAxis * 2;

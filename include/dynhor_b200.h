@@ -62,7 +62,8 @@ typedef struct dh_sil {
     uint32_t* alpha_bits;              /* [B,is,is/32] coverage bitmap, rasteriser row order                     */
     uint32_t* pos_pool;                /* [B,S,ceil(S/32)] bitmap: dL/drend > 0                                  */
     uint32_t* neg_pool;                /* [B,S,ceil(S/32)] bitmap: dL/drend < 0                                  */
-    float* gpool;                      /* [B,S,S] dL/drend (fused path writes it; API path copies grad_rend in)  */
+    float* gpool;                      /* reserved (16 bytes): dL/drend is rebuilt from the bitmaps (fused path) or read   */
+                                       /* from the caller's grad_rend (dh_sil_backward); never materialised               */
     float* gmax;                       /* [B] max |dL/d(raster pixel)| per frame (scales the backward's fixed point) */
     uint32_t* owned;                   /* [B,ceil(2F/32)] bitmap: face fn owns at least one pixel of the frame       */
     uint32_t* negT;                    /* [B,is,is/32] column-major bitmap: pixel uncovered && dL/dpixel < 0         */
