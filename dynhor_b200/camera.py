@@ -56,28 +56,22 @@ def compute_transformation_persp(meshes, translations, rotations=None, intrinsic
 
 
 def get_K_crop_resize(K, boxes, crop_resize, invert_xy=False):
-    """utils/camera.py:84-130 (skew is not handled, like the reference)."""
+    """Intrinsics of the image cropped to `boxes` [n,4] (x0, y0, x1, y1) and resized to `crop_resize`: the closed
+    formula of utils/camera.py:84-130 (pixel centres at integer coordinates; no skew, like the reference), kept in
+    the reference's floating-point operation order so that K_roi -- an input of the bit-exact rasteriser -- comes out
+    identical.  Used for the ROI intrinsics of frames (pose_initializtion.py:275-277) and of template views (:217-219)."""
     assert K.shape[1:] == (3, 3)
     assert boxes.shape[1:] == (4,)
-    K = K.float()
-    boxes = boxes.float()
-    if invert_xy:
-        boxes = torch.stack([boxes[:, 1], boxes[:, 0], boxes[:, 3], boxes[:, 2]], 1)
+    K, boxes = K.float(), boxes.float()
+    x0, y0, x1, y1 = (boxes[:, [1, 0, 3, 2]] if invert_xy else boxes).unbind(1)
+    size = torch.tensor(crop_resize, dtype=torch.float)
+    out = {"x": max(size), "y": min(size)}
     new_K = K.clone()
-    crop_resize = torch.tensor(crop_resize, dtype=torch.float)
-    final_width, final_height = max(crop_resize), min(crop_resize)
-    crop_width = boxes[:, 2] - boxes[:, 0]
-    crop_height = boxes[:, 3] - boxes[:, 1]
-    crop_cj = (boxes[:, 0] + boxes[:, 2]) / 2
-    crop_ci = (boxes[:, 1] + boxes[:, 3]) / 2
-    cx = K[:, 0, 2] + (crop_width - 1) / 2 - crop_cj
-    cy = K[:, 1, 2] + (crop_height - 1) / 2 - crop_ci
-    center_x = (crop_width - 1) / 2
-    center_y = (crop_height - 1) / 2
-    scale_x = final_width / crop_width
-    scale_y = final_height / crop_height
-    new_K[:, 0, 0] = scale_x * K[:, 0, 0]
-    new_K[:, 1, 1] = scale_y * K[:, 1, 1]
-    new_K[:, 0, 2] = (final_width - 1) / 2 + scale_x * (cx - center_x)
-    new_K[:, 1, 2] = (final_height - 1) / 2 + scale_y * (cy - center_y)
+    for axis, lo, hi, row in (("x", x0, x1, 0), ("y", y0, y1, 1)):
+        extent = hi - lo
+        half = (extent - 1) / 2                                # the crop's centre pixel
+        shifted = K[:, row, 2] + half - (lo + hi) / 2          # principal point in crop coordinates
+        scale = out[axis] / extent
+        new_K[:, row, row] = scale * K[:, row, row]
+        new_K[:, row, 2] = (out[axis] - 1) / 2 + scale * (shifted - half)
     return new_K

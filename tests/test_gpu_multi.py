@@ -90,3 +90,47 @@ def test_two_gpu_sharded_equals_single_gpu(halo, scale_opt, balance, iters):
     assert bounds[0] == 0 and bounds[-1] == B and len(bounds) == 3 and (iters < 64 or bounds[1] == 7)
     assert np.allclose(evo1["loss"], evo2["loss"], rtol=1e-12)
     assert np.allclose(evo1["iou_object"], evo2["iou_object"], rtol=1e-12)
+
+
+def _dino_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from dynhor_b200 import synth
+    from dynhor_b200.dino_match import build_bank, dino_cos_topk, dino_topk_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        N, Fm, P, D, k = 300, 20, 24, 64, 5
+        d = synth.make_dino_features(N, Fm, P, D, seed=7, device="cuda")
+        fb = build_bank(d["frames"], d["masks"])
+        sizes = [170, 130]                                   # ragged template slices
+        a = sum(sizes[:rank])
+        tb_local = build_bank(d["templ"][a:a + sizes[rank]])
+        vals, idx = dino_topk_sharded(fb, tb_local, k, rank, world, sizes)
+        _, v_all, i_all = dino_cos_topk(fb, build_bank(d["templ"]), k)
+        if rank == 0:
+            q.put((bool(torch.equal(idx, i_all)), float((vals - v_all).abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_template_sharded_topk_equals_whole_bank():
+    """The reference-sized template bank does not have to live on one GPU: templates sharded over ranks, per-rank
+    top-k, one all_gather of the [Fm,k] lists, merge_topk == the top-k of the whole bank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = [ctx.Process(target=_dino_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same_idx, dv = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same_idx and dv < 1e-5
