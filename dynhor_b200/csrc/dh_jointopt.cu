@@ -381,6 +381,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     uint32_t* s_owned = reinterpret_cast<uint32_t*>(zbuf + kSH * is);
     RasterWarp* s_rw = reinterpret_cast<RasterWarp*>(s_owned + ((owned_smem ? owned_words : 0) + 3) / 4 * 4);
     float* s_ndc = reinterpret_cast<float*>(s_rw + kRasterWarps);   // NDC coordinate of every pixel centre [is]
+    int8_t* s_mask = reinterpret_cast<int8_t*>(s_ndc + is);         // the strip's target-mask cells [cell rows][S]
     RasterWarp& RW = s_rw[threadIdx.x >> 5];
     uint32_t* g_owned = s.owned + (size_t)b * owned_words;
     // both passes' entry counts, requested before the z-buffer clear so that their latency is hidden
@@ -402,25 +403,20 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     const float4* P = reinterpret_cast<const float4*>(s.proj) + (size_t)b * s.V;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // the target-mask cells this thread scores in the epilogue, fetched now so that their latency hides behind the
-    // rasterisation (same cell order as epilogue 2)
-    constexpr int kMaskPre = 6;
-    int m_pre[kMaskPre];   // one register per epilogue iteration: nothing consumes the loads before the epilogue
-#pragma unroll
-    for (int k = 0; k < kMaskPre; k++) m_pre[k] = 0;
+    // The target-mask cells the epilogue scores (one contiguous S-byte row per cell row of the strip) are copied into
+    // shared memory with cp.async: the copies run behind the rasterisation and tie up no registers (round 1 held them
+    // in six registers per thread; the loads' DRAM latency -- the masks are long evicted from L2 by the time an
+    // iteration comes back to them -- then stalled every warp at kernel start, 7.5 % of the kernel's samples).
     if (FUSED) {
-        const int S_ = s.S, wprp_ = (S_ + 31) >> 5, rows_ = s.aa ? kSH / 2 : kSH;
-        const int sh_ = 31 - __clz(wprp_);
-        const bool pow2_ = (wprp_ & (wprp_ - 1)) == 0;   // S = 256: 8 words per row, no integer division
-#pragma unroll
-        for (int k = 0; k < kMaskPre; k++) {
-            const int seg = warp + k * kRasterWarps;
-            if (seg < rows_ * wprp_) {
-                const int ly = pow2_ ? (seg >> sh_) : seg / wprp_, x = ((seg - ly * wprp_) << 5) + lane;
-                const int yo = s.aa ? ((is - 1 - (row0 + 2 * ly)) >> 1) : (is - 1 - (row0 + ly));
-                m_pre[k] = mask_tri[((size_t)b * S_ + yo) * S_ + x];
-            }
+        const int S_ = s.S, rows_ = s.aa ? kSH / 2 : kSH, per_row = S_ >> 4;   // 16-byte pieces per row
+        for (int i = tid; i < rows_ * per_row; i += kRasterThreads) {
+            const int ly = i / per_row, piece = i - ly * per_row;
+            const int yo = s.aa ? ((is - 1 - (row0 + 2 * ly)) >> 1) : (is - 1 - (row0 + ly));
+            const int8_t* src = mask_tri + ((size_t)b * S_ + yo) * S_ + (piece << 4);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_mask + ly * S_ + (piece << 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // Two passes (given windings, then reversed windings), warp-synchronous batches of 32 bin entries handed out
     // dynamically.  Per batch: (1) lane = face: set-up; (2) lane = (face, row): analytic x-span of the row, then
@@ -654,7 +650,11 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
     int sse = 0, inter = 0, uni = 0;
     const int wprp_sh = 31 - __clz(wprp);
     const bool wprp_pow2 = (wprp & (wprp - 1)) == 0;
-    auto score_cells = [&](int seg, int m) {   // one warp = 32 consecutive cells of a row; m: the lane's mask cell
+    if (FUSED) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();   // every thread's mask copies have landed
+    }
+    auto score_cells = [&](int seg) {   // one warp = 32 consecutive cells of a row
         const int ly = wprp_pow2 ? (seg >> wprp_sh) : seg / wprp, x = ((seg - ly * wprp) << 5) + lane;
         int pop, yo;
         if (s.aa) {
@@ -669,7 +669,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
         }
         const size_t o = ((size_t)b * S + yo) * S + x;
         if (FUSED) {
-            if (m == 2) m = mask_tri[o];   // not prefetched
+            const int m = s_mask[ly * S + x];
             const int keep = m >= 0, ref = m > 0;
             const int k = keep ? pop - 4 * ref : 0;  // 4 * (image - ref)
             sse += k * k;
@@ -687,10 +687,7 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
             rend[o] = (float)pop * 0.25f;
         }
     };
-#pragma unroll
-    for (int k = 0; k < kMaskPre; k++)
-        if (warp + k * kRasterWarps < cell_rows * wprp) score_cells(warp + k * kRasterWarps, m_pre[k]);
-    for (int seg = warp + kMaskPre * kRasterWarps; seg < cell_rows * wprp; seg += kRasterWarps) score_cells(seg, 2);
+    for (int seg = warp; seg < cell_rows * wprp; seg += kRasterWarps) score_cells(seg);
     if (FUSED) {
         for (int o = 16; o > 0; o >>= 1) {
             sse += __shfl_xor_sync(0xffffffffu, sse, o);
@@ -1829,7 +1826,8 @@ size_t raster_smem_bytes(const dh_sil& s) {  // z-buffer strip + (small) face-ow
     const int words = (2 * s.F + 31) / 32;
     return (size_t)kSH * raster_size(s) * sizeof(unsigned long long) +
            (size_t)(((words <= kOwnedSmemWords ? words : 0) + 3) / 4 * 4) * sizeof(uint32_t) +
-           (size_t)kRasterWarps * sizeof(RasterWarp) + (size_t)raster_size(s) * sizeof(float);
+           (size_t)kRasterWarps * sizeof(RasterWarp) + (size_t)raster_size(s) * sizeof(float) +
+           (size_t)(s.aa ? kSH / 2 : kSH) * s.S;   // + the strip's target-mask cells
 }
 
 // pixels per frame the list path takes (dh_tune_set knob 0 lowers it: the tests force the bitmap path with it)
