@@ -430,23 +430,28 @@ def run_ours(args):
     kw = dict(objvertices=seq["verts"], objfaces=faces_b, loss_weights=lw, lr=LR, board=None, halo=args.halo,
               balance=args.balance)
     joint_optimize(params, num_iterations=2, **kw)
-    barrier()
-    t0 = time.perf_counter()
-    model2, evo = joint_optimize(params, num_iterations=e2e_iters, **kw)
-    rot_h = model2.rotations_object.detach().cpu()
-    tr_h = model2.translations_object.detach().cpu()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    # the call is one shot of ~45 ms of which several ms are host work (uploads, launches): timed args.e2e_reps times
+    # from the same host buffers, the MEDIAN is reported (every repetition is listed in seconds_all)
+    dts = []
+    for _ in range(max(1, args.e2e_reps)):
+        barrier()
+        t0 = time.perf_counter()
+        model2, evo = joint_optimize(params, num_iterations=e2e_iters, **kw)
+        rot_h = model2.rotations_object.detach().cpu()
+        tr_h = model2.translations_object.detach().cpu()
+        torch.cuda.synchronize()
+        dts.append(time.perf_counter() - t0)
     own = model2.frame_shard
     h2d = nbytes(params[own.start:own.stop]) + seq["verts"].nbytes + seq["faces"].astype(np.int32).nbytes
     d2h = rot_h.numel() * 4 + tr_h.numel() * 4 + 4 * 8 * e2e_iters
-    dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    dt_t = torch.tensor(dts, device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-    dt = float(dt_t.item())
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)      # per repetition: the slowest rank
+    dts = [float(x) for x in dt_t.cpu()]
+    dt = float(np.median(dts))
     e2e = {"value": B_total * e2e_iters / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
            "d2h_bytes_per_step": d2h / e2e_iters, "iterations": e2e_iters, "seconds": dt,
-           "final_loss": evo["loss"][-1]}
+           "seconds_all": [round(x, 5) for x in dts], "final_loss": evo["loss"][-1]}
     if getattr(model2, "timing", None):     # DH_TIMING=1: synchronised phase times of this rank's call (diagnostics)
         e2e["phases_ms"] = {k: round(v, 2) for k, v in model2.timing}
 
@@ -774,6 +779,7 @@ def main():
     ap.add_argument("--dino-templates", type=int, default=1000, help="--workload dino: templates (reference: 6000)")
     ap.add_argument("--dino-dim", type=int, default=384, help="--workload dino: feature channels (reference ViT-B: 768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-reps", type=int, default=3, help="repetitions of the end-to-end call (median reported)")
     ap.add_argument("--mesh", default=MESH, choices=["uv50x100", "uv100x200"],
                     help="uv100x200 = the 20k-vertex mesh of BASELINE configs[2]")
     ap.add_argument("--camera", default=f"{H}x{W}", help="full-frame camera HxW (configs[2]: 1080x1920)")

@@ -90,6 +90,7 @@ SIGNATURES = {
     "dh_dev_alloc": (c_i, [ctypes.POINTER(c_p), c_l]),
     "dh_dev_free": (c_i, [c_p]),
     "dh_memcpy_d2d": (c_i, [c_p, c_p, c_l, c_p]),
+    "dh_upload_rows": (c_i, [c_p, ctypes.POINTER(c_p), c_l, c_i, c_p]),
     "dh_ipc_export": (c_i, [c_p, c_p]),
     "dh_ipc_open": (c_i, [c_p, ctypes.POINTER(c_p)]),
     "dh_ipc_close": (c_i, [c_p]),

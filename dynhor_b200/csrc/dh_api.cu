@@ -1,6 +1,8 @@
 // dh_api.cu -- version / error / device queries of libdynhor_b200.so
 #include <string.h>
 
+#include <vector>
+
 #include "dh_common.h"
 
 namespace dh {
@@ -53,6 +55,34 @@ int dh_dev_free(void* ptr) {
 int dh_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
     DH_REQUIRE(dst && src && bytes > 0, "bad arguments");
     DH_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return DH_OK;
+}
+
+int dh_upload_rows(void* dst, const void* const* src_rows_host, int64_t row_bytes, int32_t n, void* stream) {
+    DH_REQUIRE(dst && src_rows_host && row_bytes > 0 && n > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* d = static_cast<char*>(dst);
+    // one driver call for the whole batch where the runtime has it (CUDA >= 12.8; not on the legacy default stream)
+    static thread_local int batch_ok = 1;
+    if (batch_ok && st != nullptr && n > 1) {
+        std::vector<void*> dsts(n), srcs(n);
+        std::vector<size_t> sizes(n, (size_t)row_bytes);
+        for (int i = 0; i < n; i++) {
+            dsts[i] = d + (size_t)i * row_bytes;
+            srcs[i] = const_cast<void*>(src_rows_host[i]);
+        }
+        cudaMemcpyAttributes attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t attr_idx = 0, fail_idx = 0;
+        cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), (size_t)n, &attr, &attr_idx, 1,
+                                             &fail_idx, st);
+        if (e == cudaSuccess) return DH_OK;
+        cudaGetLastError();   // not supported here: remember, and copy row by row
+        batch_ok = 0;
+    }
+    for (int i = 0; i < n; i++)
+        DH_CUDA(cudaMemcpyAsync(d + (size_t)i * row_bytes, src_rows_host[i], (size_t)row_bytes, cudaMemcpyHostToDevice, st));
     return DH_OK;
 }
 

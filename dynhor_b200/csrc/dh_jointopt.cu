@@ -748,6 +748,10 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_FAST_COEF
 #define DH_FAST_COEF 1
 #endif
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
 // one face-index read of the ownership test: random 4-byte reads of a 1 MB map, no reuse
 __device__ __forceinline__ int load_fidx(const int32_t* p) {
 #if DH_FIDX_NOALLOC
@@ -798,7 +802,7 @@ __device__ __forceinline__ void atomic_add_fixed(unsigned long long* a, long lon
 
 // Frame-level maps the backward needs, built once per frame instead of once per backward CTA:
 //   negT      column-major bitmap of "uncovered && dL/dpixel < 0" (32x32 bit-block transposes through ballots)
-//   row_rng   first / last set pixel of every row of that bitmap
+//   row_rng   first / last set pixel of every row and of every column of that bitmap
 //   neg_lists (fused path) the same pixels as two compressed line lists -- one entry per pixel, grouped by row
 //             (axis 1) and by column (axis 0), ascending along the line -- so that an out scan walks the handful of
 //             contributing pixels of its line instead of searching bitmap words.  Per (frame, axis): kNLStart u16
@@ -923,10 +927,9 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, const int32_t* __restr
                     cnt += __popc(bits);
                 }
             }
-            if (axis == 1) {
-                s.row_rng[((size_t)b * 2 + 0) * is + tid] = (int16_t)lo;
-                s.row_rng[((size_t)b * 2 + 1) * is + tid] = (int16_t)hi;
-            }
+            // [b][0..1] rows, [b][2..3] columns: every backward CTA of the frame copies them instead of deriving them
+            s.row_rng[((size_t)b * 4 + (axis ? 0 : 2)) * is + tid] = (int16_t)lo;
+            s.row_rng[((size_t)b * 4 + (axis ? 1 : 3)) * is + tid] = (int16_t)hi;
         }
         if (!build_lists) continue;
         int total;
@@ -1146,13 +1149,13 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
 // LISTS (fused path only): out scans read the per-line pixel lists of k_neg_maps; frames whose lists overflowed
 //        are left to the bitmap kernel, which is launched behind it with only_overflow = 1.
 template <bool FUSED, bool LISTS>
-__global__ void __launch_bounds__(kBwdThreads, DH_BWD_MIN_CTAS)
-k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
-           const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
-           float* __restrict__ grad_verts, int nchunks, float gcoef_all, int only_overflow,
-           const float* __restrict__ frame_coef) {
+__device__ __forceinline__ void
+bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
+          const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
+          float* __restrict__ grad_verts, int nchunks, float gcoef_all, const float* __restrict__ frame_coef,
+          const int b) {
     extern __shared__ __align__(16) uint32_t smw[];
-    __shared__ int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
+    __shared__ __align__(16) int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
     __shared__ float s_bsum[2 * kChunkFaces / 32 + kBwdWarps][13];  // pose-gradient partial sums, one row per batch
     __shared__ int s_wcount[kBwdWarps], s_woff[kBwdWarps + 1];
@@ -1162,19 +1165,30 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     BwdWarp* s_warp = reinterpret_cast<BwdWarp*>(smw);   // per-warp queues first (static smem is capped at 48 KB)
     BwdSpans* s_spans = reinterpret_cast<BwdSpans*>(smw + kBwdWarps * (sizeof(BwdWarp) / sizeof(uint32_t)));
     uint32_t* s_alpha_smem = smw + kBwdWarps * ((sizeof(BwdWarp) + (LISTS ? sizeof(BwdSpans) : 0)) / sizeof(uint32_t));
-    const uint32_t* s_alpha = (LISTS && DH_ALPHA_GLOBAL) ? s.alpha_bits + (size_t)blockIdx.y * is * wpr : s_alpha_smem;
+    const uint32_t* s_alpha = (LISTS && DH_ALPHA_GLOBAL) ? s.alpha_bits + (size_t)b * is * wpr : s_alpha_smem;
     uint32_t* s_negT = s_alpha_smem + is * wpr;             // bitmap path
     uint32_t* s_negp = s_negT + is * wpr;
 #if !DH_LISTS_GLOBAL
     uint16_t* s_lists = reinterpret_cast<uint16_t*>(s_alpha_smem + is * wpr);  // list path: 2 x (starts, entries)
 #endif
-    const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int chunk = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint16_t* g_lists = s.neg_lists + (size_t)b * 2 * kNLAxis;
-    if (LISTS || only_overflow) {
-        const bool over = g_lists[is] == kNLOverflow;
-        if (over == LISTS) return;
+    // ---- stage the frame's maps (built per frame by k_raster / k_neg_maps) with 16-byte asynchronous copies that run
+    //      behind the item compaction below: first / last wanted pixel of every row and column, and (list path) the
+    //      coverage bitmap
+    {
+        const int per_row = is / 8;     // uint4 per range row
+        for (int i = tid; i < 4 * per_row; i += kBwdThreads) {
+            const int k = i / per_row, j = i - k * per_row;
+            cp_async16(&s_rng[k][8 * j], s.row_rng + ((size_t)b * 4 + k) * is + 8 * j);
+        }
+        if (LISTS && !DH_ALPHA_GLOBAL) {
+            const uint4* ga4 = reinterpret_cast<const uint4*>(s.alpha_bits + (size_t)b * is * wpr);
+            uint4* sa4 = reinterpret_cast<uint4*>(s_alpha_smem);
+            for (int i = tid; i < is * wpr / 4; i += kBwdThreads) cp_async16(sa4 + i, ga4 + i);
+        }
     }
     const float gmax = s.gmax[b];
     // dL/dpixel coefficients: one number for the masked-L2 loss; per frame (wanted / unwanted pixels) for the IoU loss
@@ -1213,14 +1227,8 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
     if (lane == 0) s_wcount[warp] = wcount;
     if (tid == 0) s_next_batch = 0;
 
-    // ---- stage the frame's bitmaps (built per frame by k_raster / k_neg_maps)
     NegLists nl;
     if (LISTS) {
-        // coverage bitmap + the two line lists (16-byte copies; only the entries in use)
-        const uint4* ga4 = reinterpret_cast<const uint4*>(s.alpha_bits + (size_t)b * is * wpr);
-        uint4* sa4 = reinterpret_cast<uint4*>(s_alpha_smem);
-        if (!DH_ALPHA_GLOBAL)
-            for (int i = tid; i < is * wpr / 4; i += kBwdThreads) sa4[i] = ga4[i];
 #if DH_LISTS_GLOBAL
         nl.base = g_lists;   // the lists stay in global memory (L1-cached reads)
 #else
@@ -1240,10 +1248,6 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         const uint32_t* gn = s.neg_pool + (size_t)b * S * wprp;
         for (int i = tid; i < is * wpr; i += kBwdThreads) { s_alpha_smem[i] = ga[i]; s_negT[i] = gt[i]; }
         for (int i = tid; i < S * wprp; i += kBwdThreads) s_negp[i] = gn[i];
-        for (int i = tid; i < is; i += kBwdThreads) {
-            s_rng[0][i] = s.row_rng[((size_t)b * 2 + 0) * is + i];
-            s_rng[1][i] = s.row_rng[((size_t)b * 2 + 1) * is + i];
-        }
         nl.base = nullptr;
     }
     __syncthreads();
@@ -1252,30 +1256,7 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
         for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
         s_woff[kBwdWarps] = o;
     }
-    if (LISTS) {
-        for (int i = tid; i < 2 * is; i += kBwdThreads) {  // first / last listed pixel of every row and column
-            const int axis = i >= is, line = axis ? i - is : i;   // axis of the LIST: 0 = columns, 1 = rows
-            const uint16_t* L = nl.start(axis);
-            const int ls = L[line], le = L[line + 1];
-            const int lo = ls < le ? (int)(L[kNLStart + ls] & 1023u) : is;
-            const int hi = ls < le ? (int)(L[kNLStart + le - 1] & 1023u) : -1;
-            s_rng[axis ? 0 : 2][line] = (int16_t)lo;
-            s_rng[axis ? 1 : 3][line] = (int16_t)hi;
-        }
-    } else {
-        for (int c = tid; c < is; c += kBwdThreads) {  // first / last set pixel of every column
-            int lo = is, hi = -1;
-            for (int w = 0; w < wpr; w++) {
-                const uint32_t bits = s_negT[c * wpr + w];
-                if (bits) {
-                    if (lo == is) lo = (w << 5) + ctz32(bits);
-                    hi = (w << 5) + 31 - __clz((int)bits);
-                }
-            }
-            s_rng[2][c] = (int16_t)lo;
-            s_rng[3][c] = (int16_t)hi;
-        }
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (gmax > 0.0f) {
         int pos = s_woff[warp];
@@ -1518,6 +1499,33 @@ k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __r
                 for (int k = 0; k < n_batches; k++) t += s_bsum[k][tid];
             partials[((size_t)b * nchunks + chunk) * 16 + tid] = t;
         }
+    }
+}
+
+// Grid (chunks, frames).  only_overflow (the bitmap kernel launched behind the list kernel): a small grid whose rows
+// walk the frames and work only on those whose lists overflowed -- normally none, and the launch ends after B / gridDim.y
+// flag reads per CTA instead of starting B x chunks CTAs that return at once.
+template <bool FUSED, bool LISTS>
+__global__ void __launch_bounds__(kBwdThreads, DH_BWD_MIN_CTAS)
+k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
+           const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
+           float* __restrict__ grad_verts, int nchunks, float gcoef_all, int only_overflow,
+           const float* __restrict__ frame_coef) {
+    const int is = raster_size(s);
+    if (LISTS) {
+        const int b = blockIdx.y;
+        if (s.neg_lists[(size_t)b * 2 * kNLAxis + is] == kNLOverflow) return;
+        bwd_frame<FUSED, LISTS>(s, verts_src, Rmat, trans, scale, partials, grad_verts, nchunks, gcoef_all, frame_coef, b);
+    } else if (only_overflow) {
+        for (int b = blockIdx.y; b < s.B; b += gridDim.y) {
+            if (s.neg_lists[(size_t)b * 2 * kNLAxis + is] != kNLOverflow) continue;   // (uniform over the CTA)
+            bwd_frame<FUSED, LISTS>(s, verts_src, Rmat, trans, scale, partials, grad_verts, nchunks, gcoef_all, frame_coef,
+                                    b);
+            __syncthreads();   // the next frame reuses the shared arrays
+        }
+    } else {
+        bwd_frame<FUSED, LISTS>(s, verts_src, Rmat, trans, scale, partials, grad_verts, nchunks, gcoef_all, frame_coef,
+                                blockIdx.y);
     }
 }
 
@@ -1868,6 +1876,16 @@ int launch_forward_common(const dh_sil& s, cudaStream_t st) {
 
 // Optional per-kernel timing: 9 events bracket the kernels of one iteration (dh_jointopt_profile).
 struct IterEvents { cudaEvent_t ev[9]; };
+// DH_CORR_FORK=0 in the environment keeps the correspondence kernel in line with the others (measurement knob)
+// 0 in line, 1 branch after k_pose_prep, 2 branch after k_raster, 3 the same at low priority (DH_CORR_FORK overrides).
+// Measured (300 frames, profiles/r2_jointopt_ncu.md): beside k_neg_maps a 10k-correspondence launch is free (-0.019 ms
+// per iteration); a 50k one outlasts k_neg_maps, takes shared memory from the first wave of backward CTAs and costs
+// +0.05 ms, so it stays in line.
+int corr_fork_mode(int C) {
+    const char* e = getenv("DH_CORR_FORK");
+    if (e != nullptr && e[0] >= '0' && e[0] <= '3') return e[0] - '0';
+    return C <= 20000 ? 2 : 0;
+}
 #define DH_REC(i) do { if (evs) cudaEventRecord(evs->ev[i], st); } while (0)
 
 // The silhouette term's kernels of one iteration for the plan's frames: projection, binning, raster (+ fused loss
@@ -1915,7 +1933,7 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
         s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0, fcoef);
     DH_LAUNCH_OK("k_backward<lists>");
     // frames with more contributing pixels than the lists hold (only these CTAs do any work)
-    k_backward<true, false><<<dim3(p.nchunks, B), kBwdThreads, sb, st>>>(
+    k_backward<true, false><<<dim3(p.nchunks, min(B, 64)), kBwdThreads, sb, st>>>(
         s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1, fcoef);
     DH_LAUNCH_OK("k_backward<bitmaps>");
     return DH_OK;
@@ -1941,7 +1959,7 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
     s.gmax += o;
     s.owned += o * ((2 * F + 31) / 32);
     s.negT += o * is * wpr;
-    s.row_rng += o * 2 * is;
+    s.row_rng += o * 4 * is;
     s.neg_lists += o * 2 * kNLAxis;
     q.mask_tri += o * S * S;
     q.rot6d += o * 6;
@@ -1954,8 +1972,13 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
     return q;
 }
 
+// A second stream + two events: the correspondence kernel (HBM-bound, reads only the poses) runs as its own branch
+// beside the silhouette kernels (issue-bound) between k_pose_prep and k_pose_update.  Used when the iteration is
+// captured into a graph; the plain-stream paths (profile, eval, grads, use_graph = 0) stay serial.
+struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join; bool after_raster; };
+
 int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
-                     cudaStream_t st, IterEvents* evs = nullptr) {
+                     cudaStream_t st, IterEvents* evs = nullptr, const SideBranch* side = nullptr) {
     const dh_sil& s = p.sil;
     const int B = s.B;
     const bool with_sil = p.lw_sil > 0.0;
@@ -1964,19 +1987,40 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
     DH_LAUNCH_OK("k_pose_prep");
     DH_REC(1);
     const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
-    if (with_corr) {
+    const bool forked = with_corr && with_sil && side != nullptr;
+    auto corr_launch = [&](bool fork) -> int {
+        cudaStream_t cs = st;
+        if (fork) {
+            DH_CUDA(cudaEventRecord(side->fork, st));
+            DH_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            cs = side->stream;
+        }
         const int rc = launch_corr(p.corr.records, B, p.corr.C, p.Rmat, p.trans, p.scale, s.K, s.S, p.corr.delta,
-                                   p.corr.partials, p.corr.nslots, st);
+                                   p.corr.partials, p.corr.nslots, cs);
+        if (rc) return rc;
+        if (fork) DH_CUDA(cudaEventRecord(side->join, cs));
+        return DH_OK;
+    };
+    if (with_corr && !(forked && side->after_raster)) {
+        const int rc = corr_launch(forked);
         if (rc) return rc;
     }
     DH_REC(8);
     if (with_sil) {
-        const int rc = launch_sil_kernels(p, mode == 2, st, evs);
+        int rc;
+        if (forked && side->after_raster) {   // the branch starts beside k_neg_maps, which leaves most of the machine idle
+            rc = launch_sil_kernels(p, mode == 2, st, evs, 1);
+            if (!rc) rc = corr_launch(true);
+            if (!rc) rc = launch_sil_kernels(p, mode == 2, st, evs, 2);
+        } else {
+            rc = launch_sil_kernels(p, mode == 2, st, evs);
+        }
         if (rc) return rc;
     } else {
         DH_REC(2); DH_REC(3); DH_REC(4);
     }
     DH_REC(5);
+    if (forked) DH_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
     DH_LAUNCH_OK("k_pose_update");
     DH_REC(6);
@@ -2063,7 +2107,7 @@ int dh_sil_scratch_bytes(int32_t B, int32_t V, int32_t F, int32_t S, int32_t aa,
     out13[6] = out13[5];
     out13[7] = 16;   // gpool: the fused path no longer materialises dL/drend, the API path reads the caller's grad_rend
     out13[10] = (int64_t)B * is * (is / 32) * 4;
-    out13[11] = (int64_t)B * 2 * is * 2;
+    out13[11] = (int64_t)B * 4 * is * 2;
     out13[12] = (int64_t)B * 2 * kNLAxis * 2;
     return DH_OK;
 }
@@ -2220,10 +2264,26 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         if (rc) return rc;
         cudaStream_t cs;
         DH_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        SideBranch side;
+        const int fork_mode = corr_fork_mode(p->corr.C);
+        const bool fork_corr = fork_mode != 0;
+        side.after_raster = fork_mode >= 2;
+        if (fork_corr) {
+            int pr_lo = 0, pr_hi = 0;
+            DH_CUDA(cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi));
+            DH_CUDA(cudaStreamCreateWithPriority(&side.stream, cudaStreamNonBlocking, fork_mode == 3 ? pr_lo : 0));
+            DH_CUDA(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+            DH_CUDA(cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming));
+        }
         cudaGraph_t graph = nullptr;
         DH_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, cs);
+        rc = launch_iteration(*p, 0, nullptr, nullptr, nullptr, cs, nullptr, fork_corr ? &side : nullptr);
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (fork_corr) {
+            cudaEventDestroy(side.fork);
+            cudaEventDestroy(side.join);
+            cudaStreamDestroy(side.stream);
+        }
         if (rc || ce != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
             cudaStreamDestroy(cs);

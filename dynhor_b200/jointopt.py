@@ -13,6 +13,7 @@ per-step host synchronisation) and fills `loss_evolution` / `board` after the lo
 """
 import ctypes
 import os
+import threading
 from collections import defaultdict
 
 import numpy as np
@@ -423,8 +424,8 @@ def _stack_frames(frames, key, pick=None, dtype=None):
         out = torch.cat(ts)
     elif t0.is_pinned() and t0.numel() * t0.element_size() >= 65536:
         out = torch.empty((sum(int(t.shape[0]) for t in ts),) + tuple(t0.shape[1:]), dtype=t0.dtype, device="cuda")
-        if all(t.shape[0] == 1 for t in ts):
-            torch._foreach_copy_(list(out.split(1)), ts, non_blocking=True)   # one dispatch for all the copies
+        if all(t.shape == t0.shape and t.is_contiguous() and t.dtype == t0.dtype for t in ts) and t0.shape[0] == 1:
+            _upload_rows(out, ts)      # one batched driver call for all the frames
         else:
             row = 0
             for t in ts:
@@ -436,6 +437,27 @@ def _stack_frames(frames, key, pick=None, dtype=None):
         torch.cat(ts, out=stage)
         out = stage.cuda(non_blocking=True)
     return out if dtype is None or out.dtype == dtype else out.to(dtype)
+
+
+_upload_stream = {}
+
+
+def _upload_rows(out, rows):
+    """rows: equal-shaped contiguous pinned host tensors -> out[i] (dh_upload_rows: one cudaMemcpyBatchAsync instead of
+    len(rows) copy calls).  Batched copies need a real stream, torch's default one is the legacy stream: they go through
+    a per-device side stream the current stream then waits for."""
+    dev = out.device
+    cur = torch.cuda.current_stream(dev)
+    up = _upload_stream.get(dev.index)
+    if up is None:
+        up = _upload_stream[dev.index] = torch.cuda.Stream(dev)
+    up.wait_stream(cur)                       # `out` may reuse memory the current stream is still working on
+    n = len(rows)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows])
+    _lib.check(_lib.load().dh_upload_rows(ctypes.c_void_p(out.data_ptr()), ptrs, rows[0].numel() * rows[0].element_size(),
+                                          n, ctypes.c_void_p(up.cuda_stream)), "dh_upload_rows")
+    out.record_stream(up)
+    cur.wait_stream(up)
 
 
 class _SharedFaces:
@@ -452,8 +474,12 @@ class _SharedFaces:
         self.first = one
         self.dev = one.to(torch.int32).contiguous().cuda()
         self.checked = []
+        self.pending, self.bad = [], False
 
     def check(self, start, stop):
+        """Starts the comparison of rows [start, stop) on a worker thread (72 MB of host reads at 300 frames: it runs
+        beside the uploads and the kernel launches); `join` -- called before joint_optimize returns anything -- raises
+        if a row differed."""
         if self.rows is None:
             return
         stop = min(stop, self.rows.shape[0])
@@ -464,10 +490,23 @@ class _SharedFaces:
                 stop = a
         if start >= stop:
             return
-        if not torch.equal(self.rows[start:stop], self.first.expand(stop - start, -1, -1)):
+        self.checked.append((start, stop))
+
+        def work():
+            if not torch.equal(self.rows[start:stop], self.first.expand(stop - start, -1, -1)):
+                self.bad = True
+
+        t = threading.Thread(target=work, daemon=True)
+        t.start()
+        self.pending.append(t)
+
+    def join(self):
+        for t in self.pending:
+            t.join()
+        self.pending = []
+        if self.bad:
             raise NotImplementedError("dynhor_b200 renders one mesh topology for all frames (run.py:158 stacks "
                                       "identical faces); per-frame face lists are not supported")
-        self.checked.append((start, stop))
 
 
 def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weights=None, num_iterations=400,
@@ -525,7 +564,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
         faces.check(sh.start, sh.stop)
         trans = _stack_frames(local, "translations")
         rots = _stack_frames(local, "rotations")
-        K = _stack_frames(local, "K_roi", pick=lambda t: t[:, 0])
+        K = _stack_frames(local, "K_roi")[:, 0]
         m0, s0 = reuse if reuse is not None else (None, None)
         old_masks = None if m0 is None else m0.ref_mask_object + m0.keep_mask_object - 1.0
         masks = frames_on_device(sh, "target_masks", (old_masks, s0), dtype=torch.float32)
@@ -620,6 +659,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
                 fused, model, shard = rebalance(fused, model, shard, done)
                 mark("rebalance")
         mark("launched")
+        faces.join()     # the face-list identity check that ran beside the launches; raises before anything is returned
         loss_evolution = fused.history()  # the only host synchronisation of the loop
         mark("loop")
         if loop is not None:

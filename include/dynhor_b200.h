@@ -67,7 +67,7 @@ typedef struct dh_sil {
     float* gmax;                       /* [B] max |dL/d(raster pixel)| per frame (scales the backward's fixed point) */
     uint32_t* owned;                   /* [B,ceil(2F/32)] bitmap: face fn owns at least one pixel of the frame       */
     uint32_t* negT;                    /* [B,is,is/32] column-major bitmap: pixel uncovered && dL/dpixel < 0         */
-    int16_t* row_rng;                  /* [B,2,is] first / last set pixel of every row of that bitmap              */
+    int16_t* row_rng;                  /* [B,4,is] first / last set pixel of every row, then of every column       */
     uint16_t* neg_lists;               /* [B,2,32768] the same pixels as per-column / per-row lists (fused backward) */
 } dh_sil;
 
@@ -256,6 +256,11 @@ int dh_jointopt_probe(const dh_jointopt* p, int32_t nblocks, float* ms_out_host,
 int dh_dev_alloc(void** ptr, int64_t bytes);
 int dh_dev_free(void* ptr);
 int dh_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+/* n host rows of row_bytes each (src_rows_host: n HOST pointers, pinned memory for an asynchronous copy) -> the
+ * contiguous device rows dst + i * row_bytes, as ONE batched driver call where the runtime offers it.  Replaces the
+ * per-frame `.cuda()` calls of the reference's loaders (jointopt.py:104-123 concatenates per-frame tensors that
+ * pose_initializtion.py:460-471 left on the device one by one). */
+int dh_upload_rows(void* dst, const void* const* src_rows_host, int64_t row_bytes, int32_t n, void* stream);
 /* CUDA IPC: export / open / close a dh_dev_alloc allocation (handle = 64 bytes of HOST memory) */
 int dh_ipc_export(const void* ptr, void* handle64_host);
 int dh_ipc_open(const void* handle64_host, void** ptr);
