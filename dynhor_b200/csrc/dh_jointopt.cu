@@ -739,6 +739,15 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_BWD_MIN_CTAS
 #define DH_BWD_MIN_CTAS 2
 #endif
+#ifndef DH_GUIDED
+#define DH_GUIDED 1      // 1: batch sizes shrink towards the end of the chunk (guided schedule); 0: DH_EVEN_LAST's
+#endif
+#ifndef DH_GUIDE_MIN
+#define DH_GUIDE_MIN 10  // smallest batch of the guided schedule (6 / 8 / 12 / 16 measured: 1.02 / 1.03 / 1.01 / 1.03 ms)
+#endif
+#ifndef DH_GUIDE_DIV
+#define DH_GUIDE_DIV 1   // next batch = remaining items / (warps * DH_GUIDE_DIV), at most 32
+#endif
 #ifndef DH_EVEN_LAST
 #define DH_EVEN_LAST 1
 #endif
@@ -764,29 +773,43 @@ __device__ __forceinline__ int load_fidx(const int32_t* p) {
 }
 constexpr int kBwdThreads = DH_BWD_THREADS;   // 11 warps x 2 CTAs/SM (80 registers, ~97 KB smem); 9 / 10 / 12 warps measured slower
 constexpr int kBwdWarps = kBwdThreads / 32;
-constexpr int kTaskCap = 96;
+constexpr int kTaskCap = 64;
+constexpr int kMaxBatches = 96;
 #ifndef DH_CHUNK_FACES
 #define DH_CHUNK_FACES 1024
 #endif
 constexpr int kChunkFaces = DH_CHUNK_FACES;   // faces per backward CTA at most (item list: 2 windings x 1024 x u16 = 4 KB)
 #ifndef DH_PAIR_CAP
-#define DH_PAIR_CAP 8
+#define DH_PAIR_CAP 16
 #endif
 constexpr int kPairCap = DH_PAIR_CAP;  // pixels one out-scan task handles before it re-queues its remainder
 
 struct __align__(16) BwdWarp {
     float px[3][32], py[3][32];          // pixel coordinates of the batch's faces, by lane slot
-    int fn[32];
     unsigned long long acc[6][32];       // fixed-point sums of the terms, [vertex * 2 + xy][slot]
     uint2 tq[kTaskCap];                  // .x: slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 | resume d1 << 19
                                          // .y: d1_cross of the task's crossing (float bits; computed once, in phase 1)
 };
-// list path only: the six (edge, axis) spans of every face of the batch, set up at full lanes before the crossing
-// loop.  rng = d0_from | d0_to << 10 | (direction > 0) << 20 | empty << 21
+#ifndef DH_FLAT_ENUM
+#define DH_FLAT_ENUM 1   // 1 (list path): crossings of a batch enumerated one per lane over the batch's compacted span list
+#endif                   // 0: every lane walks the six spans of its own face
+// list path only: the (edge, axis) spans of the faces of the batch, set up at full lanes before the crossing loop.
+#if DH_FLAT_ENUM
+// The non-empty spans, compacted in (lane, span) order.  With start = number of crossings (scan lines) of the spans
+// before it: info = lane | (edge * 2 + axis) << 5 | (direction > 0) << 8 | (d0_from - start + 2^17) << 9 (a crossing's
+// scan line is its number + that offset), start16 = start mod 2^16 (only differences below 2^14 are ever taken).
+struct __align__(16) BwdSpans {
+    float slope[192];
+    uint32_t info[192];
+    uint16_t start16[192];
+};
+#else
+// rng = d0_from | d0_to << 10 | (direction > 0) << 20 | empty << 21
 struct __align__(16) BwdSpans {
     float slope[6][32];
     uint32_t rng[6][32];
 };
+#endif
 
 // 64-bit fixed-point accumulation in shared memory as two native 32-bit atomics (a 64-bit shared atomicAdd is a
 // compare-and-swap loop): the low words add up modulo 2^32, and every add that wraps carries one into the high
@@ -986,7 +1009,7 @@ __device__ __forceinline__ float grad_value(const BwdMaps& m, int r, int c, bool
 // scans (a line running along the mismatch band) are cut into pieces so that the 32 lanes of a round do similar
 // amounts of work.
 // LISTS: the out scan walks the line's compressed pixel list (k_neg_maps) instead of bitmap words; task word
-//        slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 (9 bits) | (resume list index + 1) << 18.
+//        slot | edge << 5 | axis << 7 | kind << 8 | d0 << 9 (9 bits) | (resume index within the line's list + 1) << 18.
 struct NegLists {   // both axes behind one base pointer (indexing an array of pointers by axis would go to local memory)
     const uint16_t* base;
     __device__ __forceinline__ const uint16_t* start(int axis) const { return base + axis * kNLAxis; }
@@ -994,7 +1017,7 @@ struct NegLists {   // both axes behind one base pointer (indexing an array of p
 template <bool FUSED, bool LISTS>
 __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp& W, const BwdMaps& m,
                                              const NegLists& nl, float eps, float fpscale, float gcoef,
-                                             float gcoef_pos) {
+                                             float gcoef_pos, const uint16_t* items, int f0, int nF) {
     const int slot = t & 31, edge = (t >> 5) & 3, axis = (t >> 7) & 1, kind = (t >> 8) & 1;
     const int d0 = LISTS ? (int)((t >> 9) & 511u) : (int)((t >> 9) & 1023u);
     const int resume = LISTS ? (int)(t >> 18) : (int)(t >> 19);
@@ -1022,7 +1045,8 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
         sp.d0_to = f2i_sat(fminf(fmaxf(sp.p00, sp.p10), (float)(is - 1)));
         sp.slope = (sp.p11 - sp.p01) / (sp.p10 - sp.p00);
     }
-    const int fn = W.fn[slot];
+    const uint32_t item = items[slot];   // the batch's items: local face | winding << 15
+    const int fn = f0 + (int)(item & 0x7FFFu) + ((item >> 15) ? nF : 0);
     EdgeCoef ec;
 #if DH_FAST_COEF
     if (LISTS) {  // gradients carry a 1e-3 bar: the approximate divider (2 ulp) is enough for the coefficients
@@ -1049,7 +1073,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             const int step = up ? 1 : -1;
             const int i_end = up ? le : ls - 1;
             const int lim = d1_out * step;
-            int i = resume ? resume - 1 : (up ? ls : le - 1);
+            int i = resume ? ls + resume - 1 : (up ? ls : le - 1);   // resume: 1 + index within the line's list
             const int left = (i_end - i) * step;
             const int i_stop = (left > kPairCap) ? i + step * kPairCap : i_end;
             const float dunit = (gcoef * 0.5f) * m.gscale;
@@ -1078,7 +1102,7 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
                     i += step;
                     e = e_next;
                 }
-                if (i != i_end) cont = (t & 0x3FFFFu) | ((uint32_t)(i + 1) << 18);  // rest of the line: a later round
+                if (i != i_end) cont = (t & 0x3FFFFu) | ((uint32_t)(i - ls + 1) << 18);  // rest of the line: a later round
                 sa *= dunit;
                 sb *= dunit;
             }
@@ -1157,7 +1181,11 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
     extern __shared__ __align__(16) uint32_t smw[];
     __shared__ __align__(16) int16_t s_rng[4][kMaxIS];       // row_lo, row_hi, col_lo, col_hi
     __shared__ uint16_t s_items[2 * kChunkFaces];  // local face | winding << 15, compacted, in face order
-    __shared__ float s_bsum[2 * kChunkFaces / 32 + kBwdWarps][13];  // pose-gradient partial sums, one row per batch
+    __shared__ float s_bsum[kMaxBatches][13];  // pose-gradient partial sums, one row per batch
+#if DH_GUIDED
+    __shared__ uint16_t s_bstart[kMaxBatches + 1];
+    __shared__ int s_nbatches;
+#endif
     __shared__ int s_wcount[kBwdWarps], s_woff[kBwdWarps + 1];
     __shared__ int s_next_batch;
     const int is = raster_size(s), S = s.S;
@@ -1255,6 +1283,22 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
         int o = 0;
         for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
         s_woff[kBwdWarps] = o;
+#if DH_GUIDED
+        // Guided schedule, a function of the item count only: full batches while there is more than a round of them
+        // left, then ever smaller ones, so that the warps run out of work at nearly the same time.  (With one crossing
+        // per lane a small batch costs no lanes in the loops, only in its set-up and tail.)
+        int pos = 0, nb = 0;
+        while (pos < o) {
+            const int rem = o - pos;
+            int sz = min(32, max(DH_GUIDE_MIN, rem / (kBwdWarps * DH_GUIDE_DIV)));
+            if (rem - sz < DH_GUIDE_MIN / 2) sz = min(rem, 32);                       // no crumbs at the end
+            if (nb + (rem + 31) / 32 >= kMaxBatches - 1) sz = min(rem, 32);          // (never with <= 2048 items)
+            s_bstart[nb++] = (uint16_t)pos;
+            pos += sz;
+        }
+        s_bstart[nb] = (uint16_t)o;
+        s_nbatches = nb;
+#endif
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
@@ -1270,6 +1314,7 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
     }
     __syncthreads();
     const int n_items = s_woff[kBwdWarps];
+    (void)n_items;
 
     BwdMaps m;
     m.alpha = s_alpha; m.neg = nullptr; m.negT = LISTS ? nullptr : s_negT; m.neg_pool = LISTS ? nullptr : s_negp;
@@ -1304,6 +1349,9 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
     // Batch schedule (a function of n_items only): rounds of kBwdWarps full batches, then the remainder split
     // evenly into kBwdWarps smaller batches, so that the last round keeps every warp busy instead of leaving most
     // of them waiting at the final barrier.
+#if DH_GUIDED
+    const int n_batches = s_nbatches;
+#else
 #if DH_EVEN_LAST
     const int full_batches = (n_items / (32 * kBwdWarps)) * kBwdWarps;
 #else
@@ -1312,13 +1360,18 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
     const int rem_items = n_items - 32 * full_batches;
     const int last_size = DH_EVEN_LAST ? (rem_items + kBwdWarps - 1) / kBwdWarps : 32;
     const int n_batches = full_batches + (rem_items ? (rem_items + last_size - 1) / last_size : 0);
+#endif
     for (;;) {
         int batch = 0;
         if (lane == 0) batch = atomicAdd(&s_next_batch, 1);
         batch = __shfl_sync(0xffffffffu, batch, 0);
         if (batch >= n_batches) break;
+#if DH_GUIDED
+        const int bstart = s_bstart[batch], bsize = s_bstart[batch + 1] - bstart;
+#else
         const int bstart = batch < full_batches ? 32 * batch : 32 * full_batches + (batch - full_batches) * last_size;
         const int bsize = batch < full_batches ? 32 : min(last_size, n_items - bstart);
+#endif
         float acc[13];
 #pragma unroll
         for (int i = 0; i < 13; i++) acc[i] = 0.0f;
@@ -1337,118 +1390,203 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
                 W.px[k][lane] = px[k];
                 W.py[k][lane] = py[k];
             }
-            W.fn[lane] = fn;
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) W.acc[k][lane] = 0ull;
         __syncwarp();
-        // ---- phase 1: enumerate crossings, emit tasks
+        // ---- phase 1 / 2: enumerate crossings, queue tasks, run them 32 at a time.  ONE loop with ONE inlined copy of
+        //      bwd_task (the kernel's hot code stays within the instruction cache): every trip enumerates one step of
+        //      crossings and queues its out scans -- or queues the (rare) in scans held back from the step before, so
+        //      that the queue never holds more than 31 + 32 tasks -- and then runs full rounds; the last trip drains.
         int n_tasks = 0;
+        bool pend_in = false;     // this lane holds an in-scan task back
+        uint32_t tw_in = 0;
+        float tc_in = 0.0f;
+        int stage = 0;            // 1: the next trip queues the held-back in scans (warp-uniform)
+        bool more;                // crossings left to enumerate (warp-uniform)
+#if DH_FLAT_ENUM
+        // list path: one crossing per lane.  Every lane sets up the six spans of its face and appends the non-empty
+        // ones to the batch's span list (one warp scan gives list positions and crossing offsets); the crossings of the
+        // batch are then numbered 0 .. T-1 along that list and handed out 32 at a time, whatever face they belong to:
+        // all lanes work until the batch is done, and a lane never switches spans in the middle of the loop.
+        int T = 0, NS = 0, s0 = 0, base = 0;   // s0: a span that starts at or before the step's first crossing
+        const float* Pb = &W.px[0][0];         // px[3][32] then py[3][32]: [axis][vertex][slot]
+        if (LISTS) {
+            uint32_t len[6], inf[6], pack = 0;
+            float slp[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                len[k] = 0; inf[k] = 0; slp[k] = 0.0f;
+                if (have) {
+                    Span t;
+                    span_setup(px, py, k >> 1, k & 1, is, t);
+                    const int l = t.d0_to - t.d0_from + 1;
+                    len[k] = l > 0 ? (uint32_t)l : 0u;
+                    slp[k] = t.slope;
+                    inf[k] = (uint32_t)lane | ((uint32_t)k << 5) | ((0 < t.direction) ? (1u << 8) : 0u) |
+                             ((uint32_t)(t.d0_from + (1 << 17)) << 9);
+                    pack += len[k] + (len[k] ? (1u << 20) : 0u);   // crossings (< 2^17 per batch) | spans << 20
+                }
+            }
+            uint32_t incl = pack;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t totals = __shfl_sync(0xffffffffu, incl, 31);
+            T = (int)(totals & 0xFFFFFu);
+            NS = (int)(totals >> 20);
+            uint32_t tb = (incl - pack) & 0xFFFFFu, cb = (incl - pack) >> 20;
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (len[k]) {
+                    SP.start16[cb] = (uint16_t)tb; SP.slope[cb] = slp[k]; SP.info[cb] = inf[k] - (tb << 9);
+                    cb++; tb += len[k];
+                }
+            __syncwarp();
+        }
+#endif
+        // bitmap path (and DH_FLAT_ENUM = 0): every lane walks the six spans of its own face
         int span_id = have ? 0 : 6, d0 = 0;
         Span sp;
         sp.d0_to = -1;
-        if (have) {
-            if (LISTS) {
+        if (!(LISTS && DH_FLAT_ENUM)) {
+            if (have) {
+#if !DH_FLAT_ENUM
+                if (LISTS) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    Span t;
-                    span_setup(px, py, k >> 1, k & 1, is, t);
-                    SP.slope[k][lane] = t.slope;
-                    SP.rng[k][lane] = (uint32_t)t.d0_from | ((uint32_t)max(t.d0_to, 0) << 10) |
-                                      ((0 < t.direction) ? (1u << 20) : 0u) | ((t.d0_to < t.d0_from) ? (1u << 21) : 0u);
-                    if (k == 0) { sp = t; d0 = t.d0_from; }
-                }
-            } else {
-                span_setup(px, py, 0, 0, is, sp);
-                d0 = sp.d0_from;
-            }
-        }
-        while (__any_sync(0xffffffffu, span_id < 6)) {
-            bool t_out = false, t_in = false;
-            uint32_t tw = 0;
-            float tcross = 0.0f;
-            if (span_id < 6) {
-                if (d0 <= sp.d0_to) {
-                    const int axis = span_id & 1;
-                    float d1_cross;
-                    int d1_in, d1_out;
-                    if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out)) {
-                        // an out scan can contribute iff the line has a wanted pixel at or beyond d1_out in the scan
-                        // direction: one compare against the line's last (direction +) or first (direction -) one
-                        const bool dpos = 0 < sp.direction;
-                        const int bound = s_rng[(axis ? 0 : 2) + (dpos ? 1 : 0)][d0];
-                        t_out = dpos ? (d1_out <= bound) : (bound <= d1_out);
-                        const int r_out = (axis == 0) ? d1_out : d0, c_out = (axis == 0) ? d0 : d1_out;
-                        t_in = !((s_alpha[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u);
-                        tw = (uint32_t)lane | ((uint32_t)(span_id >> 1) << 5) | ((uint32_t)axis << 7) |
-                             ((uint32_t)d0 << 9);
-                        tcross = d1_cross;
+                    for (int k = 0; k < 6; k++) {
+                        Span t;
+                        span_setup(px, py, k >> 1, k & 1, is, t);
+                        SP.slope[k][lane] = t.slope;
+                        SP.rng[k][lane] = (uint32_t)t.d0_from | ((uint32_t)max(t.d0_to, 0) << 10) |
+                                          ((0 < t.direction) ? (1u << 20) : 0u) | ((t.d0_to < t.d0_from) ? (1u << 21) : 0u);
+                        if (k == 0) { sp = t; d0 = t.d0_from; }
                     }
-                    d0++;
+                } else
+#endif
+                {
+                    span_setup(px, py, 0, 0, is, sp);
+                    d0 = sp.d0_from;
                 }
-                if (d0 > sp.d0_to) {  // next span of this lane's face (its set-up was done at full lanes above)
-                    span_id++;
+            }
+            more = __any_sync(0xffffffffu, span_id < 6);
+        } else {
+#if DH_FLAT_ENUM
+            more = T > 0;
+#endif
+        }
+        for (;;) {
+            bool q = false;
+            uint32_t tw = 0;
+            float tc = 0.0f;
+            if (stage) {
+                q = pend_in; tw = tw_in; tc = tc_in;
+                stage = 0;
+            } else if (more) {
+                bool t_out = false, t_in = false;
+                // (axis, scan line, crossing, pixel inside / outside) -> which scans can contribute.  Out scan: iff the
+                // line has a wanted pixel at or beyond d1_out in the scan direction -- one compare against the line's
+                // last (direction +) or first (direction -) one.  In scan: iff the pixel outside is uncovered.
+                auto classify = [&](int slot, int edge, int axis, int d0_, bool dpos, int d1_out, float d1_cross) {
+                    const int bound = s_rng[(axis ? 0 : 2) + (dpos ? 1 : 0)][d0_];
+                    t_out = dpos ? (d1_out <= bound) : (bound <= d1_out);
+                    const int r_out = (axis == 0) ? d1_out : d0_, c_out = (axis == 0) ? d0_ : d1_out;
+                    t_in = !((s_alpha[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u);
+                    tw = (uint32_t)slot | ((uint32_t)edge << 5) | ((uint32_t)axis << 7) | ((uint32_t)d0_ << 9);
+                    tc = d1_cross;
+                };
+#if DH_FLAT_ENUM
+                if (LISTS) {
+                    // spans that start inside this step mark their first crossing; a lane's span = s0 + marks up to itself
+                    uint32_t bit = 0;
+                    const int j = s0 + 1 + lane;
+                    if (j < NS) {
+                        const uint32_t rel = (uint32_t)(uint16_t)(SP.start16[j] - (uint16_t)base);
+                        if (rel < 32u) bit = 1u << rel;
+                    }
+                    const uint32_t M = __reduce_or_sync(0xffffffffu, bit);
+                    const int span = s0 + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
+                    s0 += __popc(M);
+                    const int idx = base + lane;
+                    if (idx < T) {
+                        const uint32_t info = SP.info[span];
+                        const int slot = (int)(info & 31u), k = (int)((info >> 5) & 7u), axis = k & 1, edge = k >> 1;
+                        const int d0_ = idx + (int)(info >> 9) - (1 << 17);
+                        const bool dpos = (info >> 8) & 1u;
+                        const float p00 = Pb[(axis * 3 + edge) * 32 + slot], p01 = Pb[((1 - axis) * 3 + edge) * 32 + slot];
+                        float c = SP.slope[span] * ((float)d0_ - p00);   // span_crossing (dh_core.h), same operation order
+                        c = c + p01;
+                        const int d1_in = f2i_sat(dpos ? floorf(c) : ceilf(c));
+                        const int d1_out = d1_in + (dpos ? 1 : -1);
+                        if ((unsigned)d1_in < (unsigned)is && (unsigned)d1_out < (unsigned)is)
+                            classify(slot, edge, axis, d0_, dpos, d1_out, c);
+                    }
+                    base += 32;
+                    more = base < T;
+                } else
+#endif
+                {
                     if (span_id < 6) {
-                        if (LISTS) {
-                            const int e0 = span_id >> 1, ax = span_id & 1;
-                            const uint32_t rg = SP.rng[span_id][lane];
-                            sp.slope = SP.slope[span_id][lane];
-                            sp.p00 = ax ? W.py[e0][lane] : W.px[e0][lane];
-                            sp.p01 = ax ? W.px[e0][lane] : W.py[e0][lane];
-                            sp.direction = (rg >> 20) & 1u ? 1 : -1;
-                            d0 = (int)(rg & 1023u);
-                            sp.d0_to = (rg >> 21) & 1u ? -1 : (int)((rg >> 10) & 1023u);
-                        } else {
-                            span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
-                            d0 = sp.d0_from;
+                        if (d0 <= sp.d0_to) {
+                            float d1_cross;
+                            int d1_in, d1_out;
+                            if (span_crossing(sp, d0, is, &d1_cross, &d1_in, &d1_out))
+                                classify(lane, span_id >> 1, span_id & 1, d0, 0 < sp.direction, d1_out, d1_cross);
+                            d0++;
+                        }
+                        if (d0 > sp.d0_to) {  // next span of this lane's face
+                            span_id++;
+                            if (span_id < 6) {
+#if !DH_FLAT_ENUM
+                                if (LISTS) {   // (its set-up was done at full lanes above)
+                                    const int e0 = span_id >> 1, ax = span_id & 1;
+                                    const uint32_t rg = SP.rng[span_id][lane];
+                                    sp.slope = SP.slope[span_id][lane];
+                                    sp.p00 = ax ? W.py[e0][lane] : W.px[e0][lane];
+                                    sp.p01 = ax ? W.px[e0][lane] : W.py[e0][lane];
+                                    sp.direction = (rg >> 20) & 1u ? 1 : -1;
+                                    d0 = (int)(rg & 1023u);
+                                    sp.d0_to = (rg >> 21) & 1u ? -1 : (int)((rg >> 10) & 1023u);
+                                } else
+#endif
+                                {
+                                    span_setup(px, py, span_id >> 1, span_id & 1, is, sp);
+                                    d0 = sp.d0_from;
+                                }
+                            }
                         }
                     }
+                    more = __any_sync(0xffffffffu, span_id < 6);
                 }
+                q = t_out;
+                pend_in = t_in; tw_in = tw | (1u << 8); tc_in = tc;
+                stage = __any_sync(0xffffffffu, t_in) ? 1 : 0;
             }
-            const uint32_t mo = __ballot_sync(0xffffffffu, t_out), mi = __ballot_sync(0xffffffffu, t_in);
-            if (t_out) {
-                const int q = n_tasks + __popc(mo & lt_mask);
-                W.tq[q] = make_uint2(tw, __float_as_uint(tcross));
-            }
-            if (t_in) {
-                const int q = n_tasks + __popc(mo) + __popc(mi & lt_mask);
-                W.tq[q] = make_uint2(tw | (1u << 8), __float_as_uint(tcross));
-            }
-            n_tasks += __popc(mo) + __popc(mi);
+            const uint32_t mq = __ballot_sync(0xffffffffu, q);
+            if (q) W.tq[n_tasks + __popc(mq & lt_mask)] = make_uint2(tw, __float_as_uint(tc));
+            n_tasks += __popc(mq);
             __syncwarp();
-            while (n_tasks >= 32) {
-                n_tasks -= 32;
-                const uint2 tk = W.tq[n_tasks + lane];
-                const float dc = __uint_as_float(tk.y);
-                const uint32_t cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef, gcoef_pos);
+            const bool last = !more && !stage;
+            while (n_tasks >= 32 || (last && n_tasks > 0)) {   // (the drain's remainders are drained too)
+                const int nt = min(n_tasks, 32);
+                n_tasks -= nt;
+                uint32_t cont = 0;
+                float dc = 0.0f;
+                if (lane < nt) {
+                    const uint2 tk = W.tq[n_tasks + lane];
+                    dc = __uint_as_float(tk.y);
+                    cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef, gcoef_pos, s_items + bstart, f0,
+                                                  s.F);
+                }
                 __syncwarp();
                 const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
-                if (cont) {
-                    const int q = n_tasks + __popc(mc & lt_mask);
-                    W.tq[q] = make_uint2(cont, __float_as_uint(dc));
-                }
+                if (cont) W.tq[n_tasks + __popc(mc & lt_mask)] = make_uint2(cont, __float_as_uint(dc));
                 n_tasks += __popc(mc);
                 __syncwarp();
             }
-        }
-        while (n_tasks > 0) {  // drain, including the remainders the drain itself produces
-            const int nt = min(n_tasks, 32);
-            n_tasks -= nt;
-            uint32_t cont = 0;
-            float dc = 0.0f;
-            if (lane < nt) {
-                const uint2 tk = W.tq[n_tasks + lane];
-                dc = __uint_as_float(tk.y);
-                cont = bwd_task<FUSED, LISTS>(tk.x, dc, W, m, nl, s.eps, fpscale, gcoef, gcoef_pos);
-            }
-            __syncwarp();
-            const uint32_t mc = __ballot_sync(0xffffffffu, cont != 0u);
-            if (cont) {
-                const int q = n_tasks + __popc(mc & lt_mask);
-                W.tq[q] = make_uint2(cont, __float_as_uint(dc));
-            }
-            n_tasks += __popc(mc);
-            __syncwarp();
+            if (last) break;
         }
         // ---- tail: per item, fixed point -> float, then through the projection and the rigid transform
         if (have) {
