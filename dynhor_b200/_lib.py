@@ -33,7 +33,7 @@ class DhCorr(ctypes.Structure):
     """struct dh_corr (include/dynhor_b200.h) -- builder-defined correspondence term."""
     _fields_ = [
         ("records", c_p), ("C", c_i), ("nslots", c_i), ("delta", c_f), ("pad_", c_f),
-        ("w_sum", c_d), ("lw_corr", c_d), ("partials", c_p),
+        ("w_sum", c_d), ("lw_corr", c_d), ("partials", c_p), ("w_sum_dev", c_p),
     ]
 
 
@@ -84,6 +84,7 @@ SIGNATURES = {
     "dh_jointopt_eval": (c_i, [ctypes.POINTER(DhJointOpt), c_p]),
     "dh_jointopt_grads": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_p, c_p, c_p]),
     "dh_jointopt_profile": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
+    "dh_jointopt_run_part": (c_i, [ctypes.POINTER(DhJointOpt), c_i, c_p]),
     "dh_jointopt_release": (c_i, [ctypes.POINTER(DhJointOpt)]),
     "dh_jointopt_probe": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
     "dh_scale_apply": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_i, c_p]),

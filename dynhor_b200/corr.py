@@ -72,7 +72,9 @@ class _CorrSums(torch.autograd.Function):
 class CorrespondenceTerm:
     """Holds the records of the local frames and evaluates loss_corr_obj (composable autograd path)."""
 
-    def __init__(self, records, K_roi, image_size=REND_SIZE, delta=1.0, w_sum=None):
+    def __init__(self, records, K_roi, image_size=REND_SIZE, delta=1.0, w_sum=None, ready=None):
+        """ready: a CUDA event after which `records` is valid -- the term was built on a side stream that is still
+        uploading (joint_optimize); every use from another stream waits for it first."""
         self.records = pad_records(records)
         if not self.records.is_cuda:
             if not torch.cuda.is_available():
@@ -81,9 +83,28 @@ class CorrespondenceTerm:
         self.K = K_roi
         self.S = int(image_size)
         self.delta = float(delta)
-        self.w_local = self.records[..., 5].double().sum()
-        self.w_sum = float(self.w_local.item()) if w_sum is None else float(w_sum)
+        self.w_local = self.records[..., 5].double().sum()      # device scalar: no host synchronisation here
+        self._w_sum = None if w_sum is None else float(w_sum)
+        self.ready = ready
+
+    def wait_ready(self):
+        """Make the current stream wait for the records (no-op once done)."""
+        if self.ready is not None:
+            torch.cuda.current_stream().wait_event(self.ready)
+            self.ready = None
+
+    @property
+    def w_sum(self):
+        if self._w_sum is None:
+            self.wait_ready()
+            self._w_sum = float(self.w_local.item())
+        return self._w_sum
+
+    @w_sum.setter
+    def w_sum(self, v):
+        self._w_sum = float(v)
 
     def loss(self, rotations, translations, scale_abs):
+        self.wait_ready()
         sums = _CorrSums.apply(rotations, translations, scale_abs, self.records, self.K, self.S, self.delta)
         return sums.sum() / self.w_sum

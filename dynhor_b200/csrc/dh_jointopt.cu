@@ -884,7 +884,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 // whole frame is rasterised; they are stored per frame, in the units the backward uses for the masked-L2 loss
 // (pixel gradient = 2 * coefficient), together with the frame's gradient bound gmax.
 __global__ void __launch_bounds__(kNegThreads)
-k_neg_maps(const dh_sil s, int build_lists, int list_cap, const int32_t* __restrict__ loss_counts,
+k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ loss_counts,
            float* __restrict__ frame_coef, float lw_iou) {
     extern __shared__ uint32_t nm_words[];  // [is][wpr + 1] row-major; the column-side CTA transposes it in place
                                             // (rows padded by one word: a thread per line and the block transposes
@@ -960,7 +960,12 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, const int32_t* __restr
         uint16_t* L = s.neg_lists + ((size_t)b * 2 + axis) * kNLAxis;
         const bool over = total > list_cap;
         if (tid < is) L[tid] = (uint16_t)(over ? 0 : start);
-        if (tid == 0) L[is] = (uint16_t)(over ? kNLOverflow : (uint32_t)total);
+        if (tid == 0) {
+            L[is] = (uint16_t)(over ? kNLOverflow : (uint32_t)total);
+            // the frames' overflow flags side by side (slot 3 of the frame's loss counters, zeroed by k_project): the
+            // bitmap kernel behind the list kernel reads them in one pass and normally ends right there
+            if (over && loss_counts != nullptr) loss_counts[b * 4 + 3] = 1;
+        }
         if (over || tid >= is) continue;
         uint16_t* E = L + kNLStart + start;
         for (int w = 0; w < wpr; w++) {
@@ -1648,15 +1653,18 @@ __global__ void __launch_bounds__(kBwdThreads, DH_BWD_MIN_CTAS)
 k_backward(const dh_sil s, const float* __restrict__ verts_src, const float* __restrict__ Rmat,
            const float* __restrict__ trans, const float* __restrict__ scale, float* __restrict__ partials,
            float* __restrict__ grad_verts, int nchunks, float gcoef_all, int only_overflow,
-           const float* __restrict__ frame_coef) {
+           const float* __restrict__ frame_coef, const int32_t* __restrict__ loss_counts) {
     const int is = raster_size(s);
     if (LISTS) {
         const int b = blockIdx.y;
         if (s.neg_lists[(size_t)b * 2 * kNLAxis + is] == kNLOverflow) return;
         bwd_frame<FUSED, LISTS>(s, verts_src, Rmat, trans, scale, partials, grad_verts, nchunks, gcoef_all, frame_coef, b);
     } else if (only_overflow) {
+        int any = 0;
+        for (int b = threadIdx.x; b < s.B; b += kBwdThreads) any |= loss_counts[b * 4 + 3];
+        if (!__syncthreads_or(any)) return;
         for (int b = blockIdx.y; b < s.B; b += gridDim.y) {
-            if (s.neg_lists[(size_t)b * 2 * kNLAxis + is] != kNLOverflow) continue;   // (uniform over the CTA)
+            if (loss_counts[b * 4 + 3] == 0) continue;   // (uniform over the CTA)
             bwd_frame<FUSED, LISTS>(s, verts_src, Rmat, trans, scale, partials, grad_verts, nchunks, gcoef_all, frame_coef,
                                     b);
             __syncthreads();   // the next frame reuses the shared arrays
@@ -1781,7 +1789,7 @@ __global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__
             const float* cp = p.corr.partials + ((size_t)b * p.corr.nslots + c) * 16;
             for (int i = 0; i < 13; i++) q[i] += (double)cp[i];
         }
-        const double coef = p.corr.lw_corr / p.corr.w_sum;
+        const double coef = p.corr.lw_corr / (p.corr.w_sum_dev ? *p.corr.w_sum_dev : p.corr.w_sum);
         const double sc = (double)p.scale[0], s_abs = fabs(sc), sgn = (sc < 0.0) ? -1.0 : 1.0;
         double dot = 0.0;
         for (int i = 0; i < 3; i++) gT[i] += coef * q[i];
@@ -1890,7 +1898,8 @@ __global__ void __launch_bounds__(kThreads) k_finalize(const dh_jointopt p, int 
                 h[1] = t[0] / 16.0 / p.keep_sum / (double)p.B_total;
                 h[2] = t[1] / (double)p.B_total;
             }
-            h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0) ? t[3] / p.corr.w_sum : 0.0;
+            h[3] = (p.corr.records != nullptr && p.corr.lw_corr > 0.0)
+                       ? t[3] / (p.corr.w_sum_dev ? *p.corr.w_sum_dev : p.corr.w_sum) : 0.0;
         }
         redg[0] = tg;   // this rank's exact partial
         if (mode == 1 && grad_scale != nullptr) grad_scale[0] = (float)fx_to_double(tg);
@@ -2068,11 +2077,11 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     rc = set_smem(k_backward<true, false>, sb);
     if (rc) return rc;
     k_backward<true, true><<<dim3(p.nchunks, B), kBwdThreads, sl, st>>>(
-        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0, fcoef);
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 0, fcoef, p.loss_counts);
     DH_LAUNCH_OK("k_backward<lists>");
     // frames with more contributing pixels than the lists hold (only these CTAs do any work)
-    k_backward<true, false><<<dim3(p.nchunks, min(B, 64)), kBwdThreads, sb, st>>>(
-        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1, fcoef);
+    k_backward<true, false><<<dim3(p.nchunks, min(B, 32)), kBwdThreads, sb, st>>>(
+        s, p.verts_og, p.Rmat, p.trans, p.scale, p.partials, nullptr, p.nchunks, gcoef, 1, fcoef, p.loss_counts);
     DH_LAUNCH_OK("k_backward<bitmaps>");
     return DH_OK;
 }
@@ -2115,16 +2124,36 @@ dh_jointopt sub_plan(const dh_jointopt& p, int b0, int nb) {
 // captured into a graph; the plain-stream paths (profile, eval, grads, use_graph = 0) stay serial.
 struct SideBranch { cudaStream_t stream; cudaEvent_t fork, join; bool after_raster; };
 
+// half: 0 = the whole iteration; 1 = pose preparation + silhouette kernels only, 2 = correspondence kernel + pose
+// update + bookkeeping only (dh_jointopt_run_part).
 int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_trans, float* g_scale,
-                     cudaStream_t st, IterEvents* evs = nullptr, const SideBranch* side = nullptr) {
+                     cudaStream_t st, IterEvents* evs = nullptr, const SideBranch* side = nullptr, int half = 0) {
     const dh_sil& s = p.sil;
     const int B = s.B;
     const bool with_sil = p.lw_sil > 0.0;
+    const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
+    if (half != 0) {
+        if (half == 1) {
+            k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
+            DH_LAUNCH_OK("k_pose_prep");
+            if (with_sil) return launch_sil_kernels(p, mode == 2, st);
+            return DH_OK;
+        }
+        if (with_corr) {
+            const int rc = launch_corr(p.corr.records, B, p.corr.C, p.Rmat, p.trans, p.scale, s.K, s.S, p.corr.delta,
+                                       p.corr.partials, p.corr.nslots, st);
+            if (rc) return rc;
+        }
+        k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
+        DH_LAUNCH_OK("k_pose_update");
+        k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
+        DH_LAUNCH_OK("k_finalize");
+        return DH_OK;
+    }
     DH_REC(0);
     k_pose_prep<<<(B + 127) / 128, 128, 0, st>>>(p);
     DH_LAUNCH_OK("k_pose_prep");
     DH_REC(1);
-    const bool with_corr = p.corr.records != nullptr && p.corr.lw_corr > 0.0;
     const bool forked = with_corr && with_sil && side != nullptr;
     auto corr_launch = [&](bool fork) -> int {
         cudaStream_t cs = st;
@@ -2201,7 +2230,8 @@ int check_plan(const dh_jointopt* p) {
     DH_REQUIRE(p->keep_sum > 0.0 || !(p->lw_sil > 0.0), "keep_sum must be positive");
     if (p->corr.records != nullptr && p->corr.lw_corr > 0.0) {
         DH_REQUIRE(p->corr.partials != nullptr && p->corr.C > 0 && p->corr.nslots > 0, "corr: bad plan");
-        DH_REQUIRE(p->corr.w_sum > 0.0 && p->corr.delta > 0.0f, "corr: w_sum and delta must be positive");
+        DH_REQUIRE((p->corr.w_sum_dev != nullptr || p->corr.w_sum > 0.0) && p->corr.delta > 0.0f,
+                   "corr: w_sum and delta must be positive");
     }
     return DH_OK;
 }
@@ -2294,7 +2324,7 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
     if (rc) return rc;
     const int nchunks = dh_jointopt_default_chunks(s->B, s->F);
     k_backward<false, false><<<dim3(nchunks, s->B), kBwdThreads, sb, st>>>(
-        t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0, nullptr);
+        t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0, nullptr, nullptr);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
 }
@@ -2445,6 +2475,17 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
     }
     for (int it = 0; it < n_iters; it++) DH_CUDA(cudaGraphLaunch(exec, st));
     return DH_OK;
+}
+
+int dh_jointopt_run_part(const dh_jointopt* p, int32_t part, void* stream) {
+    int rc = check_plan(p);
+    if (rc) return rc;
+    DH_REQUIRE(part == 1 || part == 2, "part must be 1 or 2");
+    if (part == 1) {   // function attributes (the graph path sets them before its capture)
+        rc = set_smem(k_raster<true>, raster_smem_bytes(p->sil));
+        if (rc) return rc;
+    }
+    return launch_iteration(*p, 0, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr, nullptr, part);
 }
 
 int dh_jointopt_eval(const dh_jointopt* p, void* stream) {

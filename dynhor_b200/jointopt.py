@@ -66,7 +66,9 @@ class Joint_Optimizer(nn.Module):
                              camintr_rois_object=self.camintr_rois_object)
         self.corr_delta = float(corr_delta)
         self.corr_term = None
-        if correspondences is not None:
+        if isinstance(correspondences, CorrespondenceTerm):     # built by the caller (joint_optimize: on its upload stream)
+            self.corr_term = correspondences
+        elif correspondences is not None:
             self.corr_term = CorrespondenceTerm(correspondences.cuda(), self.camintr_rois_object,
                                                 image_size=int(target_masks_object.shape[-1]), delta=corr_delta)
 
@@ -150,15 +152,25 @@ class FusedJointOpt:
             raise ValueError("corr_on=True but this rank's model has no correspondences / lw_corr_obj")
         # one fused all-reduce for the sequence-wide constants: sum(keep), sum(w), and the ranks' view of corr_on
         # (a rank that disagreed would otherwise hang the others in a mismatched collective later)
+        # Single rank: the records may still be on their way (joint_optimize uploads them on a side stream).  Then the
+        # kernels read the sum of weights from device memory (dh_corr.w_sum_dev) and the first iteration runs as two
+        # halves with the wait for the upload between them (_run): its silhouette kernels overlap the copy.
+        self._corr_event = None
+        if self.corr_on and model.corr_term.ready is not None:
+            if self.shard.world == 1:
+                self._corr_event, model.corr_term.ready = model.corr_term.ready, None
+            else:
+                model.corr_term.wait_ready()
         consts = torch.zeros(4, dtype=torch.float64, device=dev)
         consts[0] = keep[0].to(torch.float64)
-        if self.corr_on:
+        if self.corr_on and self._corr_event is None:
             consts[1] = model.corr_term.w_local.reshape(()).to(torch.float64)
         consts[2] = 1.0 if self.corr_on else 0.0
         consts[3] = 1.0
         if exchange and self.shard.world > 1:
             allreduce_sum_(consts, self.shard, group)
-        consts_h = consts.cpu().numpy() if (keep_sum is None or self.corr_on or exchange) else None
+        consts_h = consts.cpu().numpy() if (keep_sum is None or (self.corr_on and self._corr_event is None) or
+                                            exchange) else None
         if exchange and self.shard.world > 1 and consts_h[2] not in (0.0, consts_h[3]):
             raise _lib.DynhorError("the correspondence term is active on some ranks only: pass the same "
                                    "loss_weights / correspondences to every rank")
@@ -218,11 +230,17 @@ class FusedJointOpt:
             p.offscreen, p.frame_coef = self.offscreen.data_ptr(), self.frame_coef.data_ptr()
         if self.corr_on:
             ct = model.corr_term
-            self.corr_w_sum = float(consts_h[1]) if (exchange and consts_h is not None) else ct.w_sum
             cp = corr_plan(B, ct.records.shape[1])
             self.corr_partials = z(B, cp["nslots"], 16)
             p.corr.records, p.corr.C, p.corr.nslots = ct.records.data_ptr(), ct.records.shape[1], cp["nslots"]
-            p.corr.delta, p.corr.w_sum, p.corr.lw_corr = ct.delta, self.corr_w_sum, lw_corr
+            if self._corr_event is not None:
+                self.corr_w_sum = None          # known on the device only (ct.w_sum synchronises when asked)
+                ct.w_local.record_stream(torch.cuda.current_stream())
+                p.corr.w_sum_dev, p.corr.w_sum = ct.w_local.data_ptr(), 0.0
+            else:
+                self.corr_w_sum = float(consts_h[1]) if (exchange and consts_h is not None) else ct.w_sum
+                p.corr.w_sum = self.corr_w_sum
+            p.corr.delta, p.corr.lw_corr = ct.delta, lw_corr
             p.corr.partials = self.corr_partials.data_ptr()
         self.p = p
         sharded = self.shard.world > 1
@@ -279,8 +297,20 @@ class FusedJointOpt:
         torch.ops.dynhor.jointopt_run(self.model.rotations_object.detach(), self.model.translations_object.detach(),
                                       self.scale.detach(), self._handle, int(n_iters), bool(use_graph))
 
+    def _wait_corr(self):
+        if self._corr_event is not None:
+            torch.cuda.current_stream().wait_event(self._corr_event)
+            self._corr_event = None
+
     def _run(self, n_iters, use_graph=True):
         lib = _lib.load()
+        n_iters = int(n_iters)
+        if self._corr_event is not None and n_iters > 0:
+            # first iteration: everything but the correspondence kernel, then wait for the records, then the rest
+            _lib.check(lib.dh_jointopt_run_part(ctypes.byref(self.p), 1, _lib.stream_ptr()), "dh_jointopt_run_part")
+            self._wait_corr()
+            _lib.check(lib.dh_jointopt_run_part(ctypes.byref(self.p), 2, _lib.stream_ptr()), "dh_jointopt_run_part")
+            n_iters -= 1
         if self.halo_mode != "nccl":
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), int(n_iters), int(use_graph), _lib.stream_ptr()),
                        "dh_jointopt_run")
@@ -313,6 +343,7 @@ class FusedJointOpt:
         """Gradients of the weighted loss for the current parameters (no update)."""
         B = self.shard.B
         dev = self.step.device
+        self._wait_corr()
         g_rot = torch.empty(B, 3, 2, device=dev)
         g_tr = torch.empty(B, 1, 3, device=dev)
         g_s = torch.zeros(1, device=dev)
@@ -322,12 +353,14 @@ class FusedJointOpt:
 
     def evaluate(self):
         """Losses of the current parameters -> dict of one-element lists (synchronises)."""
+        self._wait_corr()
         _lib.check(_lib.load().dh_jointopt_eval(ctypes.byref(self.p), _lib.stream_ptr()), "dh_jointopt_eval")
         return self._rows_to_dict(self.hist[self.max_iters:self.max_iters + 1].clone())
 
     def probe(self, nblocks):
         """Milliseconds of the heavy kernels of one iteration for `nblocks` equal blocks of this rank's frames, plus
         the correspondence kernel over all of them as the last entry (dh_jointopt_probe; parameters untouched)."""
+        self._wait_corr()
         ms = (ctypes.c_float * (int(nblocks) + 1))()
         _lib.check(_lib.load().dh_jointopt_probe(ctypes.byref(self.p), int(nblocks), ms, _lib.stream_ptr()),
                    "dh_jointopt_probe")
@@ -390,6 +423,7 @@ class FusedJointOpt:
 
     def profile(self, n_iters=5):
         """Average per-kernel milliseconds over n_iters real iterations (CUDA events on the launch stream)."""
+        self._wait_corr()
         ms = (ctypes.c_float * 8)()
         _lib.check(_lib.load().dh_jointopt_profile(ctypes.byref(self.p), int(n_iters), ms, _lib.stream_ptr()),
                    "dh_jointopt_profile")
@@ -442,15 +476,31 @@ def _stack_frames(frames, key, pick=None, dtype=None):
 _upload_stream = {}
 
 
+def upload_stream(dev):
+    """The per-device side stream the batched uploads run on."""
+    dev = torch.device(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    up = _upload_stream.get(idx)
+    if up is None:
+        up = _upload_stream[idx] = torch.cuda.Stream(idx)
+    return up
+
+
 def _upload_rows(out, rows):
     """rows: equal-shaped contiguous pinned host tensors -> out[i] (dh_upload_rows: one cudaMemcpyBatchAsync instead of
     len(rows) copy calls).  Batched copies need a real stream, torch's default one is the legacy stream: they go through
-    a per-device side stream the current stream then waits for."""
+    a per-device side stream the current stream then waits for (when the upload stream itself is current -- the
+    deferred correspondence upload of joint_optimize -- nobody waits here)."""
     dev = out.device
     cur = torch.cuda.current_stream(dev)
-    up = _upload_stream.get(dev.index)
-    if up is None:
-        up = _upload_stream[dev.index] = torch.cuda.Stream(dev)
+    up = upload_stream(dev)
+    if cur == up:
+        n = len(rows)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows])
+        _lib.check(_lib.load().dh_upload_rows(ctypes.c_void_p(out.data_ptr()), ptrs,
+                                              rows[0].numel() * rows[0].element_size(), n,
+                                              ctypes.c_void_p(up.cuda_stream)), "dh_upload_rows")
+        return
     up.wait_stream(cur)                       # `out` may reuse memory the current stream is still working on
     n = len(rows)
     ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows])
@@ -574,7 +624,19 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
             C = int(local[0]["correspondences"].shape[1])
             if old_corr is not None and old_corr.shape[1] != C:
                 old_corr = old_corr[:, :C]       # (pad_records appended a zero-weight record to an odd C)
-            corr = frames_on_device(sh, "correspondences", (old_corr, s0))
+            if old_corr is None and sh.world == 1 and not local[0]["correspondences"].is_cuda:
+                # the largest upload, needed by one kernel only: it goes LAST on the upload stream, and nothing on the
+                # compute stream waits for it until the first iteration's correspondence kernel (FusedJointOpt._run)
+                cur, up = torch.cuda.current_stream(), upload_stream(K.device)
+                up.wait_stream(cur)
+                with torch.cuda.stream(up):
+                    rec = _stack_frames(local, "correspondences")
+                    rec.record_stream(cur)
+                    corr = CorrespondenceTerm(rec, K, image_size=int(masks.shape[-1]), delta=corr_delta)
+                    corr.records.record_stream(cur)
+                    corr.ready = up.record_event()
+            else:
+                corr = frames_on_device(sh, "correspondences", (old_corr, s0))
         return Joint_Optimizer(
             translations_object=trans, rotations_object=rots, verts_object_og=verts_object_og,
             faces_object=faces_dev, target_masks_object=masks, camintr_rois_object=K,

@@ -118,6 +118,8 @@ typedef struct dh_corr {
     double w_sum;                  /* sum of the weights over ALL ranks                                          */
     double lw_corr;                /* loss weight, 0 disables the term                                           */
     float* partials;               /* [B,nslots,16] scratch: dT(3), X (x) dc (9), loss (1), pad(3)               */
+    const double* w_sum_dev;       /* optional: the same sum in DEVICE memory, read by the kernels instead of     */
+                                   /* w_sum (lets the host queue iterations before the records are uploaded)     */
 } dh_corr;
 
 /* Launch plan of the streaming kernel: a frame's ceil(C/1024) record tiles form `nslots` segments of 8 tiles; every
@@ -212,6 +214,11 @@ int dh_jointopt_default_chunks(int32_t B, int32_t F);
 /* run n_iters fused iterations on `stream` (no host sync).  use_graph != 0: capture one iteration into a CUDA
  * graph (cached per plan address) and replay it. */
 int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, void* stream);
+/* ONE iteration as two plain-stream halves (no graph): part 1 = pose preparation + the silhouette term's kernels
+ * (projection ... backward), part 2 = correspondence kernel + pose update + bookkeeping.  The caller may make the
+ * stream wait for the upload of the correspondence records between the halves, so that the first iteration's
+ * silhouette work runs beside that copy.  Same arithmetic and results as dh_jointopt_run(p, 1, ...). */
+int dh_jointopt_run_part(const dh_jointopt* p, int32_t part, void* stream);
 /* forward only: losses of the current parameters into hist[max_iters] without touching parameters or step. */
 int dh_jointopt_eval(const dh_jointopt* p, void* stream);
 /* gradients of the weighted loss w.r.t. rot6d [B,6] and trans [B,3] (and scale [1]) for the current
