@@ -155,10 +155,15 @@ class FusedJointOpt:
         # Single rank: the records may still be on their way (joint_optimize uploads them on a side stream).  Then the
         # kernels read the sum of weights from device memory (dh_corr.w_sum_dev) and the first iteration runs as two
         # halves with the wait for the upload between them (_run): its silhouette kernels overlap the copy.
-        self._corr_event = None
+        # Sharded: the same, with the all-reduce of the sum of weights queued behind the upload on the upload stream.
+        self._corr_event, self._w_sum_dev = None, None
         if self.corr_on and model.corr_term.ready is not None:
             if self.shard.world == 1:
                 self._corr_event, model.corr_term.ready = model.corr_term.ready, None
+                self._w_sum_dev = model.corr_term.w_local
+            elif exchange:
+                self._w_sum_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+                self._corr_event = "pending"     # the all-reduce is queued at the end of __init__, behind the halo exchange
             else:
                 model.corr_term.wait_ready()
         consts = torch.zeros(4, dtype=torch.float64, device=dev)
@@ -234,9 +239,9 @@ class FusedJointOpt:
             self.corr_partials = z(B, cp["nslots"], 16)
             p.corr.records, p.corr.C, p.corr.nslots = ct.records.data_ptr(), ct.records.shape[1], cp["nslots"]
             if self._corr_event is not None:
-                self.corr_w_sum = None          # known on the device only (ct.w_sum synchronises when asked)
-                ct.w_local.record_stream(torch.cuda.current_stream())
-                p.corr.w_sum_dev, p.corr.w_sum = ct.w_local.data_ptr(), 0.0
+                self.corr_w_sum = None          # known on the device only
+                self._w_sum_dev.record_stream(torch.cuda.current_stream())
+                p.corr.w_sum_dev, p.corr.w_sum = self._w_sum_dev.data_ptr(), 0.0
             else:
                 self.corr_w_sum = float(consts_h[1]) if (exchange and consts_h is not None) else ct.w_sum
                 p.corr.w_sum = self.corr_w_sum
@@ -249,6 +254,17 @@ class FusedJointOpt:
         self._sync_halo()
         if self.halo_mode == "p2p":
             self._setup_p2p()
+        if self._corr_event == "pending":
+            # sum of the correspondence weights over the ranks, on the upload stream behind the records' copy.  Queued
+            # last: collectives run in issue order, and the halo exchange above must not wait for the upload.
+            cur, up = torch.cuda.current_stream(), upload_stream(dev, deferred=True)
+            up.wait_stream(cur)
+            with torch.cuda.stream(up):
+                self._w_sum_dev.copy_(model.corr_term.w_local.reshape(1))
+                allreduce_sum_(self._w_sum_dev, self.shard, group)
+                self._w_sum_dev.record_stream(up)
+                self._corr_event = up.record_event()
+            model.corr_term.ready = None
         # the shared scale's gradient under sharding: exact partial sums, added up in rank order on every rank
         if p.optimize_scale and sharded:
             p.scale_mode = _lib.SCALE_P2P if self.halo_mode == "p2p" else _lib.SCALE_DEFERRED
@@ -311,6 +327,10 @@ class FusedJointOpt:
             self._wait_corr()
             _lib.check(lib.dh_jointopt_run_part(ctypes.byref(self.p), 2, _lib.stream_ptr()), "dh_jointopt_run_part")
             n_iters -= 1
+            if self.halo_mode == "nccl":
+                if self.p.scale_mode == _lib.SCALE_DEFERRED:
+                    self.apply_scale(allgather_equal(self.scale_part, self.shard, self.group))
+                self._sync_halo()
         if self.halo_mode != "nccl":
             _lib.check(lib.dh_jointopt_run(ctypes.byref(self.p), int(n_iters), int(use_graph), _lib.stream_ptr()),
                        "dh_jointopt_run")
@@ -476,13 +496,14 @@ def _stack_frames(frames, key, pick=None, dtype=None):
 _upload_stream = {}
 
 
-def upload_stream(dev):
-    """The per-device side stream the batched uploads run on."""
-    dev = torch.device(dev)
+def upload_stream(dev, deferred=False):
+    """The per-device side streams of the batched uploads: one the compute stream waits for right away, and one for
+    the deferred upload of the correspondence records (so that a later ordinary upload does not wait behind it)."""
+    dev = torch.device(dev) if not isinstance(dev, int) else torch.device("cuda", dev)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    up = _upload_stream.get(idx)
+    up = _upload_stream.get((idx, bool(deferred)))
     if up is None:
-        up = _upload_stream[idx] = torch.cuda.Stream(idx)
+        up = _upload_stream[(idx, bool(deferred))] = torch.cuda.Stream(idx)
     return up
 
 
@@ -494,7 +515,8 @@ def _upload_rows(out, rows):
     dev = out.device
     cur = torch.cuda.current_stream(dev)
     up = upload_stream(dev)
-    if cur == up:
+    if cur == up or cur == upload_stream(dev, deferred=True):
+        up = cur
         n = len(rows)
         ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in rows])
         _lib.check(_lib.load().dh_upload_rows(ctypes.c_void_p(out.data_ptr()), ptrs,
@@ -607,9 +629,23 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
             parts.append(_stack_frames(object_parameters[hi:sh.stop], key, **kw))
         return torch.cat(parts) if len(parts) > 1 else parts[0]
 
-    def build(sh, with_corr, reuse=None):
+    def start_corr_upload(sh):
+        """Begin uploading the correspondence records of the frames of `sh` on the upload stream, without making the
+        compute stream wait: (records tensor, shard) for build's `pre_corr`, or None when there is nothing to do."""
+        local = sh.slice(object_parameters)
+        if not corr_on or local[0]["correspondences"].is_cuda:
+            return None
+        cur, up = torch.cuda.current_stream(), upload_stream(torch.cuda.current_device(), deferred=True)
+        up.wait_stream(cur)
+        with torch.cuda.stream(up):
+            rec = _stack_frames(local, "correspondences")
+            rec.record_stream(cur)
+        return rec, sh
+
+    def build(sh, with_corr, reuse=None, pre_corr=None):
         """Model of the frames of `sh`.  Stage 1 hands over CUDA tensors (pose_initializtion.py:460-471); host tensors
-        are accepted too.  reuse = (model, shard) of an earlier build: frames it already holds stay on the device."""
+        are accepted too.  reuse = (model, shard) of an earlier build: frames it already holds stay on the device.
+        pre_corr = start_corr_upload's result for an earlier range: only the frames it lacks are uploaded."""
         local = sh.slice(object_parameters)
         faces.check(sh.start, sh.stop)
         trans = _stack_frames(local, "translations")
@@ -624,16 +660,17 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
             C = int(local[0]["correspondences"].shape[1])
             if old_corr is not None and old_corr.shape[1] != C:
                 old_corr = old_corr[:, :C]       # (pad_records appended a zero-weight record to an odd C)
-            if old_corr is None and sh.world == 1 and not local[0]["correspondences"].is_cuda:
+            if old_corr is None and not local[0]["correspondences"].is_cuda:
                 # the largest upload, needed by one kernel only: it goes LAST on the upload stream, and nothing on the
                 # compute stream waits for it until the first iteration's correspondence kernel (FusedJointOpt._run)
-                cur, up = torch.cuda.current_stream(), upload_stream(K.device)
+                cur, up = torch.cuda.current_stream(), upload_stream(K.device, deferred=True)
                 up.wait_stream(cur)
                 with torch.cuda.stream(up):
-                    rec = _stack_frames(local, "correspondences")
+                    rec = frames_on_device(sh, "correspondences", pre_corr)
                     rec.record_stream(cur)
                     corr = CorrespondenceTerm(rec, K, image_size=int(masks.shape[-1]), delta=corr_delta)
                     corr.records.record_stream(cur)
+                    corr.w_local.record_stream(cur)
                     corr.ready = up.record_event()
             else:
                 corr = frames_on_device(sh, "correspondences", (old_corr, s0))
@@ -649,6 +686,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
         # cost-weighted partition: time the heavy kernels block by block on the equal-count ranges, gather, re-cut
         nblocks = max(1, min(16, (B_total // shard.world) // 32))
         model0 = build(shard, with_corr=False)
+        pre = start_corr_upload(shard)      # runs beside the probe; the re-cut range reuses what it has
         lw_probe = {k: v for k, v in loss_weights.items() if k != "lw_corr_obj"}
         with FusedJointOpt(model0, lw_probe, lr, 0, shard=shard, keep_sum=1.0, exchange=False) as probe:
             ms = torch.from_numpy(probe.probe(nblocks)).cuda()
@@ -657,7 +695,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
                                for r in range(shard.world)])
         new = shard.with_bounds(balanced_bounds(cost, shard.world))
         model = model0 if (new.start, new.stop) == (shard.start, shard.stop) and not corr_on else \
-            build(new, with_corr=True, reuse=(model0, shard))
+            build(new, with_corr=True, reuse=(model0, shard), pre_corr=pre)
         shard = new
         del model0
     mark("partition")
