@@ -739,6 +739,10 @@ k_grad_signs(const float* __restrict__ g, uint32_t* __restrict__ pos_pool, uint3
 #ifndef DH_BWD_MIN_CTAS
 #define DH_BWD_MIN_CTAS 2
 #endif
+#ifndef DH_OWN_EARLY
+#define DH_OWN_EARLY 0   // 1 (list path, DH_FLAT_ENUM): the "face owns the pixel inside the edge" test of an out scan is made
+#endif                   // during the enumeration, one step behind its face-index load; tasks that fail (18 %) are never
+                         // queued.  Measured: 1.055 vs 0.981 ms -- the load's latency in the enumeration costs more
 #ifndef DH_GUIDED
 #define DH_GUIDED 1      // 1: batch sizes shrink towards the end of the chunk (guided schedule); 0: DH_EVEN_LAST's
 #endif
@@ -1070,7 +1074,12 @@ __device__ __forceinline__ uint32_t bwd_task(uint32_t t, float d1_cross, BwdWarp
             // upwards) of the line's sorted list.  Along an out scan d1 - d1_cross has the sign of the direction, so
             // the sign of dist = k (d1 - d1_cross) (2/is) -- and with it the sign of eps -- is fixed per task, and
             // a skipped term (k == 0) becomes 1 / inf.  -dL/dpixel = code * dunit; dunit multiplies the task's sums.
+#if DH_OWN_EARLY && DH_FLAT_ENUM
+            const int own = fn;   // tested before the task was queued
+            (void)r_in; (void)c_in;
+#else
             const int own = load_fidx(m.fidx + r_in * is + c_in);
+#endif
             const uint16_t* L = nl.start(axis);
             const int ls = L[d0], le = L[d0 + 1];
             const uint16_t* E = L + kNLStart;
@@ -1409,6 +1418,11 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
         float tc_in = 0.0f;
         int stage = 0;            // 1: the next trip queues the held-back in scans (warp-uniform)
         bool more;                // crossings left to enumerate (warp-uniform)
+        // DH_OWN_EARLY: out-scan candidates of the previous step, waiting for their face-index load
+        bool pq = false, pend_out = false;
+        uint32_t ptw = 0;
+        float ptc = 0.0f;
+        int pown = 0, pfn = 0;
 #if DH_FLAT_ENUM
         // list path: one crossing per lane.  Every lane sets up the six spans of its face and appends the non-empty
         // ones to the batch's span list (one warp scan gives list positions and crossing offsets); the crossings of the
@@ -1489,21 +1503,31 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
             if (stage) {
                 q = pend_in; tw = tw_in; tc = tc_in;
                 stage = 0;
-            } else if (more) {
+            } else if (more || pend_out) {
                 bool t_out = false, t_in = false;
+                int own_new = -1, fn_new = 0;
                 // (axis, scan line, crossing, pixel inside / outside) -> which scans can contribute.  Out scan: iff the
                 // line has a wanted pixel at or beyond d1_out in the scan direction -- one compare against the line's
                 // last (direction +) or first (direction -) one.  In scan: iff the pixel outside is uncovered.
                 auto classify = [&](int slot, int edge, int axis, int d0_, bool dpos, int d1_out, float d1_cross) {
                     const int bound = s_rng[(axis ? 0 : 2) + (dpos ? 1 : 0)][d0_];
                     t_out = dpos ? (d1_out <= bound) : (bound <= d1_out);
+#if DH_OWN_EARLY && DH_FLAT_ENUM
+                    if (LISTS && t_out) {   // the load is consumed one trip later
+                        const int d1_in = d1_out - (dpos ? 1 : -1);
+                        const int r_in = (axis == 0) ? d1_in : d0_, c_in = (axis == 0) ? d0_ : d1_in;
+                        own_new = load_fidx(m.fidx + r_in * is + c_in);
+                        const uint32_t item = s_items[bstart + slot];
+                        fn_new = f0 + (int)(item & 0x7FFFu) + ((item >> 15) ? s.F : 0);
+                    }
+#endif
                     const int r_out = (axis == 0) ? d1_out : d0_, c_out = (axis == 0) ? d0_ : d1_out;
                     t_in = !((s_alpha[r_out * wpr + (c_out >> 5)] >> (c_out & 31)) & 1u);
                     tw = (uint32_t)slot | ((uint32_t)edge << 5) | ((uint32_t)axis << 7) | ((uint32_t)d0_ << 9);
                     tc = d1_cross;
                 };
 #if DH_FLAT_ENUM
-                if (LISTS) {
+                if (LISTS && more) {
                     // spans that start inside this step mark their first crossing; a lane's span = s0 + marks up to itself
                     uint32_t bit = 0;
                     const int j = s0 + 1 + lane;
@@ -1530,7 +1554,7 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
                     }
                     base += 32;
                     more = base < T;
-                } else
+                } else if (!(LISTS && DH_FLAT_ENUM))
 #endif
                 {
                     if (span_id < 6) {
@@ -1565,15 +1589,26 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
                     }
                     more = __any_sync(0xffffffffu, span_id < 6);
                 }
-                q = t_out;
                 pend_in = t_in; tw_in = tw | (1u << 8); tc_in = tc;
                 stage = __any_sync(0xffffffffu, t_in) ? 1 : 0;
+#if DH_OWN_EARLY && DH_FLAT_ENUM
+                if (LISTS) {
+                    // queue the candidates of the step before (their owner has arrived), hold this step's back
+                    q = pq && pown == pfn;
+                    const uint32_t tw_q = ptw;
+                    const float tc_q = ptc;
+                    pq = t_out; ptw = tw; ptc = tc; pown = own_new; pfn = fn_new;
+                    pend_out = __any_sync(0xffffffffu, t_out);
+                    tw = tw_q; tc = tc_q;
+                } else
+#endif
+                    q = t_out;
             }
             const uint32_t mq = __ballot_sync(0xffffffffu, q);
             if (q) W.tq[n_tasks + __popc(mq & lt_mask)] = make_uint2(tw, __float_as_uint(tc));
             n_tasks += __popc(mq);
             __syncwarp();
-            const bool last = !more && !stage;
+            const bool last = !more && !stage && !pend_out;
             while (n_tasks >= 32 || (last && n_tasks > 0)) {   // (the drain's remainders are drained too)
                 const int nt = min(n_tasks, 32);
                 n_tasks -= nt;
