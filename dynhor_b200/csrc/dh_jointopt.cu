@@ -1423,6 +1423,7 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
         uint32_t ptw = 0;
         float ptc = 0.0f;
         int pown = 0, pfn = 0;
+        (void)pq; (void)ptw; (void)ptc; (void)pown; (void)pfn;
 #if DH_FLAT_ENUM
         // list path: one crossing per lane.  Every lane sets up the six spans of its face and appends the non-empty
         // ones to the batch's span list (one warp scan gives list positions and crossing offsets); the crossings of the
@@ -1506,6 +1507,7 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
             } else if (more || pend_out) {
                 bool t_out = false, t_in = false;
                 int own_new = -1, fn_new = 0;
+                (void)own_new; (void)fn_new;
                 // (axis, scan line, crossing, pixel inside / outside) -> which scans can contribute.  Out scan: iff the
                 // line has a wanted pixel at or beyond d1_out in the scan direction -- one compare against the line's
                 // last (direction +) or first (direction -) one.  In scan: iff the pixel outside is uncovered.
