@@ -15,4 +15,5 @@ ncu --set full --clock-control none --import-source on -k regex:"k_raster|k_back
 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_stage1.py tests/test_gpu_prior_features.py -q -x -k "reference_run or oracle" > gpurun_out/${TAG}_memcheck.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/${TAG}_memcheck.log
 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_sharding.py -q -x -k "loopback or emulated_shards_equal_single" > gpurun_out/${TAG}_memcheck2.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/${TAG}_memcheck2.log
 compute-sanitizer --tool racecheck --error-exitcode 1 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/${TAG}_racecheck.log
-tail -2 gpurun_out/${TAG}_memcheck.log gpurun_out/${TAG}_memcheck2.log gpurun_out/${TAG}_racecheck.log
+compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_jointopt.py -q -x -k "list_path_and_bitmap or partly_outside or joint_optimize_matches" > gpurun_out/${TAG}_memcheck3.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/${TAG}_memcheck3.log
+for f in memcheck memcheck2 memcheck3 racecheck; do echo "== $f"; tail -n 2 gpurun_out/${TAG}_$f.log; done
