@@ -305,7 +305,7 @@ def run_ours(args):
             cal.check_status()
         t_all = allgather_equal(t, shard).reshape(-1).cpu().numpy()
         calib_ms = [float(v) for v in t_all]
-        if t_all.max() > 1.03 * t_all.mean():
+        if t_all.max() > 1.01 * t_all.mean():      # (8-iteration means of a device clock: the noise is well below 1 %)
             nb = balanced_bounds(rescale_costs(cost, shard.bounds, t_all), world)
             if nb != shard.bounds:
                 shard, seq1 = shard.with_bounds(nb), None
