@@ -40,8 +40,11 @@ constexpr int kThreads = 256;      // CTA size of the backward / elementwise ker
 #ifndef DH_RASTER_EVEN
 #define DH_RASTER_EVEN 1
 #endif
+#ifndef DH_RASTER_SPLIT1
+#define DH_RASTER_SPLIT1 1  // the same for the second pass (reversed windings: mostly culled by tile-z)
+#endif
 #ifndef DH_RASTER_SPLIT
-#define DH_RASTER_SPLIT 1   // batches per warp the last (partial) round is cut into
+#define DH_RASTER_SPLIT 1   // batches per warp the last (partial) round of the first pass is cut into
 #endif
 #ifndef DH_TILE_Z
 #define DH_TILE_Z 1
@@ -454,7 +457,8 @@ k_raster(const dh_sil s, const int8_t* __restrict__ mask_tri, float gcoef, float
 #if DH_RASTER_EVEN
         const int full = (count / (32 * kRasterWarps)) * kRasterWarps;
         const int rem = count - 32 * full;
-        const int last = (rem + DH_RASTER_SPLIT * kRasterWarps - 1) / (DH_RASTER_SPLIT * kRasterWarps);
+        const int split = pass_i == 0 ? DH_RASTER_SPLIT : DH_RASTER_SPLIT1;
+        const int last = (rem + split * kRasterWarps - 1) / (split * kRasterWarps);
 #else
         const int full = count / 32, rem = count - 32 * full, last = 32;
 #endif
@@ -1797,35 +1801,49 @@ __global__ void k_pose_prep(const dh_jointopt p) {
 
 // mode 0: Adam update in place.  mode 1: write gradients to (grad_rot6d, grad_trans), leave parameters alone.
 // mode 2: per-frame loss terms only (forward-only evaluation; no backward ran, partials are not read).
-__global__ void k_pose_update(const dh_jointopt p, int mode, float* __restrict__ grad_rot6d,
-                              float* __restrict__ grad_trans, int with_sil, int with_corr) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per frame: the frame's partial-sum rows (16 floats each: one per backward chunk, one per correspondence
+// segment) are read by lane = (row parity, component) with all loads of a lane independent, added up in double
+// (even rows, odd rows, then the two halves), and handed to lane 0, which does the rest.  (A thread per frame read its
+// 12 rows one after the other behind a run-time trip count: 25 us for 300 frames.)
+constexpr int kPoseUpdateThreads = 128;
+__device__ __forceinline__ double shfl_double(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src),
+                            __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+__device__ __forceinline__ double warp_row_sums(const float* __restrict__ rows, int nrows, int lane) {
+    const int comp = lane & 15, half = lane >> 4;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int c = half; c < nrows; c += 2) acc += (double)rows[c * 16 + comp];
+    return acc + shfl_double(acc, (lane + 16) & 31);   // lanes l and l + 16 now both hold component l & 15
+}
+__global__ void __launch_bounds__(kPoseUpdateThreads)
+k_pose_update(const dh_jointopt p, int mode, float* __restrict__ grad_rot6d,
+              float* __restrict__ grad_trans, int with_sil, int with_corr) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (kPoseUpdateThreads / 32) + (threadIdx.x >> 5);
     if (b >= p.sil.B) return;
-    double G[9], gT[3], gs = 0.0;
-    for (int i = 0; i < 9; i++) G[i] = 0.0;
-    for (int i = 0; i < 3; i++) gT[i] = 0.0;
-    if (with_sil && mode != 2) {
-        for (int c = 0; c < p.nchunks; c++) {
-            const float* q = p.partials + ((size_t)b * p.nchunks + c) * 16;
-            for (int i = 0; i < 3; i++) gT[i] += (double)q[i];
-            for (int i = 0; i < 9; i++) G[i] += (double)q[3 + i];
-            gs += (double)q[12];
-        }
-        gs *= (p.scale[0] < 0.0f) ? -1.0 : 1.0;
+    double sil_c = 0.0, corr_c = 0.0;   // component (lane & 15) of the frame's sums
+    if (with_sil && mode != 2) sil_c = warp_row_sums(p.partials + (size_t)b * p.nchunks * 16, p.nchunks, lane);
+    if (with_corr) corr_c = warp_row_sums(p.corr.partials + (size_t)b * p.corr.nslots * 16, p.corr.nslots, lane);
+    double G[9], gT[3], gs = 0.0, q[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++) {
+        const double v = shfl_double(sil_c, i);
+        q[i] = shfl_double(corr_c, i);
+        if (i < 3) gT[i] = v;
+        else if (i < 12) G[i - 3] = v;
+        else gs = v;
     }
+    if (lane != 0) return;
+    if (with_sil && mode != 2) gs *= (p.scale[0] < 0.0f) ? -1.0 : 1.0;
     const double* st = p.smooth_terms + (size_t)b * 16;
     for (int i = 0; i < 3; i++) gT[i] += st[i];
     for (int i = 0; i < 9; i++) G[i] += st[3 + i];
     gs += st[12];
-    // correspondence term (builder-defined, dh_corr.cu): slots summed in order, then lw / sum(w)
+    // correspondence term (builder-defined, dh_corr.cu): segment sums, then lw / sum(w)
     double corr_loss = 0.0;
     if (with_corr) {
-        double q[13];
-        for (int i = 0; i < 13; i++) q[i] = 0.0;
-        for (int c = 0; c < p.corr.nslots; c++) {
-            const float* cp = p.corr.partials + ((size_t)b * p.corr.nslots + c) * 16;
-            for (int i = 0; i < 13; i++) q[i] += (double)cp[i];
-        }
         const double coef = p.corr.lw_corr / (p.corr.w_sum_dev ? *p.corr.w_sum_dev : p.corr.w_sum);
         const double sc = (double)p.scale[0], s_abs = fabs(sc), sgn = (sc < 0.0) ? -1.0 : 1.0;
         double dot = 0.0;
@@ -2181,7 +2199,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
                                        p.corr.partials, p.corr.nslots, st);
             if (rc) return rc;
         }
-        k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
+        k_pose_update<<<(B + kPoseUpdateThreads / 32 - 1) / (kPoseUpdateThreads / 32), kPoseUpdateThreads, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
         DH_LAUNCH_OK("k_pose_update");
         k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);
         DH_LAUNCH_OK("k_finalize");
@@ -2225,7 +2243,7 @@ int launch_iteration(const dh_jointopt& p, int mode, float* g_rot, float* g_tran
     }
     DH_REC(5);
     if (forked) DH_CUDA(cudaStreamWaitEvent(st, side->join, 0));
-    k_pose_update<<<(B + 127) / 128, 128, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
+    k_pose_update<<<(B + kPoseUpdateThreads / 32 - 1) / (kPoseUpdateThreads / 32), kPoseUpdateThreads, 0, st>>>(p, mode, g_rot, g_trans, with_sil ? 1 : 0, with_corr ? 1 : 0);
     DH_LAUNCH_OK("k_pose_update");
     DH_REC(6);
     k_finalize<<<1, kThreads, 0, st>>>(p, mode, g_scale);

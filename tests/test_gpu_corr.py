@@ -155,6 +155,72 @@ def test_joint_optimize_drop_in_with_and_without_correspondences():
     assert not torch.equal(m2.rotations_object, m0.rotations_object)
 
 
+def test_deferred_upload_and_split_first_iteration_change_nothing():
+    """Host frames (pinned: one batched copy per key through dh_upload_rows, the correspondence records on their own
+    stream with the first iteration split around the wait -- dh_jointopt_run_part, dh_corr.w_sum_dev) against the same
+    frames handed over as CUDA tensors (no deferral, sum of weights on the host, every iteration a graph replay): the
+    same bits."""
+    from dynhor_b200 import synth
+    from dynhor_b200.jointopt import joint_optimize
+    seq = _seq(6, 2000, masks=True)
+    faces = np.stack([seq["faces"]] * 6)
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0, "lw_corr_obj": 0.1}
+    host = synth.to_object_parameters(seq)
+    pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in p.items()} for p in host]
+    dev = [{k: (v.cuda() if torch.is_tensor(v) else v) for k, v in p.items()} for p in host]
+    runs = []
+    for params in (dev, host, pinned):
+        m, e = joint_optimize(params, objvertices=seq["verts"], objfaces=faces, loss_weights=lw, num_iterations=4,
+                              lr=1e-4)
+        runs.append((m.rotations_object.detach().cpu(), m.translations_object.detach().cpu(), e))
+    for r, t, e in runs[1:]:
+        assert torch.equal(r, runs[0][0]) and torch.equal(t, runs[0][1])
+        assert e["loss"] == runs[0][2]["loss"] and e["loss_corr_obj"] == runs[0][2]["loss_corr_obj"]
+
+
+def test_run_part_halves_equal_one_iteration():
+    """dh_jointopt_run_part(1) + (2) on the plain stream == dh_jointopt_run(p, 1) (graph), bit for bit."""
+    import ctypes
+    from dynhor_b200 import _lib
+    from dynhor_b200.jointopt import FusedJointOpt
+    seq = _seq(5, 1500, masks=True)
+    lw = {"lw_sil_obj": 1.0, "lw_smooth_obj": 10.0, "lw_corr_obj": 0.1}
+    out = []
+    for split in (False, True):
+        model = _model(seq)
+        with FusedJointOpt(model, lw, 1e-3, 4) as fused:
+            lib = _lib.load()
+            for _ in range(3):
+                if split:
+                    for part in (1, 2):
+                        _lib.check(lib.dh_jointopt_run_part(ctypes.byref(fused.p), part, _lib.stream_ptr()), "run_part")
+                else:
+                    fused.run(1)
+            hist = fused.history()
+        out.append((model.rotations_object.detach().cpu(), model.translations_object.detach().cpu(), hist))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][2]["loss"] == out[1][2]["loss"]
+
+
+def test_upload_rows_batched_copy():
+    """dh_upload_rows: n pinned host rows -> contiguous device rows (one batched driver copy on a real stream, row by
+    row on the legacy default stream)."""
+    import ctypes
+    from dynhor_b200 import _lib
+    rows = [torch.randn(1, 257, 6).pin_memory() for _ in range(37)]
+    want = torch.cat(rows)
+    lib = _lib.load()
+    nbytes = rows[0].numel() * 4
+    ptrs = (ctypes.c_void_p * len(rows))(*[r.data_ptr() for r in rows])
+    for stream in (torch.cuda.Stream(), None):
+        out = torch.zeros(37, 257, 6, device="cuda")
+        torch.cuda.synchronize()
+        sp = ctypes.c_void_p(stream.cuda_stream) if stream is not None else ctypes.c_void_p(0)
+        _lib.check(lib.dh_upload_rows(ctypes.c_void_p(out.data_ptr()), ptrs, nbytes, len(rows), sp), "dh_upload_rows")
+        torch.cuda.synchronize()
+        assert torch.equal(out.cpu(), want)
+
+
 def test_composable_autograd_path_with_correspondences():
     """Joint_Optimizer.forward (the reference-shaped loop: weighted sum, backward, torch.optim.Adam)."""
     seq = _seq(3, 900, masks=True)
