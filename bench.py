@@ -428,7 +428,7 @@ def run_ours(args):
     faces_b = np.stack([seq["faces"]] * B_total)     # run.py:158
     e2e_iters = args.steps
     kw = dict(objvertices=seq["verts"], objfaces=faces_b, loss_weights=lw, lr=LR, board=None, halo=args.halo,
-              balance=args.balance)
+              balance="auto" if args.balance == "probe" else args.balance)   # the call's own policy: probe from 64 iterations on
     joint_optimize(params, num_iterations=2, **kw)
     # the call is one shot of ~45 ms of which several ms are host work (uploads, launches): timed args.e2e_reps times
     # from the same host buffers, the MEDIAN is reported (every repetition is listed in seconds_all)
@@ -451,7 +451,9 @@ def run_ours(args):
     dt = float(np.median(dts))
     e2e = {"value": B_total * e2e_iters / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
            "d2h_bytes_per_step": d2h / e2e_iters, "iterations": e2e_iters, "seconds": dt,
-           "seconds_all": [round(x, 5) for x in dts], "final_loss": evo["loss"][-1]}
+           "seconds_all": [round(x, 5) for x in dts], "final_loss": evo["loss"][-1],
+           "partition": "single" if world == 1 else ("count" if list(own.bounds) == list(FrameShard(rank, world, B_total).bounds)
+                                                      else "probe")}
     if getattr(model2, "timing", None):     # DH_TIMING=1: synchronised phase times of this rank's call (diagnostics)
         e2e["phases_ms"] = {k: round(v, 2) for k, v in model2.timing}
 
