@@ -2298,6 +2298,7 @@ struct GraphEntry {
     dh_jointopt plan;
     int device;
     int list_cap;
+    int fork_mode;
     cudaGraphExec_t exec;
 };
 constexpr size_t kGraphCacheMax = 32;
@@ -2472,9 +2473,12 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
     int device = 0;
     DH_CUDA(cudaGetDevice(&device));
     const int list_cap = neg_list_cap();
+    const int fork_mode = corr_fork_mode(p->corr.C);
     std::lock_guard<std::mutex> lock(graph_mutex());
     for (auto& e : graph_cache())
-        if (e.device == device && e.list_cap == list_cap && memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0) exec = e.exec;
+        if (e.device == device && e.list_cap == list_cap && e.fork_mode == fork_mode &&
+            memcmp(&e.plan, p, sizeof(dh_jointopt)) == 0)
+            exec = e.exec;
     if (exec == nullptr) {
         // warm the function attributes outside capture
         rc = set_smem(k_raster<true>, raster_smem_bytes(p->sil));
@@ -2488,7 +2492,6 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         cudaStream_t cs;
         DH_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         SideBranch side;
-        const int fork_mode = corr_fork_mode(p->corr.C);
         const bool fork_corr = fork_mode != 0;
         side.after_raster = fork_mode >= 2;
         if (fork_corr) {
@@ -2525,6 +2528,7 @@ int dh_jointopt_run(const dh_jointopt* p, int32_t n_iters, int32_t use_graph, vo
         memcpy(&e.plan, p, sizeof(dh_jointopt));
         e.device = device;
         e.list_cap = list_cap;
+        e.fork_mode = fork_mode;
         e.exec = exec;
         c.push_back(e);
     }

@@ -174,12 +174,14 @@ class FusedJointOpt:
         consts[3] = 1.0
         if exchange and self.shard.world > 1:
             allreduce_sum_(consts, self.shard, group)
-        consts_h = consts.cpu().numpy() if (keep_sum is None or (self.corr_on and self._corr_event is None) or
-                                            exchange) else None
-        if exchange and self.shard.world > 1 and consts_h[2] not in (0.0, consts_h[3]):
-            raise _lib.DynhorError("the correspondence term is active on some ranks only: pass the same "
-                                   "loss_weights / correspondences to every rank")
-        self.keep_sum = float(keep_sum) if keep_sum is not None else float(consts_h[0])
+        # the host needs them (keep_sum enters the kernels by value): copied back asynchronously, read after the
+        # allocations below -- the host works on while the masks are still crossing PCIe
+        consts_pin, consts_ev = None, None
+        if keep_sum is None or (self.corr_on and self._corr_event is None) or exchange:
+            consts_pin = torch.empty(4, dtype=torch.float64, pin_memory=True)
+            consts_pin.copy_(consts, non_blocking=True)
+            consts_ev = torch.cuda.Event()
+            consts_ev.record()
         self.keep_local = keep
         self.moments = torch.empty(12, dtype=torch.float64, device=dev)
         _lib.check(lib.dh_mesh_moments(_lib.ptr(verts), V, _lib.ptr(self.moments), st), "dh_mesh_moments")
@@ -204,6 +206,14 @@ class FusedJointOpt:
         _lib.check(lib.dh_jointopt_scratch_bytes(B, self.nchunks, sizes), "dh_jointopt_scratch_bytes")
         self.scratch = [torch.zeros(int(n), dtype=torch.uint8, device=dev) for n in sizes]
         self.loss_weights = dict(loss_weights)
+        consts_h = None
+        if consts_ev is not None:
+            consts_ev.synchronize()
+            consts_h = consts_pin.numpy().copy()
+        if exchange and self.shard.world > 1 and consts_h[2] not in (0.0, consts_h[3]):
+            raise _lib.DynhorError("the correspondence term is active on some ranks only: pass the same "
+                                   "loss_weights / correspondences to every rank")
+        self.keep_sum = float(keep_sum) if keep_sum is not None else float(consts_h[0])
         p = _lib.DhJointOpt()
         p.sil = self.sil.c
         p.verts_og, p.mask_tri = verts.data_ptr(), self.mask_tri.data_ptr()
