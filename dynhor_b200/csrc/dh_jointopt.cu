@@ -903,9 +903,10 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ 
     // grid (B, 2): block y = 1 builds the row side (row ranges, row lists), y = 0 the column side (transposed bitmap,
     // column lists)
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int axis_lo = blockIdx.y, axis_hi = blockIdx.y;
+    // gridDim.y == 2: one CTA per side; gridDim.y == 1: one CTA does the row side, transposes, then the column side
+    const bool single = gridDim.y == 1;
     const int warp = tid >> 5, lane = tid & 31;
-    if (frame_coef != nullptr && blockIdx.y == 0 && tid == 0) {
+    if (frame_coef != nullptr && blockIdx.y == 0 && tid == 0) {   // (either grid shape)
         const float I = (float)loss_counts[b * 4 + 1] * 0.25f, U = (float)loss_counts[b * 4 + 2] * 0.25f + 0.000001f;
         const float g_neg = lw_iou / U, g_pos = (lw_iou * I / U) / U;
         frame_coef[2 * b + 0] = 0.5f * g_neg;
@@ -926,28 +927,9 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ 
         words[r * wps + w] = neg_row_word(s_alpha, gn, is, s.aa, wpr, wprp, r, w);
     }
     __syncthreads();
-    if (axis_lo == 0) {
-        // in-place transpose: the 32x32 bit blocks (rb, cb) and (cb, rb), rb <= cb, are transposed through ballots
-        // and swapped; every warp owns whole block pairs
-        const int npairs = wpr * (wpr + 1) / 2;
-        for (int pr = warp; pr < npairs; pr += kNegThreads / 32) {
-            int rb = 0, rem = pr;
-            while (rem >= wpr - rb) { rem -= wpr - rb; rb++; }
-            const int cb = rb + rem;
-            const uint32_t wa = words[(32 * rb + lane) * wps + cb], wb = words[(32 * cb + lane) * wps + rb];
-            const uint32_t ta = transpose32(wa, lane), tb = transpose32(wb, lane);
-            __syncwarp();
-            words[(32 * cb + lane) * wps + rb] = ta;
-            words[(32 * rb + lane) * wps + cb] = tb;
-        }
-    }
-    __syncthreads();
-    uint32_t* gT = s.negT + (size_t)b * is * wpr;
-    if (axis_lo == 0)
-        for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[(i / wpr) * wps + (i % wpr)];
-    for (int axis = axis_lo; axis <= axis_hi; axis++) {
-        // axis 0: lines are columns (words of wordsT), axis 1: lines are rows
-        const uint32_t* W = axis ? words : wordsT;
+    // ranges + lists of one axis from its line-major bitmap W (axis 0: lines are columns = words of the transposed
+    // bitmap, axis 1: lines are rows)
+    auto side = [&](int axis, const uint32_t* W) {
         int cnt = 0, lo = is, hi = -1;
         if (tid < is) {
             for (int w = 0; w < wpr; w++) {
@@ -962,7 +944,7 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ 
             s.row_rng[((size_t)b * 4 + (axis ? 0 : 2)) * is + tid] = (int16_t)lo;
             s.row_rng[((size_t)b * 4 + (axis ? 1 : 3)) * is + tid] = (int16_t)hi;
         }
-        if (!build_lists) continue;
+        if (!build_lists) return;
         int total;
         const int start = block_exclusive_scan_512(cnt, s_wsum, &total);
         uint16_t* L = s.neg_lists + ((size_t)b * 2 + axis) * kNLAxis;
@@ -974,7 +956,7 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ 
             // bitmap kernel behind the list kernel reads them in one pass and normally ends right there
             if (over && loss_counts != nullptr) loss_counts[b * 4 + 3] = 1;
         }
-        if (over || tid >= is) continue;
+        if (over || tid >= is) return;
         uint16_t* E = L + kNLStart + start;
         for (int w = 0; w < wpr; w++) {
             uint32_t bits = W[tid * wps + w];
@@ -991,6 +973,27 @@ k_neg_maps(const dh_sil s, int build_lists, int list_cap, int32_t* __restrict__ 
                 *E++ = (uint16_t)((uint32_t)d1 | ((uint32_t)(4 - pop) << 10));
             }
         }
+    };
+    if (single || blockIdx.y == 1) side(1, words);
+    if (single || blockIdx.y == 0) {
+        if (single) __syncthreads();   // the row side has read the row-major words
+        // in-place transpose: the 32x32 bit blocks (rb, cb) and (cb, rb), rb <= cb, are transposed through ballots
+        // and swapped; every warp owns whole block pairs
+        const int npairs = wpr * (wpr + 1) / 2;
+        for (int pr = warp; pr < npairs; pr += kNegThreads / 32) {
+            int rb = 0, rem = pr;
+            while (rem >= wpr - rb) { rem -= wpr - rb; rb++; }
+            const int cb = rb + rem;
+            const uint32_t wa = words[(32 * rb + lane) * wps + cb], wb = words[(32 * cb + lane) * wps + rb];
+            const uint32_t ta = transpose32(wa, lane), tb = transpose32(wb, lane);
+            __syncwarp();
+            words[(32 * cb + lane) * wps + rb] = ta;
+            words[(32 * rb + lane) * wps + cb] = tb;
+        }
+        __syncthreads();
+        uint32_t* gT = s.negT + (size_t)b * is * wpr;
+        for (int i = tid; i < is * wpr; i += kNegThreads) gT[i] = wordsT[(i / wpr) * wps + (i % wpr)];
+        side(0, wordsT);
     }
 }
 
@@ -2055,6 +2058,11 @@ size_t bwd_lists_smem_bytes(const dh_sil& s) {
            (DH_ALPHA_GLOBAL ? 16 : (size_t)(is * (is / 32)) * sizeof(uint32_t)) +
            (DH_LISTS_GLOBAL ? 0 : (size_t)2 * kNLAxis * sizeof(uint16_t));
 }
+// CTAs per frame of k_neg_maps: 2 = one per side (rows / columns), 1 = both sides in one CTA (DH_NEG_SIDES overrides)
+int neg_maps_sides() {
+    const char* e = getenv("DH_NEG_SIDES");
+    return (e != nullptr && e[0] == '2') ? 2 : ((e != nullptr && e[0] == '1') ? 1 : 2);
+}
 size_t neg_maps_smem_bytes(const dh_sil& s) {
     const int is = raster_size(s);
     return (size_t)(is * (is / 32 + 1) + is * (is / 32)) * sizeof(uint32_t);
@@ -2123,7 +2131,7 @@ int launch_sil_kernels(const dh_jointopt& p, bool forward_only, cudaStream_t st,
     rc = set_smem(k_neg_maps, neg_maps_smem_bytes(s));
     if (rc) return rc;
     float* fcoef = stage1 ? p.frame_coef : nullptr;
-    k_neg_maps<<<dim3(B, 2), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap(), p.loss_counts, fcoef,
+    k_neg_maps<<<dim3(B, neg_maps_sides()), kNegThreads, neg_maps_smem_bytes(s), st>>>(s, 1, neg_list_cap(), p.loss_counts, fcoef,
                                                                         (float)p.lw_sil);
     DH_LAUNCH_OK("k_neg_maps");
     const size_t sl = bwd_lists_smem_bytes(s), sb = bwd_smem_bytes(s);
