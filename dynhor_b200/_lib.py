@@ -85,6 +85,7 @@ SIGNATURES = {
     "dh_jointopt_grads": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_p, c_p, c_p]),
     "dh_jointopt_profile": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
     "dh_jointopt_run_part": (c_i, [ctypes.POINTER(DhJointOpt), c_i, c_p]),
+    "dh_bwd_schedule": (c_i, [c_i, ctypes.POINTER(ctypes.c_int32), c_i]),
     "dh_jointopt_release": (c_i, [ctypes.POINTER(DhJointOpt)]),
     "dh_jointopt_probe": (c_i, [ctypes.POINTER(DhJointOpt), c_i, ctypes.POINTER(c_f), c_p]),
     "dh_scale_apply": (c_i, [ctypes.POINTER(DhJointOpt), c_p, c_i, c_p]),

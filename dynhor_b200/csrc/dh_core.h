@@ -353,6 +353,26 @@ DH_HD uint32_t neg_line_word(const BwdMaps& m, int axis, int d0, int w) {
     return neg_row_word(m.alpha, m.neg_pool, m.is, m.aa, m.wpr, m.wpr_pool, d0, w);
 }
 
+// Guided batch schedule of the backward's items (a function of the item count only, so that the sums of a chunk are
+// added up in the same order whatever warp ran which batch): full 32-item batches while more than a round of them is
+// left, then remaining / (warps * div), never fewer than `min_items`; no crumbs at the end.  starts[0 .. nb] (starts[nb]
+// = n_items); at most max_batches - 1 batches.  Returns nb.
+DH_HD int bwd_guided_schedule(int n_items, int warps, int min_items, int div, int max_batches, uint16_t* starts) {
+    int pos = 0, nb = 0;
+    while (pos < n_items) {
+        const int rem = n_items - pos;
+        int sz = rem / (warps * div);
+        if (sz < min_items) sz = min_items;
+        if (sz > 32) sz = 32;
+        if (rem - sz < min_items / 2) sz = rem < 32 ? rem : 32;
+        if (nb + (rem + 31) / 32 >= max_batches - 1) sz = rem < 32 ? rem : 32;   // (never with <= 2048 items)
+        starts[nb++] = (uint16_t)pos;
+        pos += sz;
+    }
+    starts[nb] = (uint16_t)n_items;
+    return nb;
+}
+
 // One edge of a face seen along one axis: p0 -> p1 is the edge, p2 the opposite vertex; component 0 is the
 // coordinate the scan steps along (d0), component 1 the one it scans (d1).
 struct Span {

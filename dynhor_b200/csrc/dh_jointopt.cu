@@ -1305,19 +1305,8 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
         for (int w = 0; w < kBwdWarps; w++) { s_woff[w] = o; o += s_wcount[w]; }
         s_woff[kBwdWarps] = o;
 #if DH_GUIDED
-        // Guided schedule, a function of the item count only: full batches while there is more than a round of them
-        // left, then ever smaller ones, so that the warps run out of work at nearly the same time.  (With one crossing
-        // per lane a small batch costs no lanes in the loops, only in its set-up and tail.)
-        int pos = 0, nb = 0;
-        while (pos < o) {
-            const int rem = o - pos;
-            int sz = min(32, max(DH_GUIDE_MIN, rem / (kBwdWarps * DH_GUIDE_DIV)));
-            if (rem - sz < DH_GUIDE_MIN / 2) sz = min(rem, 32);                       // no crumbs at the end
-            if (nb + (rem + 31) / 32 >= kMaxBatches - 1) sz = min(rem, 32);          // (never with <= 2048 items)
-            s_bstart[nb++] = (uint16_t)pos;
-            pos += sz;
-        }
-        s_bstart[nb] = (uint16_t)o;
+        // (with one crossing per lane a small batch costs no lanes in the loops, only in its set-up and tail)
+        const int nb = bwd_guided_schedule(o, kBwdWarps, DH_GUIDE_MIN, DH_GUIDE_DIV, kMaxBatches, s_bstart);
         s_nbatches = nb;
 #endif
     }
@@ -2391,6 +2380,21 @@ int dh_sil_backward(const dh_sil* s, const float* verts_cam, const float* grad_r
         t, verts_cam, nullptr, nullptr, nullptr, nullptr, grad_verts, nchunks, 0.0f, 0, nullptr, nullptr);
     DH_LAUNCH_OK("k_backward");
     return DH_OK;
+}
+
+int dh_bwd_schedule(int32_t n_items, int32_t* starts_out, int32_t cap) {
+    DH_REQUIRE(n_items >= 0 && n_items <= 2 * kChunkFaces && starts_out != nullptr && cap >= kMaxBatches + 1,
+               "dh_bwd_schedule: 0 <= n_items <= %d, cap >= %d", 2 * kChunkFaces, kMaxBatches + 1);
+    uint16_t starts[kMaxBatches + 1];
+#if DH_GUIDED
+    const int nb = bwd_guided_schedule(n_items, kBwdWarps, DH_GUIDE_MIN, DH_GUIDE_DIV, kMaxBatches, starts);
+#else
+    int nb = 0;
+    for (int pos = 0; pos < n_items; pos += 32) starts[nb++] = (uint16_t)pos;
+    starts[nb] = (uint16_t)n_items;
+#endif
+    for (int i = 0; i <= nb; i++) starts_out[i] = starts[i];
+    return nb;
 }
 
 int dh_tune_set(int32_t knob, int32_t value) {

@@ -41,6 +41,10 @@ int dh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* tuning / test knobs.  knob 0: contributing pixels per frame up to which the fused backward uses its per-line
  * pixel lists (default 32248; frames above take the bitmap kernel; value < 0 restores the default).  Takes effect
  * for launches and graph captures made after the call. */
+/* The batch schedule the fused backward uses for a chunk of n_items (face, winding) items (host-side copy of the
+ * kernel's own function, for tests): starts_out[0 .. nb] = first item of every batch, starts_out[nb] = n_items;
+ * returns nb (>= 0), or a negative status.  cap: entries of starts_out, at least 97.  No reference counterpart. */
+int dh_bwd_schedule(int32_t n_items, int32_t* starts_out, int32_t cap);
 int dh_tune_set(int32_t knob, int32_t value);
 
 /* ------------------------------------------------------------------------------------------------

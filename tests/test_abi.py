@@ -48,3 +48,23 @@ def test_no_cpu_fallback():
     from dynhor_b200.jointopt import joint_optimize
     with pytest.raises(_lib.DynhorError):
         joint_optimize([], objvertices=None, objfaces=None)
+
+
+def test_backward_batch_schedule_covers_every_item_once():
+    """dh_bwd_schedule = the kernel's own guided batch schedule (dh_core.h bwd_guided_schedule), a function of the item
+    count only: consecutive batches, every item in exactly one of them, never more than 32 items (one per lane),
+    at most 95 batches (one row of partial sums each), non-increasing sizes apart from the tail that absorbs crumbs."""
+    from dynhor_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 128)()
+    for n in list(range(0, 700)) + [1000, 1023, 1024, 1500, 2047, 2048]:
+        nb = lib.dh_bwd_schedule(n, out, 128)
+        assert 0 <= nb <= 95, (n, nb)
+        starts = list(out[:nb + 1])
+        assert starts[0] == 0 if nb else True
+        assert starts[nb] == n
+        sizes = [b - a for a, b in zip(starts, starts[1:])]
+        assert all(1 <= s <= 32 for s in sizes), (n, sizes)
+        assert sum(sizes) == n
+        assert all(a >= b for a, b in zip(sizes[:-2], sizes[1:-1])), (n, sizes)   # shrinking towards the end
+    assert lib.dh_bwd_schedule(-1, out, 128) < 0 and lib.dh_bwd_schedule(10, out, 8) < 0
