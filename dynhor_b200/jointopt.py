@@ -488,7 +488,8 @@ def _stack_frames(frames, key, pick=None, dtype=None):
         out = torch.cat(ts)
     elif t0.is_pinned() and t0.numel() * t0.element_size() >= 65536:
         out = torch.empty((sum(int(t.shape[0]) for t in ts),) + tuple(t0.shape[1:]), dtype=t0.dtype, device="cuda")
-        if all(t.shape == t0.shape and t.is_contiguous() and t.dtype == t0.dtype for t in ts) and t0.shape[0] == 1:
+        if t0.shape[0] == 1 and all(t.shape == t0.shape and t.is_contiguous() and t.dtype == t0.dtype and
+                                    t.is_pinned() for t in ts):
             _upload_rows(out, ts)      # one batched driver call for all the frames
         else:
             row = 0
