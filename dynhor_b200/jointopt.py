@@ -28,7 +28,7 @@ from .geometry import matrix_to_rot6d, rot6d_to_matrix
 from .losses import Losses
 from .renderer import SilhouetteState, shared_faces
 from .sharding import (FrameShard, PeerMailboxes, allgather_equal, allgather_frames, allreduce_sum_, balanced_bounds,
-                       detect_shard, exchange_halo, frame_costs_from_blocks, rescale_costs)
+                       detect_shard, exchange_halo, frame_costs_from_blocks, rescale_costs, wants_probe)
 
 
 class Joint_Optimizer(nn.Module):
@@ -695,9 +695,7 @@ def joint_optimize(object_parameters, objvertices=None, objfaces=None, loss_weig
 
     mark("mesh")
     model, cost = None, None
-    if balance not in ("auto", "probe", "count"):
-        raise ValueError(f"balance must be 'auto', 'probe' or 'count', not {balance!r}")
-    if auto and shard.world > 1 and (balance == "probe" or (balance == "auto" and num_iterations >= 64)):
+    if wants_probe(balance, num_iterations, shard.world) and auto:
         # cost-weighted partition: time the heavy kernels block by block on the equal-count ranges, gather, re-cut
         nblocks = max(1, min(16, (B_total // shard.world) // 32))
         model0 = build(shard, with_corr=False)

@@ -70,6 +70,21 @@ def detect_shard(B_total):
     return FrameShard(0, 1, B_total)
 
 
+PROBE_MIN_ITERATIONS = 64
+
+
+def wants_probe(balance, num_iterations, world):
+    """joint_optimize's partition policy.  The cost probe (two passes of the heavy kernels over the rank's equal-count
+    range + an all-gather) costs about as much as five iterations and makes every iteration about a tenth faster
+    (measured at 8 GPUs, 4096 frames: 3.2 instead of 3.6 ms), so "auto" asks for it from PROBE_MIN_ITERATIONS
+    iterations on; "probe" always, "count" never; a single rank has nothing to cut."""
+    if balance not in ("auto", "probe", "count"):
+        raise ValueError(f"balance must be 'auto', 'probe' or 'count', not {balance!r}")
+    if world <= 1 or balance == "count":
+        return False
+    return balance == "probe" or int(num_iterations) >= PROBE_MIN_ITERATIONS
+
+
 def balanced_bounds(frame_cost, world):
     """Contiguous partition of len(frame_cost) frames into `world` ranges of (nearly) equal total cost.
     Boundary r is the frame at which the running cost crosses r/world of the total (rounded to the nearer frame);

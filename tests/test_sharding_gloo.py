@@ -189,3 +189,17 @@ def test_two_rank_scale_gradient_equals_single_shard():
     g = np.random.default_rng(3).normal(size=37) * 1e-3
     single = E.fx_sum(g)[2]
     assert got[0] == got[1] == single
+
+
+def test_partition_policy():
+    """balance="auto": the cost probe from 64 iterations on (it costs ~5 iterations and buys ~10 % of each); "probe" /
+    "count" force the choice; one rank never probes; anything else is an error (before any work is done)."""
+    import pytest
+    from dynhor_b200.sharding import PROBE_MIN_ITERATIONS, wants_probe
+    assert PROBE_MIN_ITERATIONS == 64
+    assert not wants_probe("auto", 20, 8) and wants_probe("auto", 64, 8) and wants_probe("auto", 200, 2)
+    assert wants_probe("probe", 1, 2) and not wants_probe("count", 10 ** 6, 8)
+    for b in ("auto", "probe", "count"):
+        assert not wants_probe(b, 1000, 1)
+    with pytest.raises(ValueError):
+        wants_probe("cost", 100, 8)
