@@ -1,6 +1,7 @@
 // dh_jointopt.cu -- sm_100a kernels of the joint pose-optimisation hot path and their C-ABI entry points.
 //
-// One optimisation iteration (jointopt.py:144-160) is ten stream-ordered kernels, replayed as one CUDA graph:
+// One optimisation iteration (jointopt.py:144-160) is ten kernels, replayed as one CUDA graph (k_corr as a branch
+// beside k_neg_maps; the first iteration of a call may run as two plain-stream halves, dh_jointopt_run_part):
 //   k_pose_prep    6D rotation -> R (geometry.py:19-25); closed-form smoothness loss + gradient from mesh moments
 //   k_corr         (dh_corr.cu, builder-defined correspondence term; only with correspondences and a positive weight)
 //   k_project      (|s| v) R + T  (camera.py:204-206) and the renderer's projection (camera.py:39-62) -> NDC
@@ -8,12 +9,15 @@
 //   k_raster       one CTA per (frame, strip): 64-bit (depth, face) z-buffer in shared memory, two winding passes
 //                  with tile-z culling in between, then the fused epilogue: face-index map, coverage bitmap, 2x2
 //                  pooling + flip, masked-L2 / IoU integer sums, dL/drend map and its sign bitmaps (losses.py:66-78)
-//   k_neg_maps     per frame: the "wanted but uncovered" pixels as a transposed bitmap, row ranges and per-line lists
-//   k_backward     <lists>: one CTA per (frame, face chunk): coverage bitmap staged in shared memory, per-face
+//   k_neg_maps     per frame: the "wanted but uncovered" pixels as a transposed bitmap, first / last such pixel of
+//                  every row and column, per-line lists, list-overflow flag
+//   k_backward     <lists>: one CTA per (frame, face chunk): coverage bitmap + line ranges staged in shared memory,
+//                  guided batches of items, one edge crossing per lane over the batch's span list, per-face
 //                  edge-scan pseudo-gradient over the pixel lists, projection + rigid-transform backward, CTA
 //                  reduction to 13 numbers;  <bitmaps>: the same on bitmap words, for frames whose lists overflowed
-//                  and for the composable dh_sil_backward
-//   k_pose_update  per frame: + smoothness gradient, Gram-Schmidt backward, two-group Adam (jointopt.py:135-141)
+//                  (a small grid that normally ends after reading the flags) and for the composable dh_sil_backward
+//   k_pose_update  a warp per frame: partial sums + smoothness gradient, Gram-Schmidt backward, two-group Adam
+//                  (jointopt.py:135-141)
 //   k_finalize     per-iteration loss / IoU sums -> history row, step counter, optional scale update
 // Compiled with --fmad=false: see dh_core.h for the fp32 contract.
 #include <stdlib.h>
