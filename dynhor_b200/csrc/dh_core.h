@@ -43,6 +43,13 @@ DH_HD int ctz32(uint32_t v) {
     return __builtin_ctz(v);
 #endif
 }
+DH_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 DH_HD bool finite3(float a, float b, float c) {
     return (fabsf(a) <= 3.0e38f) && (fabsf(b) <= 3.0e38f) && (fabsf(c) <= 3.0e38f);
 }
@@ -352,6 +359,27 @@ DH_HD uint32_t neg_line_word(const BwdMaps& m, int axis, int d0, int w) {
     if (m.neg != nullptr) return m.neg[d0 * m.wpr + w];
     return neg_row_word(m.alpha, m.neg_pool, m.is, m.aa, m.wpr, m.wpr_pool, d0, w);
 }
+
+// ---- span list of a backward batch: the non-empty (edge, axis) spans of the batch's <= 32 faces, compacted in (lane,
+// span) order; a span's crossings (scan lines d0_from ... d0_to) are numbered start ... start + length - 1, and the
+// batch's crossings 0 ... T-1 are handed to the lanes 32 at a time.
+//   info    = lane | (edge * 2 + axis) << 5 | (direction > 0) << 8 | (d0_from - start + 2^17) << 9
+//   start16 = start mod 2^16 (T can pass 2^16 -- 32 faces across a 512-pixel raster: 65 568, a triangle's spans add
+//             up to ~2 (width + height) scan lines; only differences below 2^14 are ever formed)
+DH_HD uint32_t span_info(int lane, int k, int d0_from, bool dpos, uint32_t start) {
+    return ((uint32_t)lane | ((uint32_t)k << 5) | (dpos ? (1u << 8) : 0u) | ((uint32_t)(d0_from + (1 << 17)) << 9)) -
+           (start << 9);
+}
+DH_HD int span_info_d0(uint32_t info, int idx) { return idx + (int)(info >> 9) - (1 << 17); }
+// Step `base` (crossings base ... base + 31): every span after s0 -- s0 starts at or before `base` -- that starts inside
+// the step marks the bit of its first crossing; at most 32 spans can (each has a crossing), so the 32 lanes looking at
+// spans s0 + 1 ... s0 + 32 see them all.  With M = OR of the marks, lane l works on span s0 + popc(M & bits 0..l), and
+// the next step's s0 is s0 + popc(M).
+DH_HD uint32_t span_mark(uint16_t start16, int base) {
+    const uint32_t rel = (uint32_t)(uint16_t)(start16 - (uint16_t)base);
+    return rel < 32u ? (1u << rel) : 0u;
+}
+DH_HD int span_of_lane(int s0, uint32_t M, int lane) { return s0 + popc32(M & (0xFFFFFFFFu >> (31 - lane))); }
 
 // Guided batch schedule of the backward's items (a function of the item count only, so that the sums of a chunk are
 // added up in the same order whatever warp ran which batch): full 32-item batches while more than a round of them is

@@ -1443,8 +1443,7 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
                     const int l = t.d0_to - t.d0_from + 1;
                     len[k] = l > 0 ? (uint32_t)l : 0u;
                     slp[k] = t.slope;
-                    inf[k] = (uint32_t)lane | ((uint32_t)k << 5) | ((0 < t.direction) ? (1u << 8) : 0u) |
-                             ((uint32_t)(t.d0_from + (1 << 17)) << 9);
+                    inf[k] = span_info(lane, k, t.d0_from, 0 < t.direction, 0u);   // (its start is subtracted below)
                     pack += len[k] + (len[k] ? (1u << 20) : 0u);   // crossings (< 2^17 per batch) | spans << 20
                 }
             }
@@ -1533,18 +1532,15 @@ bwd_frame(const dh_sil& s, const float* __restrict__ verts_src, const float* __r
                     // spans that start inside this step mark their first crossing; a lane's span = s0 + marks up to itself
                     uint32_t bit = 0;
                     const int j = s0 + 1 + lane;
-                    if (j < NS) {
-                        const uint32_t rel = (uint32_t)(uint16_t)(SP.start16[j] - (uint16_t)base);
-                        if (rel < 32u) bit = 1u << rel;
-                    }
+                    if (j < NS) bit = span_mark(SP.start16[j], base);
                     const uint32_t M = __reduce_or_sync(0xffffffffu, bit);
-                    const int span = s0 + __popc(M & (0xFFFFFFFFu >> (31 - lane)));
+                    const int span = span_of_lane(s0, M, lane);
                     s0 += __popc(M);
                     const int idx = base + lane;
                     if (idx < T) {
                         const uint32_t info = SP.info[span];
                         const int slot = (int)(info & 31u), k = (int)((info >> 5) & 7u), axis = k & 1, edge = k >> 1;
-                        const int d0_ = idx + (int)(info >> 9) - (1 << 17);
+                        const int d0_ = span_info_d0(info, idx);
                         const bool dpos = (info >> 8) & 1u;
                         const float p00 = Pb[(axis * 3 + edge) * 32 + slot], p01 = Pb[((1 - axis) * 3 + edge) * 32 + slot];
                         float c = SP.slope[span] * ((float)d0_ - p00);   // span_crossing (dh_core.h), same operation order

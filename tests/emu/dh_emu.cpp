@@ -444,4 +444,56 @@ void emu_fx_sum(const double* x, int n, unsigned long long* out2, double* val) {
     *val = fx_to_double(t);
 }
 
+
+// The backward's "one crossing per lane" enumeration of a batch (k_backward<lists>, dh_jointopt.cu), emulated for a
+// warp of 32 lanes with the SAME helpers (span_setup, span_info, span_mark, span_of_lane, span_info_d0): the span list
+// is built in (lane, span) order from prefix sums, then the crossings 0 ... T-1 are handed out 32 per step with the
+// mark / popcount trick.  px, py: [32][3] pixel coordinates of the faces (first n_have lanes valid).
+// flat[3 i ..] = (lane slot, edge * 2 + axis, scan line) of crossing i as the kernel's lanes see it;
+// ref[3 i ..]  = the same from the plain nested loops (lane, span, scan line).  Returns T (<= cap), or -1.
+int emu_span_list(const float* px, const float* py, int n_have, int is, int32_t* flat, int32_t* ref, int cap) {
+    std::vector<uint16_t> start16;
+    std::vector<uint32_t> info;
+    uint32_t tb = 0;
+    int nref = 0;
+    for (int lane = 0; lane < 32 && lane < n_have; lane++) {
+        for (int k = 0; k < 6; k++) {
+            Span t;
+            span_setup(px + 3 * lane, py + 3 * lane, k >> 1, k & 1, is, t);
+            const int l = t.d0_to - t.d0_from + 1;
+            if (l <= 0) continue;
+            start16.push_back((uint16_t)tb);
+            info.push_back(span_info(lane, k, t.d0_from, 0 < t.direction, tb));
+            for (int d0 = t.d0_from; d0 <= t.d0_to; d0++) {
+                if (nref >= cap) return -1;
+                ref[3 * nref + 0] = lane; ref[3 * nref + 1] = k; ref[3 * nref + 2] = d0;
+                nref++;
+            }
+            tb += (uint32_t)l;
+        }
+    }
+    const int T = (int)tb, NS = (int)info.size();
+    if (T != nref || NS > 192) return -1;
+    int s0 = 0;
+    for (int base = 0; base < T; base += 32) {
+        uint32_t M = 0;
+        for (int lane = 0; lane < 32; lane++) {
+            const int j = s0 + 1 + lane;
+            if (j < NS) M |= span_mark(start16[j], base);
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            const int idx = base + lane;
+            if (idx >= T) break;
+            const int span = span_of_lane(s0, M, lane);
+            if (span < 0 || span >= NS) return -1;
+            const uint32_t inf = info[span];
+            flat[3 * idx + 0] = (int)(inf & 31u);
+            flat[3 * idx + 1] = (int)((inf >> 5) & 7u);
+            flat[3 * idx + 2] = span_info_d0(inf, idx);
+        }
+        s0 += popc32(M);
+    }
+    return T;
+}
+
 }  // extern "C"

@@ -177,3 +177,47 @@ def test_emu_real_shoe_mesh_vs_oracle():
     assert abs(out["iou_object"] - ref["iou_object"]) <= 1e-6
     assert rel_err(out["grad_rot6d"], grads["rot6d"]) < 1e-3
     assert rel_err(out["grad_trans"], grads["trans"]) < 1e-3
+
+
+@pytest.mark.parametrize("case", ["mesh_sized", "mixed", "few_lanes", "giant", "degenerate"])
+def test_emu_span_list_hands_out_every_crossing_once(case):
+    """The backward's one-crossing-per-lane enumeration (k_backward<lists>: compacted span list + mark / popcount step,
+    helpers in dh_core.h shared with the kernel) visits exactly the crossings of the plain nested loops, in the same
+    order -- also when a batch has more than 2^16 crossings (32 faces across the whole 512-pixel raster: the span
+    starts are kept modulo 2^16) and when lanes or spans are empty."""
+    import ctypes
+    rng = np.random.default_rng({"mesh_sized": 1, "mixed": 2, "few_lanes": 3, "giant": 4, "degenerate": 5}[case])
+    is_ = 512
+    for trial in range(40 if case != "giant" else 4):
+        n_have = 32
+        c = rng.uniform(-20, is_ + 20, (32, 1, 2))
+        if case == "mesh_sized":
+            tri = c + rng.uniform(-4, 4, (32, 3, 2))
+        elif case == "mixed":
+            tri = c + rng.uniform(-1, 1, (32, 3, 2)) * rng.choice([0.3, 5.0, 60.0, 700.0], (32, 1, 1))
+        elif case == "few_lanes":
+            n_have = int(rng.integers(0, 6))
+            tri = c + rng.uniform(-30, 30, (32, 3, 2))
+        elif case == "giant":
+            # a triangle's spans add up to at most ~2 x (width + height) of the raster = 2049 scan lines: 32 such faces
+            # give the largest batch there can be, 65 568 crossings -- just past 2^16
+            big = np.array([[806.152244, 575.274903], [448.0696, -0.0979789455], [-87.0836405, -200.319568]])
+            tri = np.stack([big if trial == 0 else big + rng.uniform(-0.01, 0.01, (3, 2)) for _ in range(32)])
+        else:                      # axis-aligned and zero-length edges, vertices on pixel centres
+            tri = np.round(c + rng.uniform(-6, 6, (32, 3, 2)))
+            tri[::3, 1] = tri[::3, 0]
+        px = np.ascontiguousarray(tri[:, :, 0], np.float32)
+        py = np.ascontiguousarray(tri[:, :, 1], np.float32)
+        cap = 32 * 6 * is_
+        flat = np.full((cap, 3), -7, np.int32)
+        ref = np.full((cap, 3), -9, np.int32)
+        fn = E.lib().emu_span_list
+        fn.restype = ctypes.c_int
+        T = fn(E._p(px), E._p(py), n_have, is_, E._p(flat), E._p(ref), cap)
+        assert T >= 0
+        if case == "giant" and trial == 0:
+            assert T == 32 * 2049 > 1 << 16
+        if case == "few_lanes" and n_have == 0:
+            assert T == 0
+        assert np.array_equal(flat[:T], ref[:T])
+        assert (ref[:T, 2] >= 0).all() and (ref[:T, 2] < is_).all()
